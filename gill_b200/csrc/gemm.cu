@@ -1,0 +1,230 @@
+// Host side of the tcgen05 GEMM: tensor-map construction, tile-shape selection, launch, C ABI.
+#include "../../include/gillb200.h"
+#include "gemm_sm100.cuh"
+#include "host_common.h"
+
+#include <cstring>
+#include <mutex>
+
+namespace gb {
+
+static thread_local char g_err[512] = "";
+char* err_buf() { return g_err; }
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool is_bf16) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_err(-EIO, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_err(-EINVAL, "tensor base %p not 16-byte aligned", base);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) {
+      gstr[i - 1] = strides_bytes[i - 1];
+      if (gstr[i - 1] % 16 != 0) return set_err(-EINVAL, "tensor stride %llu B not a multiple of 16", (unsigned long long)gstr[i - 1]);
+    }
+  }
+  CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(-EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+  using C = GemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int tiles = num_m * num_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Pick the N tile that minimises (waves x per-tile cost), counting padded columns as wasted work.
+static int pick_block_n(int M, int N) {
+  const int cands[5] = {256, 160, 128, 64, 32};
+  const int sms = num_sms();
+  const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
+  double best = 1e30;
+  int best_bn = 128;
+  for (int i = 0; i < 5; ++i) {
+    const int bn = cands[i];
+    const int num_n = (N + bn - 1) / bn;
+    const long long tiles = 1LL * num_m * num_n;
+    const long long waves = (tiles + sms - 1) / sms;
+    // per-tile cost ~ MMA cycles (prop. to bn) + fixed per-tile overhead (epilogue/pipeline fill)
+    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    if (cost < best * 0.999) {
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int gillb200_version(void) { return GILLB200_VERSION; }
+extern "C" const char* gillb200_last_error(void) { return gb::err_buf(); }
+extern "C" int gillb200_num_sms(void) { return gb::num_sms(); }
+
+extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(a != nullptr, "null args");
+  GB_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "bad GEMM shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  GB_CHECK_ARG(a->in_dtype == DT_BF16 || a->in_dtype == DT_F16, "operand dtype must be bf16 or fp16");
+  GB_CHECK_ARG(a->out != nullptr && a->a != nullptr && a->b != nullptr, "null operand");
+  GB_CHECK_ARG(a->out_dtype >= 0 && a->out_dtype <= 2, "bad out dtype");
+  const bool bf16 = a->in_dtype == DT_BF16;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a->M;
+  p.N = a->N;
+  int kb_main;
+  if (a->conv3x3) {
+    GB_CHECK_ARG(a->conv_C % BLOCK_K == 0, "conv3x3 needs C %% 64 == 0 (C=%d)", a->conv_C);
+    GB_CHECK_ARG(a->M == a->conv_B * a->conv_H * a->conv_W, "conv3x3: M != B*H*W");
+    GB_CHECK_ARG(a->K == 9 * a->conv_C, "conv3x3: K != 9*C");
+    const int W = a->conv_W, H = a->conv_H;
+    int bw, bh, bb;
+    if (W >= 128) {
+      GB_CHECK_ARG(W % 128 == 0, "conv3x3: W=%d must be a multiple of 128 when >= 128", W);
+      bw = 128, bh = 1, bb = 1;
+    } else {
+      GB_CHECK_ARG(128 % W == 0, "conv3x3: W=%d must divide 128", W);
+      bw = W;
+      bh = 128 / W;
+      if (bh > H) bh = H;
+      GB_CHECK_ARG(H % bh == 0, "conv3x3: H=%d not a multiple of the box height %d", H, bh);
+      bb = 128 / (bw * bh);
+    }
+    const uint64_t dims[4] = {(uint64_t)a->conv_C, (uint64_t)W, (uint64_t)H, (uint64_t)a->conv_B};
+    const uint64_t strides[3] = {(uint64_t)a->conv_C * 2, (uint64_t)W * a->conv_C * 2, (uint64_t)H * W * a->conv_C * 2};
+    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    int r = encode_tmap_16bit(&p.tma_a, a->a, 4, dims, strides, box, bf16);
+    if (r) return r;
+    p.a_mode = A_CONV3X3;
+    p.conv_cblocks = a->conv_C / BLOCK_K;
+    p.conv_W = W;
+    p.conv_H = H;
+    kb_main = 9 * p.conv_cblocks;
+  } else {
+    GB_CHECK_ARG(a->lda % 8 == 0, "lda=%lld must be a multiple of 8 elements", a->lda);
+    const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
+    const uint64_t strides[1] = {(uint64_t)a->lda * 2};
+    const uint32_t box[2] = {BLOCK_K, BLOCK_M};
+    int r = encode_tmap_16bit(&p.tma_a, a->a, 2, dims, strides, box, bf16);
+    if (r) return r;
+    p.a_mode = A_PLAIN;
+    kb_main = (a->K + BLOCK_K - 1) / BLOCK_K;
+  }
+  p.kb_split = kb_main;
+  p.num_k_blocks = kb_main;
+  p.b_kb_wrap = 1 << 30;
+  int kb_total_cols = a->K;
+  if (a->a2_mode != 0) {
+    GB_CHECK_ARG(a->a2 != nullptr && a->k2 > 0, "a2_mode set without a2/k2");
+    GB_CHECK_ARG(a->lda2 % 8 == 0, "lda2 must be a multiple of 8 elements");
+    GB_CHECK_ARG(a->K % BLOCK_K == 0, "a second A source needs K %% 64 == 0");
+    const uint64_t dims[2] = {(uint64_t)a->k2, (uint64_t)a->M};
+    const uint64_t strides[1] = {(uint64_t)a->lda2 * 2};
+    const uint32_t box[2] = {BLOCK_K, BLOCK_M};
+    int r = encode_tmap_16bit(&p.tma_a2, a->a2, 2, dims, strides, box, bf16);
+    if (r) return r;
+    p.num_k_blocks = kb_main + (a->k2 + BLOCK_K - 1) / BLOCK_K;
+    if (a->a2_mode == 2) {
+      GB_CHECK_ARG(a->k2 == a->K && !a->conv3x3, "split-precision A needs k2 == K and a plain A");
+      p.b_kb_wrap = kb_main;
+    } else {
+      kb_total_cols = a->K + a->k2;
+    }
+  }
+  {
+    GB_CHECK_ARG(a->ldb % 8 == 0, "ldb=%lld must be a multiple of 8 elements", a->ldb);
+    GB_CHECK_ARG(a->ldb >= kb_total_cols, "ldb=%lld smaller than K=%d", a->ldb, kb_total_cols);
+  }
+
+  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N);
+  if (a->act == ACT_GEGLU) GB_CHECK_ARG(a->N % 2 == 0, "GEGLU needs even N");
+  {
+    const uint64_t dims[2] = {(uint64_t)kb_total_cols, (uint64_t)a->N};
+    const uint64_t strides[1] = {(uint64_t)a->ldb * 2};
+    const uint32_t box[2] = {BLOCK_K, (uint32_t)bn};
+    int r = encode_tmap_16bit(&p.tma_b, a->b, 2, dims, strides, box, bf16);
+    if (r) return r;
+  }
+  p.out = a->out;
+  p.out_lo = a->out_lo;
+  p.bias = a->bias;
+  p.rowbias = a->rowbias;
+  p.residual = a->residual;
+  p.ldo = a->ldo;
+  p.ldr = a->ldr;
+  p.ld_rowbias = a->ld_rowbias;
+  p.out_dtype = a->out_dtype;
+  p.res_dtype = a->res_dtype;
+  p.bias_along_m = a->bias_along_m;
+  p.rows_per_group = a->rows_per_group > 0 ? a->rows_per_group : 1;
+  p.act = a->act;
+  p.in_dtype = a->in_dtype;
+  p.alpha = a->alpha;
+  if (a->out_lo) GB_CHECK_ARG(a->out_dtype == DT_BF16, "out_lo requires a bf16 primary output");
+
+  switch (bn) {
+    case 32: return launch_gemm<32>(p, stream);
+    case 64: return launch_gemm<64>(p, stream);
+    case 128: return launch_gemm<128>(p, stream);
+    case 160: return launch_gemm<160>(p, stream);
+    case 256: return launch_gemm<256>(p, stream);
+    default: return set_err(-EINVAL, "unsupported block_n %d", bn);
+  }
+}

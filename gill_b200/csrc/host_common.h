@@ -1,0 +1,35 @@
+// Host-side helpers shared by every translation unit of libgillb200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cerrno>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+namespace gb {
+
+// thread-local error string returned by gillb200_last_error()
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+
+#define GB_CHECK_ARG(cond, ...)                       \
+  do {                                                \
+    if (!(cond)) return gb::set_err(-EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define GB_CUDA(call)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) return gb::set_err(-EIO, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency).
+// dims/strides innermost-first; strides in bytes for dims 1..rank-1. 16-bit elements, SWIZZLE_128B.
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool is_bf16);
+
+int num_sms();
+
+}  // namespace gb

@@ -1,0 +1,85 @@
+/* libgillb200.so -- C ABI of the B200-native (sm_100a) GILL image-emission hot path.
+ *
+ * The reference (kohjingyu/gill @ 4600b71) is pure Python and has no FFI of its own; its seams are Python
+ * attribute calls into torch / transformers / diffusers. Each entry point below names the reference call site
+ * whose arithmetic it replaces. The Python host layer (gill_b200/*.py) binds these with ctypes and mirrors the
+ * reference's own class/function surface on top.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative errno-style code on failure (-EINVAL bad shape/alignment,
+ *     -EIO CUDA error); gillb200_last_error() returns a thread-local description of the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller, 16-byte aligned, row-major / innermost-contiguous.
+ *   - `stream` is a cudaStream_t passed as void*. No function synchronises the stream or allocates device memory,
+ *     so every call can be captured into a CUDA graph.
+ *   - dtype codes: 0 = bf16, 1 = fp16, 2 = fp32.
+ */
+#ifndef GILLB200_H_
+#define GILLB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GILLB200_VERSION 100
+
+enum { GILLB200_BF16 = 0, GILLB200_F16 = 1, GILLB200_F32 = 2 };
+enum { GILLB200_ACT_NONE = 0, GILLB200_ACT_RELU = 1, GILLB200_ACT_GELU = 2, GILLB200_ACT_SILU = 3, GILLB200_ACT_GEGLU = 4 };
+
+int gillb200_version(void);
+const char* gillb200_last_error(void);
+int gillb200_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM / implicit-GEMM convolution (tcgen05.mma + TMEM accumulators, TMA-fed).
+ *
+ *   out[M,N] = act( alpha * (A[M,K] . B[N,K]^T) + bias + rowbias ) + residual
+ *
+ * Replaces every nn.Linear / nn.Conv2d the hot path reaches through third-party modules:
+ *   gill/layers.py:42-44 (TextFcLayer fc / tfm linears / model), gill/models.py:465 (OPTForCausalLM linears),
+ *   gill/models.py:730 -> gill/custom_sd.py:633-638 (UNet convs / linears), custom_sd.py:388 (VAE decoder).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gillb200_gemm_args {
+  /* A operand: [M, K] with row stride lda (elements). With conv3x3 != 0, `a` is an NHWC activation
+   * [conv_B, conv_H, conv_W, conv_C] and the GEMM is the 3x3/stride-1/pad-1 convolution: M = B*H*W, K = 9*C,
+   * B operand laid out [N, 9*C] with k = (ky*3+kx)*C + c. */
+  const void* a;
+  long long lda;
+  /* optional second A source [M, k2], row stride lda2:
+   *   a2_mode 1: K-concatenation -- out = [A | A2] . B^T, B has K + k2 columns
+   *   a2_mode 2: split precision  -- out = (A + A2) . B^T, A2 is the bf16 residue of a higher-precision A; k2 == K */
+  const void* a2;
+  long long lda2;
+  int k2;
+  int a2_mode;
+  const void* b; /* [N, Kb] row stride ldb */
+  long long ldb;
+  int M, N, K;
+  int in_dtype; /* operand dtype of a, a2, b: bf16 or fp16 */
+  int conv3x3;
+  int conv_B, conv_H, conv_W, conv_C;
+  /* epilogue */
+  void* out;
+  long long ldo;
+  int out_dtype;
+  void* out_lo;      /* optional: bf16 residue of the (bf16) output, same layout as out */
+  const float* bias; /* [N], or [M] when bias_along_m */
+  int bias_along_m;
+  const float* rowbias; /* [M / rows_per_group, ld_rowbias] added per row group (per-sample time embedding) */
+  long long ld_rowbias;
+  int rows_per_group;
+  const void* residual; /* [M, N_out] row stride ldr */
+  long long ldr;
+  int res_dtype;
+  int act;   /* GEGLU: B rows interleaved (value, gate) pairs; N_out = N/2 */
+  float alpha;
+  int block_n; /* 0 = auto; else one of 32, 64, 128, 160, 256 */
+} gillb200_gemm_args;
+
+int gillb200_gemm(const gillb200_gemm_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GILLB200_H_ */
