@@ -84,3 +84,18 @@ def exported_symbols(header_path=None):
     header_path = header_path or os.path.join(os.path.dirname(_HERE), "include", "gillb200.h")
     txt = open(header_path).read()
     return sorted(set(re.findall(r"\b(gillb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+class AttnArgs(ctypes.Structure):
+    """Mirror of `gillb200_attn_args` (include/gillb200.h)."""
+
+    _fields_ = [
+        ("q", _c_void_p), ("k", _c_void_p), ("v", _c_void_p), ("out", _c_void_p),
+        ("ldq", _c_ll), ("ldk", _c_ll), ("ldv", _c_ll), ("ldo", _c_ll),
+        ("q_bstride", _c_ll), ("k_bstride", _c_ll), ("v_bstride", _c_ll), ("o_bstride", _c_ll),
+        ("kv_lens", _c_void_p),
+        ("B", _c_int), ("H", _c_int), ("Lq", _c_int), ("Lk", _c_int), ("hd_pad", _c_int),
+        ("causal", _c_int), ("causal_offset", _c_int),
+        ("dtype", _c_int),
+        ("scale", _c_float),
+    ]

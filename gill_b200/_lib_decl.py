@@ -5,9 +5,14 @@ vp, ci, cll, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_flo
 
 
 def declare(L):
-    def d(name, *argtypes):
+    from ._lib import AttnArgs
+
+    def d(name, *argtypes, restype=ci):
         fn = getattr(L, name)
         fn.argtypes = list(argtypes)
-        fn.restype = ci
+        fn.restype = restype
 
-    return d
+    d("gillb200_topk_workspace_bytes", ci, cll, restype=cll)
+    d("gillb200_topk_scores", vp, cll, ci, cll, vp, ci, cll, ci, cll, vp, ci, vp, vp, vp, vp)
+    d("gillb200_topk_merge", vp, vp, ci, ci, ci, ci, vp, vp, vp)
+    d("gillb200_attention", ctypes.POINTER(AttnArgs), vp)

@@ -1,0 +1,372 @@
+// Fused multi-head attention (flash style) on tcgen05 for sm_100a.
+//
+// Replaces the bmm + softmax + bmm of: diffusers Attention/AttnProcessor inside the SD-1.5 UNet (self-attention over
+// 4096/1024/256/64 latent tokens and cross-attention over the 77 GILLMapper tokens; gill/models.py:730 ->
+// gill/custom_sd.py:633-638) and OPTAttention (causal, gill/models.py:465).
+//
+// One CTA per (128-query tile, head, batch). Heads are stored padded to HD_PAD (a multiple of 64 columns, zero filled
+// by the producing projection) so that every TMA box is a clean 128-byte swizzled row.
+//   warp 0 lane 0 : TMA producer (Q once; K/V tiles double buffered)
+//   warp 1 lane 0 : MMA issuer    S_j = Q K_j^T  -> TMEM (double buffered);   O += P_j V_j -> TMEM
+//   warp 2        : TMEM allocator
+//   warps 4..7    : softmax. TMEM lane == query row, so each thread owns one row: no cross-thread reductions.
+//                   Online softmax with lazy rescaling (O is only rescaled when the running max grows by > 2^8),
+//                   P written to smem in the K-major SWIZZLE_128B layout the P.V MMA reads.
+// V tiles are consumed directly as an MN-major B operand (no transpose pass).
+#include "../../include/gillb200.h"
+#include "gemm_sm100.cuh"
+#include "host_common.h"
+
+#include <cstring>
+
+namespace gb {
+
+struct alignas(64) AttnParams {
+  CUtensorMap tma_q, tma_k, tma_v;  // 3D {cols, L, B}, box {64, 128 | BLOCK_KV, 1}
+  void* out;
+  long long ldo, o_bstride;
+  const int* kv_lens;
+  int B, H, Lq, Lk;
+  int causal, causal_offset;  // key j visible to query i iff j <= i + causal_offset
+  int out_dtype;
+  int in_dtype;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+template <int HD_PAD, int BLOCK_KV>
+struct AttnCfg {
+  static constexpr int KCH = HD_PAD / 64;           // 64-column chunks per head
+  static constexpr int Q_BYTES = 128 * HD_PAD * 2;  // chunk-major: KCH x [128 rows x 128 B]
+  static constexpr int KV_BYTES = BLOCK_KV * HD_PAD * 2;
+  static constexpr int P_BYTES = 128 * BLOCK_KV * 2;  // (BLOCK_KV/64) x [128 rows x 128 B]
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_S0 = 0;            // S buffers at columns [0, BLOCK_KV) and [BLOCK_KV, 2*BLOCK_KV)
+  static constexpr int TMEM_O = 2 * BLOCK_KV;  // O accumulator
+  static constexpr int TMEM_COLS = (2 * BLOCK_KV + HD_PAD) <= 256 ? 256 : 512;
+  static_assert(HD_PAD % 64 == 0 && HD_PAD <= 192, "head pad");
+  static_assert(BLOCK_KV == 64 || BLOCK_KV == 128, "kv tile");
+  static_assert(SMEM_BYTES <= SMEM_BUDGET, "smem");
+};
+
+struct AttnBars {
+  uint64_t q_full;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
+  uint64_t s_full[2], s_empty[2];
+  uint64_t p_full, p_empty;
+  uint64_t o_done;
+  uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD_PAD, int BLOCK_KV>
+__global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+  using C = AttnCfg<HD_PAD, BLOCK_KV>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  AttnBars* bars = reinterpret_cast<AttnBars*>(smem + C::OFF_BAR);
+  const int warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * 128;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int kv_len = p.kv_lens ? p.kv_lens[b] : p.Lk;
+  int n_tiles = (kv_len + BLOCK_KV - 1) / BLOCK_KV;
+  if (p.causal) {
+    const int last_visible = min(kv_len - 1, q0 + 127 + p.causal_offset);
+    n_tiles = min(n_tiles, last_visible / BLOCK_KV + 1);
+    if (n_tiles < 1) n_tiles = 1;
+  }
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tma_q);
+    tma_prefetch_desc(&p.tma_k);
+    tma_prefetch_desc(&p.tma_v);
+    mbar_init(&bars->q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->k_full[i], 1);
+      mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->v_full[i], 1);
+      mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->s_full[i], 1);
+      mbar_init(&bars->s_empty[i], 4);
+    }
+    mbar_init(&bars->p_full, 4);
+    mbar_init(&bars->p_empty, 1);
+    mbar_init(&bars->o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(&bars->tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+  const int col0 = head * HD_PAD;
+
+  if (warp == 0) {
+    if (lane_id() == 0) {
+      // ---------------- TMA producer
+      mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < C::KCH; ++c)
+        tma_load_3d(smem + C::OFF_Q + c * (128 * 128), &p.tma_q, &bars->q_full, col0 + c * 64, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bars->k_full[s], C::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_3d(smem + C::OFF_K + s * C::KV_BYTES + c * (BLOCK_KV * 128), &p.tma_k, &bars->k_full[s],
+                      col0 + c * 64, j * BLOCK_KV, b);
+        mbar_wait(&bars->v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&bars->v_full[s], C::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_3d(smem + C::OFF_V + s * C::KV_BYTES + c * (BLOCK_KV * 128), &p.tma_v, &bars->v_full[s],
+                      col0 + c * 64, j * BLOCK_KV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane_id() == 0) {
+      // ---------------- MMA issuer
+      const bool bf16 = p.in_dtype == DT_BF16;
+      const uint32_t idesc_s = make_idesc_f16(128, BLOCK_KV, bf16, false);
+      const uint32_t idesc_o = make_idesc_f16(128, HD_PAD, bf16, true);  // B = V, MN-major
+      const uint32_t sq = smem_u32(smem + C::OFF_Q);
+      const uint32_t sp = smem_u32(smem + C::OFF_P);
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->k_full[s], ph);
+        mbar_wait(&bars->s_empty[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + C::OFF_K + s * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < HD_PAD / 16; ++k) {
+          const int c = k >> 2, kk = k & 3;
+          const uint64_t da = make_smem_desc_sw128(sq + c * (128 * 128) + kk * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sk + c * (BLOCK_KV * 128) + kk * 32, 16, 1024);
+          umma_f16(tmem_base + C::TMEM_S0 + s * BLOCK_KV, da, db, idesc_s, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&bars->s_full[s]);
+        umma_commit(&bars->k_empty[s]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&bars->v_full[s], ph);
+        mbar_wait(&bars->p_full, j & 1);
+        tc_fence_after();
+        const uint32_t sv = smem_u32(smem + C::OFF_V + s * C::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < BLOCK_KV / 16; ++k) {
+          // A = P: K-major, 64-kv chunks of [128 x 128 B]; B = V: MN-major, rows = kv, LBO = 64-column chunk stride
+          const uint64_t da = make_smem_desc_sw128(sp + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sv + k * (16 * 128), BLOCK_KV * 128, 1024);
+          umma_f16(tmem_base + C::TMEM_O, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&bars->v_empty[s]);
+        umma_commit(&bars->p_empty);
+        if (j == n_tiles - 1) umma_commit(&bars->o_done);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- softmax / epilogue: thread <-> query row
+    const int ewarp = warp & 3;
+    const int r = ewarp * 32 + lane_id();
+    const int qrow = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(ewarp * 32) << 16;
+    const bool bf16 = p.in_dtype == DT_BF16;
+    uint8_t* sp = smem + C::OFF_P;
+    float m_used = -INFINITY, l = 0.f;
+    const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&bars->s_full[s], ph);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + C::TMEM_S0 + s * BLOCK_KV + lane_off;
+      const int kv0 = j * BLOCK_KV;
+      const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_KV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ts + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      mx *= p.scale_log2;
+      // lazy rescale decision (warp-uniform because tcgen05.ld/st are .sync.aligned)
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mx == -INFINITY ? 0.f : mx;
+      } else if (mx > m_used + 8.f) {
+        alpha = fast_exp2(m_used - mx);
+        m_used = mx;
+        need = true;
+      }
+      // P buffer free and O quiescent once P.V of tile j-1 has retired
+      if (j > 0) {
+        mbar_wait(&bars->p_empty, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        l *= alpha;
+        const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+#pragma unroll 1
+        for (int c = 0; c < HD_PAD; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(to + c, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32b_x16(to + c, v);
+        }
+        tmem_wait_st();
+      }
+      // pass 2: p = exp2(s*scale - m), row sum, P -> smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7))
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_KV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ts + c, v);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c + i <= lim) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used) : 0.f;
+          float p1 = (c + i + 1 <= lim) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used) : 0.f;
+          // accumulate the row sum from the ROUNDED probabilities so that numerator and denominator agree
+          uint32_t u = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          const float2 f = bf16 ? unpack_bf16x2(u) : unpack_f16x2(u);
+          l += f.x + f.y;
+          pk[i >> 1] = u;
+        }
+        uint8_t* chunk = sp + (c >> 6) * (128 * 128) + r * 128;
+        const int u0 = (c & 63) >> 3;  // first 16-B unit of this 32-column group within the 64-column chunk
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int phys = (u0 + u) ^ (r & 7);
+          *reinterpret_cast<uint4*>(chunk + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) {
+        mbar_arrive(&bars->s_empty[s]);
+        mbar_arrive(&bars->p_full);
+      }
+    }
+    // epilogue: O / l
+    mbar_wait(&bars->o_done, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
+                     static_cast<long long>(qrow) * p.ldo + col0;
+#pragma unroll 1
+    for (int c = 0; c < HD_PAD; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(to + c, v);
+      tmem_wait_ld();
+      if (qrow < p.Lq) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+        store16(orow + c, f, 16, p.out_dtype);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int HD_PAD, int BLOCK_KV>
+static int launch_attn(const AttnParams& p, cudaStream_t stream) {
+  using C = AttnCfg<HD_PAD, BLOCK_KV>;
+  static bool configured = false;
+  if (!configured) {
+    GB_CUDA(cudaFuncSetAttribute(attn_kernel<HD_PAD, BLOCK_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((p.Lq + 127) / 128, p.H, p.B);
+  attn_kernel<HD_PAD, BLOCK_KV><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(a && a->q && a->k && a->v && a->out, "null pointer");
+  GB_CHECK_ARG(a->hd_pad == 64 || a->hd_pad == 128 || a->hd_pad == 192, "hd_pad must be 64, 128 or 192 (got %d)",
+               a->hd_pad);
+  GB_CHECK_ARG(a->dtype == DT_BF16 || a->dtype == DT_F16, "attention operands must be bf16 or fp16");
+  GB_CHECK_ARG(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "bad attention shape");
+  GB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "row strides %% 8");
+  GB_CHECK_ARG(a->q_bstride % 8 == 0 && a->k_bstride % 8 == 0 && a->v_bstride % 8 == 0, "batch strides %% 8");
+  const bool bf16 = a->dtype == DT_BF16;
+  const int bkv = a->hd_pad == 192 ? 64 : 128;
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t cols = (uint64_t)a->H * a->hd_pad;
+  {
+    const uint64_t dims[3] = {cols, (uint64_t)a->Lq, (uint64_t)a->B};
+    const uint64_t str[2] = {(uint64_t)a->ldq * 2, (uint64_t)a->q_bstride * 2};
+    const uint32_t box[3] = {64, 128, 1};
+    int r = encode_tmap_16bit(&p.tma_q, a->q, 3, dims, str, box, bf16);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {cols, (uint64_t)a->Lk, (uint64_t)a->B};
+    const uint64_t strk[2] = {(uint64_t)a->ldk * 2, (uint64_t)a->k_bstride * 2};
+    const uint64_t strv[2] = {(uint64_t)a->ldv * 2, (uint64_t)a->v_bstride * 2};
+    const uint32_t box[3] = {64, (uint32_t)bkv, 1};
+    int r = encode_tmap_16bit(&p.tma_k, a->k, 3, dims, strk, box, bf16);
+    if (r) return r;
+    r = encode_tmap_16bit(&p.tma_v, a->v, 3, dims, strv, box, bf16);
+    if (r) return r;
+  }
+  p.out = a->out;
+  p.ldo = a->ldo;
+  p.o_bstride = a->o_bstride;
+  p.kv_lens = a->kv_lens;
+  p.B = a->B;
+  p.H = a->H;
+  p.Lq = a->Lq;
+  p.Lk = a->Lk;
+  p.causal = a->causal;
+  p.causal_offset = a->causal_offset;
+  p.out_dtype = a->dtype;
+  p.in_dtype = a->dtype;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  if (a->hd_pad == 64) return launch_attn<64, 128>(p, stream);
+  if (a->hd_pad == 128) return launch_attn<128, 128>(p, stream);
+  return launch_attn<192, 64>(p, stream);
+}

@@ -87,11 +87,11 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m) { return {t
 
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
-                                              int num_m, int num_tiles) {
+                                              int num_m, int tile_begin, int tile_end, int tile_step) {
   using C = GemmCfg<BLOCK_N>;
   int stage = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
     const TileCoord tc = tile_coord(tile, num_m);
     const int m0 = tc.m_blk * BLOCK_M;
     const int n0 = tc.n_blk * BLOCK_N;
@@ -129,14 +129,14 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
                                          uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
-                                         int num_tiles) {
+                                         int tile_begin, int tile_end, int tile_step) {
   using C = GemmCfg<BLOCK_N>;
   const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
@@ -391,11 +391,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   const uint32_t tmem_base = bars->tmem_ptr;
 
   if (warp == 0) {
-    if (lane_id() == 0) gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, num_m, num_tiles);
+    if (lane_id() == 0)
+      gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, num_m, blockIdx.x, num_tiles, gridDim.x);
   } else if (warp == 1) {
     if (lane_id() == 0)
       gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
-                        num_tiles);
+                        blockIdx.x, num_tiles, gridDim.x);
   } else if (warp >= 4) {
     gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, num_m, num_tiles);
   }

@@ -130,3 +130,61 @@ def conv3x3(
     g.act, g.alpha, g.block_n = _ACT[act], 1.0, block_n
     check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")
     return out
+
+
+def topk_scores(bank: torch.Tensor, q: torch.Tensor, k: int, *, index_base: int = 0,
+                exclude_idx: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
+    """Fused (bank @ q.T) + top-k. bank [N,D] bf16, q [Q,D] bf16 -> (values [Q,k] fp32, global indices [Q,k] int64).
+    Ties resolve to the lowest row index. exclude_idx: int64 device tensor of global rows to down-weight by 1000."""
+    _chk2d(bank, "bank")
+    _chk2d(q, "q")
+    assert bank.dtype == torch.bfloat16 and q.dtype == torch.bfloat16 and bank.shape[1] == q.shape[1]
+    Q, N = q.shape[0], bank.shape[0]
+    need = lib().gillb200_topk_workspace_bytes(Q, N)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, device=bank.device, dtype=torch.uint8)
+    vals = torch.empty((Q, k), device=bank.device, dtype=torch.float32)
+    idx = torch.empty((Q, k), device=bank.device, dtype=torch.int64)
+    n_ex = 0 if exclude_idx is None else exclude_idx.numel()
+    if n_ex:
+        assert exclude_idx.dtype == torch.int64 and exclude_idx.is_cuda and exclude_idx.is_contiguous()
+    check(lib().gillb200_topk_scores(bank.data_ptr(), N, bank.shape[1], bank.stride(0), q.data_ptr(), Q, q.stride(0),
+                                     k, index_base, _ptr(exclude_idx) if n_ex else None, n_ex,
+                                     workspace.data_ptr(), vals.data_ptr(), idx.data_ptr(), _stream()),
+          "gillb200_topk_scores")
+    return vals, idx
+
+
+def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
+    """Merge candidate lists [R,Q,Kc] -> top-k per query ordered by (value desc, index asc)."""
+    assert cand_val.dtype == torch.float32 and cand_idx.dtype == torch.int64
+    assert cand_val.is_contiguous() and cand_idx.is_contiguous() and cand_val.shape == cand_idx.shape
+    R, Q, Kc = cand_val.shape
+    vals = torch.empty((Q, k), device=cand_val.device, dtype=torch.float32)
+    idx = torch.empty((Q, k), device=cand_val.device, dtype=torch.int64)
+    check(lib().gillb200_topk_merge(cand_val.data_ptr(), cand_idx.data_ptr(), R, Q, Kc, k, vals.data_ptr(),
+                                    idx.data_ptr(), _stream()), "gillb200_topk_merge")
+    return vals, idx
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_pad: int, scale: float, *,
+              out: Optional[torch.Tensor] = None, causal: bool = False, causal_offset: int = 0,
+              kv_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B,Lq,>=H*hd_pad], k/v [B,Lk,>=H*hd_pad] (views into fused QKV buffers allowed; last dim contiguous).
+    Returns out [B,Lq,H*hd_pad]. Pad columns of each head must be zero in q, k, v."""
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    for t in (q, k, v):
+        assert t.stride(2) == 1 and t.dtype == q.dtype
+    if out is None:
+        out = torch.empty((B, Lq, heads * hd_pad), device=q.device, dtype=q.dtype)
+    a = _lib.AttnArgs()
+    a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.ldq, a.ldk, a.ldv, a.ldo = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
+    a.q_bstride, a.k_bstride, a.v_bstride, a.o_bstride = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.kv_lens = _ptr(kv_lens)
+    a.B, a.H, a.Lq, a.Lk, a.hd_pad = B, heads, Lq, Lk, hd_pad
+    a.causal, a.causal_offset = int(causal), causal_offset
+    a.dtype, a.scale = _DT[q.dtype], scale
+    check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")
+    return out

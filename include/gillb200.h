@@ -79,6 +79,49 @@ typedef struct gillb200_gemm_args {
 
 int gillb200_gemm(const gillb200_gemm_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Retrieval: fused cosine-similarity GEMM + top-k  (gill/models.py:676-683).
+ *
+ *   scores[q, n] = sum_d q[q, d] * bank[n, d]  (bf16 operands, fp32 accumulate; never materialised)
+ *   scores[q, n] -= 1000 for every global row index listed in exclude_idx   (models.py:679-680)
+ *   out = top-K per query, value descending, ties -> lowest global index; out_idx = index_base + local row.
+ *
+ * bank: [n_local, d] bf16 (already normalised and scaled as in models.py:895-900), q: [Q, d] bf16, K <= 16.
+ * `workspace` must hold gillb200_topk_workspace_bytes(Q, n_local) bytes of device memory.
+ * gillb200_topk_merge merges R candidate lists [R, Q, Kc] (e.g. one per GPU after the NCCL all-gather).
+ * ------------------------------------------------------------------------------------------------------------- */
+long long gillb200_topk_workspace_bytes(int Q, long long n_local);
+int gillb200_topk_scores(const void* bank, long long n_local, int d, long long ld_bank, const void* q, int Q,
+                         long long ldq, int K, long long index_base, const long long* exclude_idx, int n_exclude,
+                         void* workspace, float* out_val, long long* out_idx, void* stream);
+int gillb200_topk_merge(const float* cand_val, const long long* cand_idx, int R, int Q, int Kc, int K, float* out_val,
+                        long long* out_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused multi-head attention  out = softmax(scale * Q K^T [+ causal / length mask]) V   (flash style, tcgen05).
+ *
+ * Replaces diffusers' Attention (UNet self/cross attention, gill/custom_sd.py:633-638) and OPTAttention
+ * (gill/models.py:465). q: [B, Lq, *], k/v: [B, Lk, *], out: [B, Lq, *]; head h occupies columns
+ * [h*hd_pad, (h+1)*hd_pad) of each row, hd_pad in {64, 128, 192}; columns beyond the true head dim must be zero in
+ * q, k and v (the projection weights are zero-padded at load time). Strides are in elements.
+ * causal: key j is visible to query i iff j <= i + causal_offset. kv_lens: optional per-batch key count (device).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct gillb200_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* out;
+  long long ldq, ldk, ldv, ldo;
+  long long q_bstride, k_bstride, v_bstride, o_bstride;
+  const int* kv_lens;
+  int B, H, Lq, Lk, hd_pad;
+  int causal, causal_offset;
+  int dtype;
+  float scale;
+} gillb200_attn_args;
+
+int gillb200_attention(const gillb200_attn_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
