@@ -1,0 +1,359 @@
+// Small HBM-bound kernels around the tensor-core path: gathers, resampling, im2col for strided convs, the fused
+// CFG + PLMS scheduler step, the VAE uint8 epilogue, L2 normalisation and the fp32 small-sequence attention used by
+// the GILLMapper. All are 16-byte vectorised where the layout allows it.
+#include "../../include/gillb200.h"
+#include "gemm_sm100.cuh"
+#include "host_common.h"
+
+namespace gb {
+
+__device__ __forceinline__ uint4 ldg16(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// out[i, :] = (x ? x[i, :] : 0) + table[idx[i] + idx_offset, :]        (16-bit rows, D % 8 == 0)
+// OPT: inputs_embeds + embed_positions(pos + 2)  (transformers OPTLearnedPositionalEmbedding; gill/models.py:465),
+// and the token-embedding gather gill/models.py:620 / :529 / :709 when x == nullptr.
+__global__ void gather_add_rows_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ table,
+                                       const long long* __restrict__ idx, long long idx_offset, long long rows, int D,
+                                       int is_bf16, uint16_t* __restrict__ out) {
+  const int nvec = D >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / nvec;
+    const int v = static_cast<int>(i % nvec);
+    const uint4 t = ldg16(table + (idx[r] + idx_offset) * D + v * 8);
+    uint4 o = t;
+    if (x) {
+      const uint4 a = ldg16(x + r * D + v * 8);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, tw[4] = {t.x, t.y, t.z, t.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = is_bf16 ? unpack_bf16x2(aw[j]) : unpack_f16x2(aw[j]);
+        const float2 ft = is_bf16 ? unpack_bf16x2(tw[j]) : unpack_f16x2(tw[j]);
+        ow[j] = is_bf16 ? pack_bf16x2(fa.x + ft.x, fa.y + ft.y) : pack_f16x2(fa.x + ft.x, fa.y + ft.y);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    *reinterpret_cast<uint4*>(out + r * D + v * 8) = o;
+  }
+}
+
+// nearest-neighbour 2x upsample, NHWC 16-bit (F.interpolate(scale_factor=2, mode="nearest") in the UNet/VAE up blocks)
+__global__ void upsample2x_kernel(const uint16_t* __restrict__ x, int B, int H, int W, int C,
+                                  uint16_t* __restrict__ out) {
+  const int nvec = C >> 3;
+  const long long total = static_cast<long long>(B) * 2 * H * 2 * W * nvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % nvec);
+    long long t = i / nvec;
+    const int ox = static_cast<int>(t % (2 * W));
+    t /= 2 * W;
+    const int oy = static_cast<int>(t % (2 * H));
+    const int b = static_cast<int>(t / (2 * H));
+    const uint4 val = ldg16(x + ((static_cast<long long>(b) * H + (oy >> 1)) * W + (ox >> 1)) * C + v * 8);
+    *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * 2 * H + oy) * 2 * W + ox) * C + v * 8) = val;
+  }
+}
+
+// im2col for 3x3 / pad 1 convolutions with stride s (UNet downsamplers, stride 2) or tiny channel counts (conv_in,
+// C = 4). out[m, (ky*3+kx)*C + c] for m = (b, oy, ox); columns [9*C, ld_out) are zero-filled.
+__global__ void im2col3x3_kernel(const uint16_t* __restrict__ x, int B, int H, int W, int C, int stride, int Ho,
+                                 int Wo, uint16_t* __restrict__ out, long long ld_out) {
+  const long long total = static_cast<long long>(B) * Ho * Wo * ld_out;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % ld_out);
+    long long m = i / ld_out;
+    uint16_t val = 0;
+    if (col < 9 * C) {
+      const int tap = col / C, c = col - tap * C;
+      const int ox = static_cast<int>(m % Wo);
+      m /= Wo;
+      const int oy = static_cast<int>(m % Ho);
+      const int b = static_cast<int>(m / Ho);
+      const int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = x[((static_cast<long long>(b) * H + iy) * W + ix) * C + c];
+    }
+    out[i] = val;
+  }
+}
+
+// Fused classifier-free guidance + PLMS update (gill/custom_sd.py:641-646; diffusers PNDMScheduler.step_plms).
+//   eps = eps_u + g * (eps_t - eps_u);  e' = linear multistep over the last <= 4 eps;  x' = c_sample * x - c_eps * e'
+// eps_pair: [2, n] 16-bit or fp32 (uncond first). ets: ring of 4 fp32 buffers [4, n]; `head` is the slot that receives
+// this step's eps (ignored for mode 1, where eps is NOT pushed: the repeated-timestep half step averages with ets[-1]).
+// mode: 0 first step (e' = eps; cur_sample = x saved), 1 second call (e' = (eps + e_-1)/2, x = cur_sample),
+//       2/3/4: Adams-Bashforth of that order.
+__global__ void plms_step_kernel(const void* __restrict__ eps_pair, int eps_dtype, float guidance, float* __restrict__ ets,
+                                 int head, int mode, float c_sample, float c_eps, float* __restrict__ latents,
+                                 float* __restrict__ cur_sample, void* __restrict__ lat16_pair, int lat16_dtype,
+                                 long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float eu = load_elem(eps_pair, i, eps_dtype), et = load_elem(eps_pair, n + i, eps_dtype);
+    const float eps = eu + guidance * (et - eu);
+    float x = latents[i];
+    float e;
+    float* e0 = ets + static_cast<long long>(head) * n;
+    const float* e1 = ets + static_cast<long long>((head + 3) & 3) * n;
+    const float* e2 = ets + static_cast<long long>((head + 2) & 3) * n;
+    const float* e3 = ets + static_cast<long long>((head + 1) & 3) * n;
+    if (mode == 1) {
+      e = 0.5f * (eps + e1[i]);  // e1 is the most recently pushed eps (head is NOT advanced by this call)
+      x = cur_sample[i];
+    } else {
+      e0[i] = eps;
+      if (mode == 0) {
+        e = eps;
+        cur_sample[i] = x;
+      } else if (mode == 2) {
+        e = (3.f * eps - e1[i]) * 0.5f;
+      } else if (mode == 3) {
+        e = (23.f * eps - 16.f * e1[i] + 5.f * e2[i]) * (1.f / 12.f);
+      } else {
+        e = (55.f * eps - 59.f * e1[i] + 37.f * e2[i] - 9.f * e3[i]) * (1.f / 24.f);
+      }
+    }
+    const float xn = c_sample * x - c_eps * e;
+    latents[i] = xn;
+    if (lat16_pair) {  // next UNet input: the latent duplicated for the (uncond, text) pair
+      store_elem(lat16_pair, i, xn, lat16_dtype);
+      store_elem(lat16_pair, n + i, xn, lat16_dtype);
+    }
+  }
+}
+
+// VAE epilogue (gill/custom_sd.py:389-391 + numpy_to_pil): uint8 NHWC = round(clamp(x/2 + 0.5, 0, 1) * 255)
+__global__ void image_to_u8_kernel(const void* __restrict__ x, int dtype, long long pixels, int ldx, int channels,
+                                   uint8_t* __restrict__ out) {
+  const long long total = pixels * channels;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / channels;
+    const int c = static_cast<int>(i % channels);
+    float v = load_elem(x, pix * ldx + c, dtype) * 0.5f + 0.5f;
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    out[i] = static_cast<uint8_t>(rintf(v * 255.f));
+  }
+}
+
+// y = x / ||x||_2 per row (gill/models.py:674); one warp per row; fp32 in, 16-bit or fp32 out.
+__global__ void l2norm_rows_kernel(const float* __restrict__ x, long long ldx, int rows, int n, void* __restrict__ out,
+                                   long long ldo, int out_dtype) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) {
+    const float v = x[row * ldx + i];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.f / sqrtf(s);
+  for (int i = lane; i < n; i += 32) store_elem(out, row * ldo + i, x[row * ldx + i] * inv, out_dtype);
+}
+
+// elementwise convert / add: out = cast(x (+ y)); optional bf16 residue for split-precision consumers
+__global__ void cast_add_kernel(const void* __restrict__ x, int x_dtype, const void* __restrict__ y, int y_dtype,
+                                void* __restrict__ out, int out_dtype, void* __restrict__ out_lo, long long n,
+                                long long y_period) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = load_elem(x, i, x_dtype);
+    if (y) v += load_elem(y, y_period > 0 ? i % y_period : i, y_dtype);
+    store_elem(out, i, v, out_dtype);
+    if (out_lo) store_elem(out_lo, i, v - __bfloat162float(__float2bfloat16_rn(v)), DT_BF16);
+  }
+}
+
+// fp32 attention for short sequences (GILLMapper: 4 heads x 128, Lq <= 77, Lk in {8, 77}; gill/layers.py:43).
+// One CTA per (batch, head). q/k/v fp32 with row stride ld*, head h at column h*HD. Output fp32 or bf16 hi+lo.
+template <int HD>
+__global__ void __launch_bounds__(256) attn_small_f32_kernel(const float* __restrict__ q, long long ldq, long long q_bs,
+                                                             const float* __restrict__ k, long long ldk, long long k_bs,
+                                                             const float* __restrict__ v, long long ldv, long long v_bs,
+                                                             int Lq, int Lk, float scale, void* __restrict__ out,
+                                                             long long ldo, long long o_bs, int out_dtype,
+                                                             void* __restrict__ out_lo) {
+  extern __shared__ float sm[];
+  const int LkP = Lk + 1;
+  float* sk = sm;                      // [Lk][HD+1]
+  float* sv = sk + Lk * (HD + 1);      // [Lk][HD]
+  float* sp = sv + Lk * HD;            // [8 warps][LkP]
+  const int b = blockIdx.y, h = blockIdx.x;
+  const float* kb = k + b * k_bs + h * HD;
+  const float* vb = v + b * v_bs + h * HD;
+  for (int i = threadIdx.x; i < Lk * HD; i += blockDim.x) {
+    const int r = i / HD, c = i - r * HD;
+    sk[r * (HD + 1) + c] = kb[r * ldk + c];
+    sv[r * HD + c] = vb[r * ldv + c];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pw = sp + warp * LkP;
+  for (int i = warp; i < Lq; i += 8) {
+    const float* qr = q + b * q_bs + static_cast<long long>(i) * ldq + h * HD;
+    float qreg[HD / 32];
+#pragma unroll
+    for (int t = 0; t < HD / 32; ++t) qreg[t] = qr[lane + 32 * t];
+    // scores: lane handles keys lane, lane+32, lane+64, lane+96 (Lk <= 128); q elements are broadcast by shuffle
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+    int jj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) jj[u] = min(lane + 32 * u, Lk - 1) * (HD + 1);
+#pragma unroll
+    for (int t = 0; t < HD / 32; ++t) {
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) {
+        const float qv = __shfl_sync(0xffffffffu, qreg[t], l);
+        const int c = t * 32 + l;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sc[u] += qv * sk[jj[u] + c];
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = lane + 32 * u;
+      if (j < Lk) {
+        const float sv_ = sc[u] * scale;
+        pw[j] = sv_;
+        mx = fmaxf(mx, sv_);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    __syncwarp();
+    for (int j = lane; j < Lk; j += 32) {
+      const float pj = expf(pw[j] - mx);
+      pw[j] = pj;
+      sum += pj;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    float acc[HD / 32];
+#pragma unroll
+    for (int t = 0; t < HD / 32; ++t) acc[t] = 0.f;
+    for (int j = 0; j < Lk; ++j) {
+      const float pj = pw[j];
+#pragma unroll
+      for (int t = 0; t < HD / 32; ++t) acc[t] += pj * sv[j * HD + t * 32 + lane];
+    }
+    const long long o = b * o_bs + static_cast<long long>(i) * ldo + h * HD;
+#pragma unroll
+    for (int t = 0; t < HD / 32; ++t) {
+      const float val = acc[t] * inv;
+      store_elem(out, o + t * 32 + lane, val, out_dtype);
+      if (out_lo) store_elem(out_lo, o + t * 32 + lane, val - __bfloat162float(__float2bfloat16_rn(val)), DT_BF16);
+    }
+    __syncwarp();
+  }
+}
+
+static inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int gillb200_gather_add_rows(const void* x, const void* table, const long long* idx, long long idx_offset,
+                                        long long rows, int D, int dtype, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(table && idx && out && D % 8 == 0 && rows > 0, "gather_add_rows: bad args");
+  GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16, "gather_add_rows: 16-bit only");
+  gather_add_rows_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(table), idx, idx_offset, rows, D,
+      dtype == DT_BF16, reinterpret_cast<uint16_t*>(out));
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && out && C % 8 == 0, "upsample2x: bad args");
+  upsample2x_kernel<<<grid_for(4LL * B * H * W * (C / 8), 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(x), B, H, W, C, reinterpret_cast<uint16_t*>(out));
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_im2col3x3(const void* x, int B, int H, int W, int C, int stride, void* out, long long ld_out,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && out && (stride == 1 || stride == 2) && ld_out >= 9 * C, "im2col3x3: bad args");
+  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  im2col3x3_kernel<<<grid_for(1LL * B * Ho * Wo * ld_out, 256), 256, 0, stream>>>(
+      reinterpret_cast<const uint16_t*>(x), B, H, W, C, stride, Ho, Wo, reinterpret_cast<uint16_t*>(out), ld_out);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_plms_step(const void* eps_pair, int eps_dtype, float guidance, float* ets, int head, int mode,
+                                  float c_sample, float c_eps, float* latents, float* cur_sample, void* lat16_pair,
+                                  int lat16_dtype, long long n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(eps_pair && ets && latents && cur_sample && n > 0, "plms_step: null pointer");
+  GB_CHECK_ARG(mode >= 0 && mode <= 4 && head >= 0 && head < 4, "plms_step: bad mode/head");
+  plms_step_kernel<<<grid_for(n, 256), 256, 0, stream>>>(eps_pair, eps_dtype, guidance, ets, head, mode, c_sample,
+                                                         c_eps, latents, cur_sample, lat16_pair, lat16_dtype, n);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_image_to_u8(const void* x, int dtype, long long pixels, int ldx, int channels, void* out,
+                                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && out && pixels > 0 && channels > 0 && ldx >= channels, "image_to_u8: bad args");
+  image_to_u8_kernel<<<grid_for(pixels * channels, 256), 256, 0, stream>>>(x, dtype, pixels, ldx, channels,
+                                                                           reinterpret_cast<uint8_t*>(out));
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int n, void* out, long long ldo,
+                                    int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && out && rows > 0 && n > 0, "l2norm_rows: bad args");
+  l2norm_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, rows, n, out, ldo, out_dtype);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_cast_add(const void* x, int x_dtype, const void* y, int y_dtype, long long y_period, void* out,
+                                 int out_dtype, void* out_lo, long long n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && out && n > 0, "cast_add: bad args");
+  cast_add_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_attn_small_f32(const float* q, long long ldq, long long q_bs, const float* k, long long ldk,
+                                       long long k_bs, const float* v, long long ldv, long long v_bs, int B, int H,
+                                       int hd, int Lq, int Lk, float scale, void* out, long long ldo, long long o_bs,
+                                       int out_dtype, void* out_lo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(q && k && v && out, "attn_small_f32: null pointer");
+  GB_CHECK_ARG(hd == 128, "attn_small_f32: head dim must be 128 (got %d)", hd);
+  GB_CHECK_ARG(Lk >= 1 && Lk <= 128 && Lq >= 1, "attn_small_f32: Lk must be in [1,128]");
+  const size_t smem = (static_cast<size_t>(Lk) * (128 + 1) + static_cast<size_t>(Lk) * 128 + 8 * (Lk + 1)) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    GB_CUDA(cudaFuncSetAttribute(attn_small_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
+  attn_small_f32_kernel<128><<<dim3(H, B), 256, smem, stream>>>(q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
+                                                                  out, ldo, o_bs, out_dtype, out_lo);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}

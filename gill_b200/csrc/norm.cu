@@ -1,0 +1,354 @@
+// LayerNorm / GroupNorm(+SiLU) / row softmax: HBM-bound kernels, 16-byte vectorised, fp32 statistics.
+//
+// Replaces F.layer_norm / nn.GroupNorm / softmax inside the third-party modules on the hot path:
+//   nn.Transformer norms of the GILLMapper (gill/layers.py:20-22), OPT decoder layer norms (gill/models.py:465),
+//   UNet / VAE GroupNorm+SiLU and transformer-block LayerNorms (gill/custom_sd.py:633-638, :388).
+#include "../../include/gillb200.h"
+#include "gemm_sm100.cuh"
+#include "host_common.h"
+
+namespace gb {
+
+// ------------------------------------------------------------------------------------------------ helpers
+struct Vec8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Vec8 load8(const void* base, long long elem_off, int dtype) {
+  Vec8 r;
+  if (dtype == DT_F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + elem_off);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = dtype == DT_BF16 ? unpack_bf16x2(w[i]) : unpack_f16x2(w[i]);
+      r.v[2 * i] = f.x;
+      r.v[2 * i + 1] = f.y;
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void store8(void* base, long long elem_off, const Vec8& x, int dtype) {
+  if (dtype == DT_F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    p[0] = make_float4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    p[1] = make_float4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  } else {
+    uint4 u;
+    if (dtype == DT_BF16) {
+      u.x = pack_bf16x2(x.v[0], x.v[1]); u.y = pack_bf16x2(x.v[2], x.v[3]);
+      u.z = pack_bf16x2(x.v[4], x.v[5]); u.w = pack_bf16x2(x.v[6], x.v[7]);
+    } else {
+      u.x = pack_f16x2(x.v[0], x.v[1]); u.y = pack_f16x2(x.v[2], x.v[3]);
+      u.z = pack_f16x2(x.v[4], x.v[5]); u.w = pack_f16x2(x.v[6], x.v[7]);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + elem_off) = u;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One row per `WARPS` warps; each lane keeps up to MAXV 8-wide vectors of the row in registers (two-pass variance).
+template <int WARPS, int MAXV>
+__global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__ x, long long ldx, int in_dtype,
+                                                        const float* __restrict__ w, const float* __restrict__ b,
+                                                        float eps, int rows, int C, void* __restrict__ out,
+                                                        long long ldo, int out_dtype, void* __restrict__ out_lo) {
+  __shared__ float red[2][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rows_per_block = 4 / WARPS;
+  const int row = blockIdx.x * rows_per_block + (WARPS == 1 ? warp : 0);
+  const int t = WARPS == 1 ? lane : threadIdx.x;  // thread index within the row team
+  const int team = WARPS * 32;
+  const int nvec = C >> 3;
+  const bool active = row < rows;
+  Vec8 buf[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = t + i * team;
+    if (active && v < nvec) {
+      buf[i] = load8(x, static_cast<long long>(row) * ldx + v * 8, in_dtype);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += buf[i].v[j];
+    }
+  }
+  s = warp_sum(s);
+  if (WARPS > 1) {
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    s = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+  }
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = t + i * team;
+    if (active && v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = buf[i].v[j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  q = warp_sum(q);
+  if (WARPS > 1) {
+    if (lane == 0) red[1][warp] = q;
+    __syncthreads();
+    q = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+  }
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = t + i * team;
+    if (active && v < nvec) {
+      Vec8 o;
+      const float4 w0 = *reinterpret_cast<const float4*>(w + v * 8), w1 = *reinterpret_cast<const float4*>(w + v * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(b + v * 8), b1 = *reinterpret_cast<const float4*>(b + v * 8 + 4);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = (buf[i].v[j] - mean) * rstd * ww[j] + bb[j];
+      const long long off = static_cast<long long>(row) * ldo + v * 8;
+      store8(out, off, o, out_dtype);
+      if (out_lo) {
+        Vec8 lo;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo.v[j] = o.v[j] - __bfloat162float(__float2bfloat16_rn(o.v[j]));
+        store8(out_lo, off, lo, DT_BF16);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm
+// NHWC input, optionally the channel-concatenation of two tensors (UNet up blocks: cat([h, skip])).
+// Pass 1: grid (chunks, B): per-channel partial sums over a pixel chunk -> per-group (sum, sumsq) partials.
+// Pass 2: elementwise normalise (+SiLU), reducing the `chunks` partials in a fixed order (deterministic).
+struct GnSrc {
+  const void* x0;
+  const void* x1;
+  int C0, C1;  // channels of each source (C1 == 0: single source)
+};
+
+__device__ __forceinline__ Vec8 gn_load(const GnSrc& s, long long pix, int v, int dtype) {
+  const int v0 = s.C0 >> 3;
+  if (v < v0) return load8(s.x0, pix * s.C0 + v * 8, dtype);
+  return load8(s.x1, pix * s.C1 + (v - v0) * 8, dtype);
+}
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int HW, int G, int chunks,
+                                                       float* __restrict__ partial /* [B, chunks, G, 2] */) {
+  extern __shared__ float sm[];  // [C] sums, [C] sumsq
+  const int C = src.C0 + src.C1;
+  const int nvec = C >> 3;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int pix_per_chunk = (HW + chunks - 1) / chunks;
+  const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int vb = 0; vb < nvec; vb += 32) {
+    const int v = vb + lane;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    if (v < nvec) {
+      for (int pix = p0 + warp; pix < p1; pix += nwarps) {
+        const Vec8 x = gn_load(src, static_cast<long long>(b) * HW + pix, v, dtype);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += x.v[j];
+          q[j] += x.v[j] * x.v[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sm[v * 8 + j], s[j]);
+        atomicAdd(&sm[C + v * 8 + j], q[j]);
+      }
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      s += sm[c];
+      q += sm[C + c];
+    }
+    float* o = partial + ((static_cast<long long>(b) * chunks + chunk) * G + g) * 2;
+    o[0] = s;
+    o[1] = q;
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int HW, int G, int chunks,
+                                                       const float* __restrict__ partial, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float eps, int silu,
+                                                       void* __restrict__ out, int out_dtype, int pix_per_block) {
+  extern __shared__ float sm[];  // [C] scale, [C] shift
+  const int C = src.C0 + src.C1;
+  const int nvec = C >> 3;
+  const int b = blockIdx.y;
+  const int cpg = C / G;
+  float* sc = sm;
+  float* sh = sm + C;
+  __shared__ float gmean[64], grstd[64];
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const float* pp = partial + ((static_cast<long long>(b) * chunks + ch) * G + g) * 2;
+      s += pp[0];
+      q += pp[1];
+    }
+    const float n = static_cast<float>(cpg) * HW;
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    gmean[g] = mean;
+    grstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = grstd[g] * w[c];
+    sc[c] = a;
+    sh[c] = bias[c] - gmean[g] * a;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
+  const long long total = static_cast<long long>(p1 - p0) * nvec;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pix = p0 + static_cast<int>(i / nvec);
+    const int v = static_cast<int>(i % nvec);
+    const long long gp = static_cast<long long>(b) * HW + pix;
+    Vec8 x = gn_load(src, gp, v, dtype);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = x.v[j] * sc[v * 8 + j] + sh[v * 8 + j];
+      if (silu) y = y / (1.f + __expf(-y));
+      x.v[j] = y;
+    }
+    store8(out, gp * C + v * 8, x, out_dtype);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ row softmax
+// out[r, :] = softmax(scale * x[r, :]); one CTA per row; x may be fp32 or 16-bit, out 16-bit. n % 8 == 0.
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const void* __restrict__ x, long long ldx, int in_dtype,
+                                                           float scale, int n, void* __restrict__ out, long long ldo,
+                                                           int out_dtype) {
+  __shared__ float red[8];
+  const long long row = blockIdx.x;
+  const int nvec = n >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    const Vec8 a = load8(x, row * ldx + v * 8, in_dtype);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, a.v[j]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    const Vec8 a = load8(x, row * ldx + v * 8, in_dtype);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += __expf((a.v[j] - mx) * scale);
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  const float inv = 1.f / s;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    Vec8 a = load8(x, row * ldx + v * 8, in_dtype);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a.v[j] = __expf((a.v[j] - mx) * scale) * inv;
+    store8(out, row * ldo + v * 8, a, out_dtype);
+  }
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, const float* w, const float* b, float eps,
+                                  int rows, int C, void* out, long long ldo, int out_dtype, void* out_lo,
+                                  void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && w && b && out, "null pointer");
+  GB_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm needs C, ldx, ldo multiples of 8");
+  GB_CHECK_ARG(C <= 5120, "layernorm supports C <= 5120 (got %d)", C);
+  GB_CHECK_ARG(!out_lo || out_dtype == DT_BF16, "out_lo requires bf16 output");
+  if (C <= 1280) {
+    layernorm_kernel<1, 5><<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                out_dtype, out_lo);
+  } else {
+    layernorm_kernel<4, 5><<<rows, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
+                                                      out_lo);
+  }
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" long long gillb200_groupnorm_workspace_bytes(int B, int G) { return 64LL * B * G * 2 * sizeof(float); }
+
+extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1, int dtype, int B, int HW, int G,
+                                  const float* w, const float* b, float eps, int silu, void* out, int out_dtype,
+                                  void* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x0 && w && b && out && workspace, "null pointer");
+  const int C = C0 + C1;
+  GB_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % G == 0 && G <= 64, "groupnorm: C0=%d C1=%d G=%d", C0, C1, G);
+  GB_CHECK_ARG(C1 == 0 || x1 != nullptr, "groupnorm: second source missing");
+  GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16 || dtype == DT_F32, "bad dtype");
+  GnSrc src{x0, x1, C0, C1};
+  int chunks = HW / 64;
+  if (chunks > 64) chunks = 64;
+  if (chunks < 1) chunks = 1;
+  // fill the machine: B * chunks CTAs
+  while (chunks > 1 && B * chunks > 4 * num_sms()) chunks >>= 1;
+  const size_t smem = 2 * C * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, B), 256, smem, stream>>>(src, dtype, HW, G, chunks,
+                                                         reinterpret_cast<float*>(workspace));
+  GB_CUDA(cudaGetLastError());
+  int pix_per_block = (32768 + C - 1) / C;  // ~32K elements per CTA
+  if (pix_per_block < 1) pix_per_block = 1;
+  const int blocks = (HW + pix_per_block - 1) / pix_per_block;
+  gn_apply_kernel<<<dim3(blocks, B), 256, smem, stream>>>(src, dtype, HW, G, chunks,
+                                                         reinterpret_cast<const float*>(workspace), w, b, eps, silu,
+                                                         out, out_dtype, pix_per_block);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype, float scale, long long rows, int n,
+                                     void* out, long long ldo, int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && out && n % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "softmax_rows: n, ldx, ldo multiples of 8");
+  GB_CHECK_ARG(rows > 0 && rows < (1LL << 31), "softmax_rows: bad row count");
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, in_dtype, scale, n, out, ldo, out_dtype);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -49,7 +49,9 @@ __device__ __forceinline__ void topk_insert(float (&tv)[KMAX], int (&ti)[KMAX], 
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+constexpr int TOPK_THREADS = 384;
+
+__global__ void __launch_bounds__(TOPK_THREADS, 1)
 topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__ TopkEpi e) {
   using C = GemmCfg<TOPK_BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -68,7 +70,7 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 4);
+      mbar_init(&bars->tmem_empty[i], 8);
     }
     fence_barrier_init();
   }
@@ -96,7 +98,10 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
       gemm_mma<TOPK_BN>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
                         tile_begin, tile_end, tile_step);
   } else if (warp >= 4) {
+    // 8 epilogue warps: warps 4..7 scan columns [0,128) of each tile, warps 8..11 scan [128,256); both groups cover
+    // all 128 TMEM lanes (a warp may only touch lanes 32*(warp%4) .. +31). Each thread keeps its own top-KMAX.
     const int ewarp = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int qrow = m_blk * BLOCK_M + ewarp * 32 + lane_id();
     float tv[KMAX];
     int ti[KMAX];
@@ -110,28 +115,32 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
     for (int n_blk = n_lo; n_blk < n_hi; ++n_blk) {
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(ewarp * 32) << 16);
-      const long long n0 = static_cast<long long>(n_blk) * TOPK_BN;
+      const uint32_t taddr =
+          tmem_base + acc * C::ACC_STRIDE + half * (TOPK_BN / 2) + (static_cast<uint32_t>(ewarp * 32) << 16);
+      const long long n0 = static_cast<long long>(n_blk) * TOPK_BN + half * (TOPK_BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < TOPK_BN; c += 16) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(taddr + c, r);
+      for (int c = 0; c < TOPK_BN / 2; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c, r);
         tmem_wait_ld();
         float mx = __uint_as_float(r[0]);
 #pragma unroll
-        for (int j = 1; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-        if (mx > tv[KMAX - 1]) {
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+        if (__any_sync(0xffffffffu, mx > tv[KMAX - 1])) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < 32; ++j) {
             float s = __uint_as_float(r[j]);
             const long long nloc = n0 + c + j;
-            if (s > tv[KMAX - 1] && nloc < e.n_local) {
-              if (e.n_exclude > 0) {
-                const long long gidx = e.index_base + nloc;
-                for (int x = 0; x < e.n_exclude; ++x)
-                  if (e.exclude[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
+            const bool pass = s > tv[KMAX - 1] && nloc < e.n_local;
+            if (__any_sync(0xffffffffu, pass)) {  // warp-uniform: the insert body only runs for columns that hit
+              if (pass) {
+                if (e.n_exclude > 0) {
+                  const long long gidx = e.index_base + nloc;
+                  for (int x = 0; x < e.n_exclude; ++x)
+                    if (e.exclude[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
+                }
+                topk_insert(tv, ti, s, static_cast<int>(nloc));
               }
-              topk_insert(tv, ti, s, static_cast<int>(nloc));
             }
           }
         }
@@ -144,8 +153,8 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
         acc_phase ^= 1;
       }
     }
-    // this CTA's candidates for query qrow (rows >= Q carry -inf and are ignored by the merge)
-    const long long o = (static_cast<long long>(split) * e.q_pad + qrow) * KMAX;
+    // candidates of (split, column half) for query qrow; rows >= Q carry zeros/-inf and are ignored by the merge
+    const long long o = (static_cast<long long>(split * 2 + half) * e.q_pad + qrow) * KMAX;
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) {
       e.part_val[o + j] = tv[j];
@@ -224,7 +233,7 @@ extern "C" long long gillb200_topk_workspace_bytes(int Q, long long n_local) {
   int tps, num_n;
   const int splits = topk_splits(Q, n_local, &tps, &num_n);
   const int q_pad = (Q + BLOCK_M - 1) / BLOCK_M * BLOCK_M;
-  return static_cast<long long>(splits) * q_pad * KMAX * (sizeof(float) + sizeof(long long)) + 256;
+  return 2LL * splits * q_pad * KMAX * (sizeof(float) + sizeof(long long)) + 256;
 }
 
 extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, long long ld_bank, const void* q, int Q,
@@ -275,7 +284,7 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
   e.q_pad = num_m * BLOCK_M;
   e.tiles_per_split = tps;
   e.num_n = num_n;
-  const long long part_elems = static_cast<long long>(splits) * e.q_pad * KMAX;
+  const long long part_elems = 2LL * splits * e.q_pad * KMAX;
   e.part_idx = reinterpret_cast<long long*>(workspace);
   e.part_val = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part_elems * sizeof(long long));
 
@@ -285,11 +294,11 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
     GB_CUDA(cudaFuncSetAttribute(topk_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
   }
-  topk_scores_kernel<<<num_m * splits, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p, e);
+  topk_scores_kernel<<<num_m * splits, TOPK_THREADS, C::SMEM_BYTES, stream>>>(p, e);
   GB_CUDA(cudaGetLastError());
   const int warps_per_block = 4;
   topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      e.part_val, e.part_idx, splits, KMAX, static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx);
+      e.part_val, e.part_idx, splits * 2, KMAX, static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx);
   GB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -122,8 +122,10 @@ def conv3x3(
         assert bias.dtype == torch.float32
         g.bias = bias.data_ptr()
     if rowbias is not None:
-        assert rowbias.dtype == torch.float32 and rowbias.shape[0] == B
-        g.rowbias, g.ld_rowbias, g.rows_per_group = rowbias.data_ptr(), rowbias.stride(0), H * W
+        assert rowbias.dtype == torch.float32 and rowbias.shape[0] in (1, B) and rowbias.stride(1) == 1
+        # one row per sample (per-sample timestep) or a single row shared by the whole batch
+        g.rowbias, g.ld_rowbias = rowbias.data_ptr(), rowbias.stride(0)
+        g.rows_per_group = H * W if rowbias.shape[0] == B and B > 1 else B * H * W
     if residual is not None:
         r2 = residual.view(B * H * W, N)
         g.residual, g.ldr, g.res_dtype = r2.data_ptr(), r2.stride(0), _DT[residual.dtype]
@@ -187,4 +189,147 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
     a.causal, a.causal_offset = int(causal), causal_offset
     a.dtype, a.scale = _DT[q.dtype], scale
     check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# norms / softmax
+# ---------------------------------------------------------------------------------------------------------------
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e-5, *,
+              out_dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None,
+              out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the last dim of a [rows, C] tensor (fp32 weights). out_lo receives the bf16 residue."""
+    _chk2d(x, "x")
+    rows, C = x.shape
+    assert w.dtype == torch.float32 and b.dtype == torch.float32
+    if out is None:
+        out = torch.empty((rows, C), device=x.device, dtype=out_dtype or x.dtype)
+    check(lib().gillb200_layernorm(x.data_ptr(), x.stride(0), _DT[x.dtype], w.data_ptr(), b.data_ptr(), eps, rows, C,
+                                   out.data_ptr(), out.stride(0), _DT[out.dtype], _ptr(out_lo), _stream()),
+          "gillb200_layernorm")
+    return out
+
+
+_gn_ws = {}
+
+
+def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, eps: float, *, silu: bool = False,
+              x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """GroupNorm(+SiLU) over NHWC x [B,H,W,C0] (optionally channel-concatenated with x2 [B,H,W,C1])."""
+    B, H, W, C0 = x.shape
+    C1 = 0 if x2 is None else x2.shape[3]
+    assert x.is_contiguous() and (x2 is None or (x2.is_contiguous() and x2.dtype == x.dtype))
+    if out is None:
+        out = torch.empty((B, H, W, C0 + C1), device=x.device, dtype=out_dtype or x.dtype)
+    key = (x.device.index, B, groups)
+    ws = _gn_ws.get(key)
+    if ws is None:
+        ws = torch.empty(lib().gillb200_groupnorm_workspace_bytes(B, groups), device=x.device, dtype=torch.uint8)
+        _gn_ws[key] = ws
+    check(lib().gillb200_groupnorm(x.data_ptr(), C0, _ptr(x2), C1, _DT[x.dtype], B, H * W, groups, w.data_ptr(),
+                                   b.data_ptr(), eps, int(silu), out.data_ptr(), _DT[out.dtype], ws.data_ptr(),
+                                   _stream()), "gillb200_groupnorm")
+    return out
+
+
+def softmax_rows(x: torch.Tensor, scale: float, out_dtype: torch.dtype, out: Optional[torch.Tensor] = None):
+    _chk2d(x, "x")
+    rows, n = x.shape
+    if out is None:
+        out = torch.empty((rows, n), device=x.device, dtype=out_dtype)
+    check(lib().gillb200_softmax_rows(x.data_ptr(), x.stride(0), _DT[x.dtype], scale, rows, n, out.data_ptr(),
+                                      out.stride(0), _DT[out.dtype], _stream()), "gillb200_softmax_rows")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# small kernels
+# ---------------------------------------------------------------------------------------------------------------
+def gather_add_rows(table: torch.Tensor, idx: torch.Tensor, x: Optional[torch.Tensor] = None, idx_offset: int = 0,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i] = (x[i] if x is given else 0) + table[idx[i] + idx_offset]; table [V,D] 16-bit, idx int64 [rows]."""
+    assert idx.dtype == torch.int64 and idx.is_contiguous() and table.is_contiguous()
+    rows, D = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((rows, D), device=table.device, dtype=table.dtype)
+    if x is not None:
+        assert x.is_contiguous() and x.dtype == table.dtype and x.numel() == rows * D
+    check(lib().gillb200_gather_add_rows(_ptr(x), table.data_ptr(), idx.data_ptr(), idx_offset, rows, D,
+                                         _DT[table.dtype], out.data_ptr(), _stream()), "gillb200_gather_add_rows")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=x.dtype)
+    check(lib().gillb200_upsample2x(x.data_ptr(), B, H, W, C, out.data_ptr(), _stream()), "gillb200_upsample2x")
+    return out
+
+
+def im2col3x3(x: torch.Tensor, stride: int, ld_out: Optional[int] = None) -> torch.Tensor:
+    """NHWC x -> [B*Ho*Wo, ld_out] patches (k = (ky*3+kx)*C + c), zero padded to ld_out columns."""
+    B, H, W, C = x.shape
+    assert x.is_contiguous()
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    ld_out = ld_out or 9 * C
+    out = torch.empty((B * Ho * Wo, ld_out), device=x.device, dtype=x.dtype)
+    check(lib().gillb200_im2col3x3(x.data_ptr(), B, H, W, C, stride, out.data_ptr(), ld_out, _stream()),
+          "gillb200_im2col3x3")
+    return out
+
+
+def plms_step(eps_pair: torch.Tensor, guidance: float, ets: torch.Tensor, head: int, mode: int, c_sample: float,
+              c_eps: float, latents: torch.Tensor, cur_sample: torch.Tensor, lat16_pair: Optional[torch.Tensor]):
+    """In-place fused CFG + PLMS update (see gillb200_plms_step). eps_pair [2,n...]; ets [4,n] fp32; latents fp32."""
+    n = latents.numel()
+    assert eps_pair.numel() == 2 * n and ets.numel() == 4 * n and cur_sample.numel() == n
+    assert latents.dtype == torch.float32 and ets.dtype == torch.float32 and cur_sample.dtype == torch.float32
+    check(lib().gillb200_plms_step(eps_pair.data_ptr(), _DT[eps_pair.dtype], guidance, ets.data_ptr(), head, mode,
+                                   c_sample, c_eps, latents.data_ptr(), cur_sample.data_ptr(), _ptr(lat16_pair),
+                                   _DT[lat16_pair.dtype] if lat16_pair is not None else 0, n, _stream()),
+          "gillb200_plms_step")
+
+
+def image_to_u8(x: torch.Tensor, channels: int = 3) -> torch.Tensor:
+    """x NHWC [B,H,W,ld>=channels] -> uint8 [B,H,W,channels] = round(clamp(x/2+0.5,0,1)*255)."""
+    B, H, W, ld = x.shape
+    assert x.is_contiguous()
+    out = torch.empty((B, H, W, channels), device=x.device, dtype=torch.uint8)
+    check(lib().gillb200_image_to_u8(x.data_ptr(), _DT[x.dtype], B * H * W, ld, channels, out.data_ptr(), _stream()),
+          "gillb200_image_to_u8")
+    return out
+
+
+def l2norm_rows(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    _chk2d(x, "x")
+    assert x.dtype == torch.float32
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib().gillb200_l2norm_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), out.stride(0),
+                                     _DT[out_dtype], _stream()), "gillb200_l2norm_rows")
+    return out
+
+
+def cast_add(x: torch.Tensor, y: Optional[torch.Tensor], out_dtype: torch.dtype, *, y_period: int = 0,
+             out_lo: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = cast(x + y[i % y_period]) elementwise over contiguous tensors; optional bf16 residue."""
+    assert x.is_contiguous() and (y is None or y.is_contiguous())
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    check(lib().gillb200_cast_add(x.data_ptr(), _DT[x.dtype], _ptr(y), _DT[y.dtype] if y is not None else 0, y_period,
+                                  out.data_ptr(), _DT[out.dtype], _ptr(out_lo), x.numel(), _stream()),
+          "gillb200_cast_add")
+    return out
+
+
+def attn_small_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float, *,
+                   out: torch.Tensor, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 attention for short sequences: q [B,Lq,*], k/v [B,Lk,*] fp32 views (head h at columns h*128)."""
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    check(lib().gillb200_attn_small_f32(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                        v.data_ptr(), v.stride(1), v.stride(0), B, heads, 128, Lq, Lk, scale,
+                                        out.data_ptr(), out.stride(1), out.stride(0), _DT[out.dtype], _ptr(out_lo),
+                                        _stream()), "gillb200_attn_small_f32")
     return out

@@ -1,0 +1,103 @@
+"""Frozen OPT decoder forward on the libgillb200 kernels (the `self.lm(...)` call of gill/models.py:465).
+
+The reference calls HF `OPTForCausalLM(inputs_embeds=..., use_cache=False, output_hidden_states=True)` on the WHOLE
+sequence at every decode step and consumes only `hidden_states[-1]` (all positions) and `logits[:, -1]`. This class
+computes exactly those two things: one fused-QKV tcgen05 GEMM, one causal flash-attention launch, out_proj / fc1 / fc2
+GEMMs with bias + ReLU + residual in their epilogues, fp32 residual stream, and the tied lm_head only on the last
+position of each sequence.
+"""
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+SD = Dict[str, torch.Tensor]
+
+
+class OPTB200:
+    def __init__(self, sd: SD, hidden: int, layers: int, heads: int, ffn: int, device="cuda", dtype=torch.bfloat16):
+        """sd: OPTForCausalLM-named state dict (`model.decoder.*`); weights are stored bf16, biases / norms fp32."""
+        self.D, self.L, self.H, self.F = hidden, layers, heads, ffn
+        self.hd = hidden // heads
+        if self.hd != 128:
+            raise ValueError(f"OPTB200 supports head_dim 128 (OPT-6.7B family), got {self.hd}")
+        self.dev, self.dt = torch.device(device), dtype
+        f32 = torch.float32
+        p = "model.decoder."
+        g = lambda k, dt=None: sd[k].to(self.dev, dt or dtype).contiguous()
+        self.embed = g(p + "embed_tokens.weight")
+        self.pos = g(p + "embed_positions.weight")
+        self.layers = []
+        for i in range(layers):
+            l = f"{p}layers.{i}."
+            self.layers.append(dict(
+                ln1_w=g(l + "self_attn_layer_norm.weight", f32), ln1_b=g(l + "self_attn_layer_norm.bias", f32),
+                qkv_w=torch.cat([g(l + f"self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj")], 0),
+                qkv_b=torch.cat([g(l + f"self_attn.{n}.bias", f32) for n in ("q_proj", "k_proj", "v_proj")], 0),
+                o_w=g(l + "self_attn.out_proj.weight"), o_b=g(l + "self_attn.out_proj.bias", f32),
+                ln2_w=g(l + "final_layer_norm.weight", f32), ln2_b=g(l + "final_layer_norm.bias", f32),
+                fc1_w=g(l + "fc1.weight"), fc1_b=g(l + "fc1.bias", f32),
+                fc2_w=g(l + "fc2.weight"), fc2_b=g(l + "fc2.bias", f32)))
+        self.lnf_w, self.lnf_b = g(p + "final_layer_norm.weight", f32), g(p + "final_layer_norm.bias", f32)
+
+    @classmethod
+    def random_init(cls, hidden, layers, heads, ffn, vocab, max_pos=2048, seed=0, device="cuda", std=0.02):
+        """Seeded HF-style init generated directly on the device (no pretrained weights exist offline)."""
+        g = torch.Generator(device=device).manual_seed(seed)
+        n = lambda *s: (torch.randn(*s, generator=g, device=device, dtype=torch.float32) * std).to(torch.bfloat16)
+        p = "model.decoder."
+        sd = {p + "embed_tokens.weight": n(vocab, hidden), p + "embed_positions.weight": n(max_pos + 2, hidden)}
+        for i in range(layers):
+            l = f"{p}layers.{i}."
+            for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                sd[l + f"self_attn.{nm}.weight"], sd[l + f"self_attn.{nm}.bias"] = n(hidden, hidden), n(hidden)
+            sd[l + "fc1.weight"], sd[l + "fc1.bias"] = n(ffn, hidden), n(ffn)
+            sd[l + "fc2.weight"], sd[l + "fc2.bias"] = n(hidden, ffn), n(hidden)
+            for nm in ("self_attn_layer_norm", "final_layer_norm"):
+                sd[l + nm + ".weight"] = torch.ones(hidden, device=device)
+                sd[l + nm + ".bias"] = torch.zeros(hidden, device=device)
+        sd[p + "final_layer_norm.weight"] = torch.ones(hidden, device=device)
+        sd[p + "final_layer_norm.bias"] = torch.zeros(hidden, device=device)
+        return cls(sd, hidden, layers, heads, ffn, device=device)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def get_input_embeddings(self):
+        return self.embed
+
+    def embed_tokens(self, ids: torch.Tensor) -> torch.Tensor:
+        """`self.input_embeddings(ids)` (gill/models.py:620, :529, :709): [..] int64 -> [.., D]."""
+        flat = ids.reshape(-1).to(self.dev, torch.int64).contiguous()
+        return ops.gather_add_rows(self.embed, flat).view(*ids.shape, self.D)
+
+    @torch.no_grad()
+    def forward(self, inputs_embeds: torch.Tensor, need_logits: bool = True):
+        """inputs_embeds [B,T,D] -> (hidden_states[-1] [B,T,D] in the model dtype, last-position logits [B,V] fp32)."""
+        B, T, D = inputs_embeds.shape
+        H, hd = self.H, self.hd
+        x = inputs_embeds.to(self.dev, self.dt).contiguous().view(B * T, D)
+        pos_idx = torch.arange(T, device=self.dev, dtype=torch.int64).repeat(B)
+        h16 = ops.gather_add_rows(self.pos, pos_idx, x=x, idx_offset=2)           # + embed_positions(pos + 2)
+        h = ops.cast_add(h16, None, torch.float32)                                # fp32 residual stream
+        for ly in self.layers:
+            n = ops.layernorm(h, ly["ln1_w"], ly["ln1_b"], 1e-5, out_dtype=self.dt)
+            qkv = ops.gemm(n, ly["qkv_w"], bias=ly["qkv_b"]).view(B, T, 3 * D)
+            a = ops.attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], H, hd, hd ** -0.5, causal=True)
+            h = ops.gemm(a.view(B * T, D), ly["o_w"], bias=ly["o_b"], residual=h, out_dtype=torch.float32)
+            n = ops.layernorm(h, ly["ln2_w"], ly["ln2_b"], 1e-5, out_dtype=self.dt)
+            f = ops.gemm(n, ly["fc1_w"], bias=ly["fc1_b"], act="relu")
+            h = ops.gemm(f, ly["fc2_w"], bias=ly["fc2_b"], residual=h, out_dtype=torch.float32)
+        hs = ops.layernorm(h, self.lnf_w, self.lnf_b, 1e-5, out_dtype=self.dt).view(B, T, D)
+        logits = None
+        if need_logits:
+            last = hs[:, -1, :].contiguous()
+            logits = ops.gemm(last, self.embed, out_dtype=torch.float32)          # tied lm_head, last position only
+        return hs, logits
+
+    def __call__(self, inputs_embeds=None, use_cache=False, output_hidden_states=True, **kw):
+        """HF-shaped result for the reference's call site: `.logits[:, -1, :]` and `.hidden_states[-1]` are valid."""
+        if inputs_embeds is None:
+            raise ValueError("OPTB200 is driven with inputs_embeds (gill/models.py:465)")
+        hs, logits = self.forward(inputs_embeds)
+        return SimpleNamespace(logits=logits[:, None, :], hidden_states=(hs,))

@@ -1,0 +1,507 @@
+"""Stable Diffusion v1.5 image emission on the libgillb200 kernels: UNet denoising loop, PLMS scheduler, VAE decoder.
+
+Drop-in for the object the reference calls at gill/models.py:730-731
+    self.sd_pipe(prompt_embeds=gen_emb, generator=g, guidance_scale=7.5, num_inference_steps=50).images
+whose control flow is restated by gill/custom_sd.py:567-666 (the arithmetic lives in diffusers==0.17.1).
+
+B200-first layout decisions
+  * activations are NHWC fp16 (the reference runs SD in fp16): a [B,H,W,C] tensor IS the [B*H*W, C] token matrix, so
+    conv <-> transformer transitions are views, 1x1 convs are plain GEMMs and 3x3 convs are implicit GEMMs whose taps
+    are TMA box shifts (no im2col buffer);
+  * attention heads are stored padded to 64/128/192 columns (zero weight rows), so every TMA box is a full 128-byte
+    swizzled row; the padding is folded into the projection weights at load time;
+  * GEGLU value/gate rows are interleaved so the gate is applied in the GEMM epilogue;
+  * everything that does not depend on the latent is hoisted out of the 51-step loop: the time-embedding MLP and all
+    22 resnet time projections (a [51, sum_c] table built once), the 16 cross-attention K/V pairs (once per prompt),
+    the PLMS coefficients (host scalars);
+  * CFG + PLMS is one fused elementwise kernel; the VAE epilogue writes uint8 NHWC on the device.
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+SD = Dict[str, torch.Tensor]
+
+UNET_CFG = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+                cross_attention_dim=768, heads=8, norm_groups=32, has_attn_down=(True, True, True, False),
+                has_attn_up=(False, True, True, True))
+VAE_CFG = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+               norm_groups=32, scaling_factor=0.18215)
+
+
+def _hd_pad(hd: int) -> int:
+    for p in (64, 128, 192):
+        if hd <= p:
+            return p
+    raise ValueError(f"head dim {hd} > 192 not supported by the fused attention kernel")
+
+
+def _conv_w(w: torch.Tensor, dt) -> torch.Tensor:
+    """[Co, Ci, 3, 3] -> [Co, 9*Ci], k = (ky*3+kx)*Ci + c."""
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(dt).contiguous()
+
+
+def _pad_heads_rows(w: torch.Tensor, heads: int, hd: int, hp: int) -> torch.Tensor:
+    """[heads*hd, K] -> [heads*hp, K] with zero rows in each head's padding."""
+    out = torch.zeros((heads, hp, w.shape[1]), dtype=w.dtype, device=w.device)
+    out[:, :hd] = w.view(heads, hd, -1)
+    return out.view(heads * hp, -1)
+
+
+def _pad_heads_cols(w: torch.Tensor, heads: int, hd: int, hp: int) -> torch.Tensor:
+    """[N, heads*hd] -> [N, heads*hp] with zero columns in each head's padding."""
+    out = torch.zeros((w.shape[0], heads, hp), dtype=w.dtype, device=w.device)
+    out[:, :, :hd] = w.view(w.shape[0], heads, hd)
+    return out.view(w.shape[0], heads * hp)
+
+
+def plms_table(num_inference_steps: int = 50, num_train_timesteps: int = 1000, beta_start=0.00085, beta_end=0.012):
+    """Host-side PNDM/PLMS schedule (diffusers PNDMScheduler with SD-1.5's scheduler_config: scaled_linear betas,
+    skip_prk_steps, steps_offset 1, set_alpha_to_one False). Returns [(timestep, c_sample, c_eps, mode)] for the
+    n+1 UNet evaluations: x' = c_sample * x - c_eps * e'. mode selects the multistep formula (see plms_step)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+    ac = torch.cumprod(1.0 - betas, dim=0)
+    final = ac[0]
+    ratio = num_train_timesteps // num_inference_steps
+    ts = (torch.arange(0, num_inference_steps) * ratio).round().long() + 1
+    plms = torch.cat([ts[:-1], ts[-2:-1], ts[-1:]]).flip(0).tolist()
+    out, n_ets, counter = [], 0, 0
+    for t in plms:
+        prev_t, tt = t - ratio, t
+        if counter != 1:
+            n_ets = min(n_ets + 1, 4)
+        else:
+            prev_t, tt = t, t + ratio
+        mode = 0 if (n_ets == 1 and counter == 0) else 1 if (n_ets == 1 and counter == 1) else n_ets
+        a_t = ac[tt]
+        a_p = ac[prev_t] if prev_t >= 0 else final
+        b_t, b_p = 1 - a_t, 1 - a_p
+        cs = (a_p / a_t) ** 0.5
+        ce = (a_p - a_t) / (a_t * b_p ** 0.5 + (a_t * b_t * a_p) ** 0.5)
+        out.append((int(t), float(cs), float(ce), mode))
+        counter += 1
+    return out
+
+
+class _Out:
+    def __init__(self, images):
+        self.images = images
+        self.nsfw_content_detected = None
+
+
+# ================================================================================================================
+class UNetB200:
+    """SD-1.5 UNet2DConditionModel forward on B200 kernels. Weights: diffusers-named state dict (any float dtype)."""
+
+    def __init__(self, sd: SD, cfg=None, device="cuda", dtype=torch.float16):
+        self.cfg = cfg or UNET_CFG
+        self.dev, self.dt = torch.device(device), dtype
+        self.G = self.cfg["norm_groups"]
+        self.heads = self.cfg["heads"]
+        self.w: Dict[str, torch.Tensor] = {}
+        self._temb_names: List[str] = []
+        self._temb_off: Dict[str, tuple] = {}
+        self._pack(sd)
+        self._temb_table = None
+        self._temb_steps = None
+
+    # ------------------------------------------------------------------------------------------------ packing
+    def _put(self, k, v, dt=None):
+        self.w[k] = v.to(self.dev, dt or self.dt).contiguous()
+
+    def _pack_resnet(self, sd, p):
+        f32 = torch.float32
+        for n in ("norm1", "norm2"):
+            self._put(f"{p}.{n}.weight", sd[f"{p}.{n}.weight"], f32)
+            self._put(f"{p}.{n}.bias", sd[f"{p}.{n}.bias"], f32)
+        for n in ("conv1", "conv2"):
+            self._put(f"{p}.{n}.weight", _conv_w(sd[f"{p}.{n}.weight"], self.dt))
+            self._put(f"{p}.{n}.bias", sd[f"{p}.{n}.bias"], f32)
+        if f"{p}.conv_shortcut.weight" in sd:
+            w = sd[f"{p}.conv_shortcut.weight"]
+            self._put(f"{p}.conv_shortcut.weight", w.reshape(w.shape[0], w.shape[1]))
+            self._put(f"{p}.conv_shortcut.bias", sd[f"{p}.conv_shortcut.bias"], f32)
+        if f"{p}.time_emb_proj.weight" in sd:
+            self._temb_names.append(p)
+
+    def _pack_transformer(self, sd, p, c):
+        f32 = torch.float32
+        H = self.heads
+        hd = c // H
+        hp = _hd_pad(hd)
+        for n in ("norm",):
+            self._put(f"{p}.{n}.weight", sd[f"{p}.{n}.weight"], f32)
+            self._put(f"{p}.{n}.bias", sd[f"{p}.{n}.bias"], f32)
+        for n in ("proj_in", "proj_out"):
+            w = sd[f"{p}.{n}.weight"]
+            self._put(f"{p}.{n}.weight", w.reshape(w.shape[0], w.shape[1]))
+            self._put(f"{p}.{n}.bias", sd[f"{p}.{n}.bias"], f32)
+        t = p + ".transformer_blocks.0"
+        for n in ("norm1", "norm2", "norm3"):
+            self._put(f"{t}.{n}.weight", sd[f"{t}.{n}.weight"], f32)
+            self._put(f"{t}.{n}.bias", sd[f"{t}.{n}.bias"], f32)
+        q, k, v = (sd[f"{t}.attn1.to_{x}.weight"].float() for x in "qkv")
+        self._put(f"{t}.attn1.qkv", torch.cat([_pad_heads_rows(x, H, hd, hp) for x in (q, k, v)], 0))
+        self._put(f"{t}.attn1.out.weight", _pad_heads_cols(sd[f"{t}.attn1.to_out.0.weight"].float(), H, hd, hp))
+        self._put(f"{t}.attn1.out.bias", sd[f"{t}.attn1.to_out.0.bias"], f32)
+        self._put(f"{t}.attn2.q", _pad_heads_rows(sd[f"{t}.attn2.to_q.weight"].float(), H, hd, hp))
+        self._put(f"{t}.attn2.kv", torch.cat([_pad_heads_rows(sd[f"{t}.attn2.to_{x}.weight"].float(), H, hd, hp)
+                                              for x in "kv"], 0))
+        self._put(f"{t}.attn2.out.weight", _pad_heads_cols(sd[f"{t}.attn2.to_out.0.weight"].float(), H, hd, hp))
+        self._put(f"{t}.attn2.out.bias", sd[f"{t}.attn2.to_out.0.bias"], f32)
+        # GEGLU: interleave (value_j, gate_j) rows so that the gate is applied in the GEMM epilogue
+        w, b = sd[f"{t}.ff.net.0.proj.weight"], sd[f"{t}.ff.net.0.proj.bias"]
+        half = w.shape[0] // 2
+        self._put(f"{t}.ff.geglu.weight", torch.stack([w[:half], w[half:]], 1).reshape(w.shape[0], w.shape[1]))
+        self._put(f"{t}.ff.geglu.bias", torch.stack([b[:half], b[half:]], 1).reshape(-1), f32)
+        self._put(f"{t}.ff.out.weight", sd[f"{t}.ff.net.2.weight"])
+        self._put(f"{t}.ff.out.bias", sd[f"{t}.ff.net.2.bias"], f32)
+        self._tf_meta = getattr(self, "_tf_meta", {})
+        self._tf_meta[p] = (c, hd, hp)
+
+    def _pack(self, sd):
+        cfg, f32 = self.cfg, torch.float32
+        boc = cfg["block_out_channels"]
+        self.temb_dim = boc[0] * 4
+        for n in ("time_embedding.linear_1", "time_embedding.linear_2"):
+            self._put(n + ".weight", sd[n + ".weight"], f32)
+            self._put(n + ".bias", sd[n + ".bias"], f32)
+        w = _conv_w(sd["conv_in.weight"], self.dt)  # [320, 36] -> zero-pad K to 64 for the im2col GEMM
+        wp = torch.zeros((w.shape[0], 64), dtype=w.dtype)
+        wp[:, : w.shape[1]] = w
+        self._put("conv_in.weight", wp)
+        self._put("conv_in.bias", sd["conv_in.bias"], f32)
+        self.tf_layers: List[str] = []
+        ch = boc[0]
+        for i, c in enumerate(boc):
+            for j in range(cfg["layers_per_block"]):
+                self._pack_resnet(sd, f"down_blocks.{i}.resnets.{j}")
+                ch = c
+                if cfg["has_attn_down"][i]:
+                    self._pack_transformer(sd, f"down_blocks.{i}.attentions.{j}", c)
+                    self.tf_layers.append(f"down_blocks.{i}.attentions.{j}")
+            if i < len(boc) - 1:
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                self._put(p + ".weight", _conv_w(sd[p + ".weight"], self.dt))
+                self._put(p + ".bias", sd[p + ".bias"], f32)
+        self._pack_resnet(sd, "mid_block.resnets.0")
+        self._pack_transformer(sd, "mid_block.attentions.0", ch)
+        self.tf_layers.append("mid_block.attentions.0")
+        self._pack_resnet(sd, "mid_block.resnets.1")
+        for i, c in enumerate(reversed(boc)):
+            for j in range(cfg["layers_per_block"] + 1):
+                self._pack_resnet(sd, f"up_blocks.{i}.resnets.{j}")
+                if cfg["has_attn_up"][i]:
+                    self._pack_transformer(sd, f"up_blocks.{i}.attentions.{j}", c)
+                    self.tf_layers.append(f"up_blocks.{i}.attentions.{j}")
+            if i < len(boc) - 1:
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                self._put(p + ".weight", _conv_w(sd[p + ".weight"], self.dt))
+                self._put(p + ".bias", sd[p + ".bias"], f32)
+        self._put("conv_norm_out.weight", sd["conv_norm_out.weight"], f32)
+        self._put("conv_norm_out.bias", sd["conv_norm_out.bias"], f32)
+        self._put("conv_out.weight", _conv_w(sd["conv_out.weight"], self.dt))
+        self._put("conv_out.bias", sd["conv_out.bias"], f32)
+        # all resnet time projections as one [sum_c, 1280] matrix
+        ws, bs, off = [], [], 0
+        for p in self._temb_names:
+            w = sd[p + ".time_emb_proj.weight"]
+            ws.append(w)
+            bs.append(sd[p + ".time_emb_proj.bias"])
+            self._temb_off[p] = (off, off + w.shape[0])
+            off += w.shape[0]
+        self._put("temb_proj_all.weight", torch.cat(ws, 0), torch.float16)
+        self._put("temb_proj_all.bias", torch.cat(bs, 0), f32)
+        self.temb_total = off
+
+    # ------------------------------------------------------------------------------------------------ hoisted work
+    def prepare_timesteps(self, timesteps: List[int]):
+        """Time-embedding MLP + every resnet's time projection for all timesteps of the schedule: [n_steps, sum_c].
+        Depends only on the weights and the schedule, so it is built once (cached per schedule)."""
+        key = tuple(timesteps)
+        if self._temb_steps == key:
+            return
+        boc0 = self.cfg["block_out_channels"][0]
+        half = boc0 // 2
+        t = torch.tensor(timesteps, dtype=torch.float32, device=self.dev)
+        freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=self.dev) / half)
+        args = t[:, None] * freqs[None]
+        emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)  # flip_sin_to_cos
+        n = len(timesteps)
+        # tiny [n,320]x[320,1280] MLP on the tensor cores with fp16 hi+lo operands (~22 mantissa bits)
+        def split(x):
+            hi = x.to(torch.float16)
+            return hi, (x - hi.float()).to(torch.float16)
+        w1, w2 = self.w["time_embedding.linear_1.weight"], self.w["time_embedding.linear_2.weight"]
+        w1h, w1l = split(w1)
+        w2h, w2l = split(w2)
+        eh, el = split(emb)
+        h = ops.gemm(eh, w1h, a2=el, a2_mode=2, bias=self.w["time_embedding.linear_1.bias"], out_dtype=torch.float32)
+        h = h + ops.gemm(eh, w1l, out_dtype=torch.float32)
+        h = torch.nn.functional.silu(h)
+        hh, hl = split(h)
+        te = ops.gemm(hh, w2h, a2=hl, a2_mode=2, bias=self.w["time_embedding.linear_2.bias"], out_dtype=torch.float32)
+        te = te + ops.gemm(hh, w2l, out_dtype=torch.float32)
+        act = torch.nn.functional.silu(te)
+        ah, al = split(act)
+        self._temb_table = ops.gemm(ah, self.w["temb_proj_all.weight"], a2=al, a2_mode=2,
+                                    bias=self.w["temb_proj_all.bias"], out_dtype=torch.float32)  # [n, sum_c]
+        self._temb_steps = key
+
+    def precompute_ctx(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Cross-attention K/V of all transformer layers for a batch of conditionings [B2,77,768]: once per prompt."""
+        B2, L, D = ctx.shape
+        c2 = ctx.to(self.dt).reshape(B2 * L, D).contiguous()
+        out = {}
+        for p in self.tf_layers:
+            kv = ops.gemm(c2, self.w[f"{p}.transformer_blocks.0.attn2.kv"])
+            out[p] = kv.view(B2, L, -1)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ blocks
+    def _resnet(self, x, p, step, x2=None):
+        w, G = self.w, self.G
+        B, H, W, _ = x.shape
+        lo, hi = self._temb_off[p]
+        rb = self._temb_table[step : step + 1, lo:hi]
+        n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-5, silu=True, x2=x2)
+        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], rowbias=rb)
+        n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-5, silu=True)
+        if (p + ".conv_shortcut.weight") in w:
+            M = B * H * W
+            if x2 is not None:
+                sc = ops.gemm(x.view(M, -1), w[p + ".conv_shortcut.weight"], a2=x2.view(M, -1), a2_mode=1,
+                              bias=w[p + ".conv_shortcut.bias"])
+            else:
+                sc = ops.gemm(x.view(M, -1), w[p + ".conv_shortcut.weight"], bias=w[p + ".conv_shortcut.bias"])
+            sc = sc.view(B, H, W, -1)
+        else:
+            assert x2 is None
+            sc = x
+        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc)
+
+    def _transformer(self, x, p, ctx_kv):
+        w, G, Hh = self.w, self.G, self.heads
+        B, H, W, C = x.shape
+        _, hd, hp = self._tf_meta[p]
+        M, L = B * H * W, H * W
+        t = p + ".transformer_blocks.0"
+        n = ops.groupnorm(x, w[p + ".norm.weight"], w[p + ".norm.bias"], G, 1e-6)
+        h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"])
+        # self attention
+        n1 = ops.layernorm(h, w[t + ".norm1.weight"], w[t + ".norm1.bias"], 1e-5)
+        qkv = ops.gemm(n1, w[t + ".attn1.qkv"]).view(B, L, 3 * Hh * hp)
+        a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
+                          hd ** -0.5)
+        h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h)
+        # cross attention against the precomputed K/V of the conditioning
+        n2 = ops.layernorm(h, w[t + ".norm2.weight"], w[t + ".norm2.bias"], 1e-5)
+        q = ops.gemm(n2, w[t + ".attn2.q"]).view(B, L, Hh * hp)
+        kv = ctx_kv[p]
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5)
+        h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h)
+        # GEGLU feed-forward
+        n3 = ops.layernorm(h, w[t + ".norm3.weight"], w[t + ".norm3.bias"], 1e-5)
+        g = ops.gemm(n3, w[t + ".ff.geglu.weight"], bias=w[t + ".ff.geglu.bias"], act="geglu")
+        h = ops.gemm(g, w[t + ".ff.out.weight"], bias=w[t + ".ff.out.bias"], residual=h)
+        out = ops.gemm(h, w[p + ".proj_out.weight"], bias=w[p + ".proj_out.bias"], residual=x.view(M, C))
+        return out.view(B, H, W, C)
+
+    def _conv_s2(self, x, p):
+        B, H, W, C = x.shape
+        cols = ops.im2col3x3(x, 2)
+        o = ops.gemm(cols, self.w[p + ".weight"], bias=self.w[p + ".bias"])
+        return o.view(B, H // 2, W // 2, -1)
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, step: int, ctx_kv: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """x: NHWC [B2,H,W,4] fp16 latent pair; step: index into the prepared timestep table; returns eps NHWC."""
+        cfg, w = self.cfg, self.w
+        boc = cfg["block_out_channels"]
+        B, H, W, _ = x.shape
+        cols = ops.im2col3x3(x, 1, ld_out=64)
+        h = ops.gemm(cols, w["conv_in.weight"], bias=w["conv_in.bias"]).view(B, H, W, boc[0])
+        skips = [h]
+        for i in range(len(boc)):
+            for j in range(cfg["layers_per_block"]):
+                h = self._resnet(h, f"down_blocks.{i}.resnets.{j}", step)
+                if cfg["has_attn_down"][i]:
+                    h = self._transformer(h, f"down_blocks.{i}.attentions.{j}", ctx_kv)
+                skips.append(h)
+            if i < len(boc) - 1:
+                h = self._conv_s2(h, f"down_blocks.{i}.downsamplers.0.conv")
+                skips.append(h)
+        h = self._resnet(h, "mid_block.resnets.0", step)
+        h = self._transformer(h, "mid_block.attentions.0", ctx_kv)
+        h = self._resnet(h, "mid_block.resnets.1", step)
+        for i in range(len(boc)):
+            for j in range(cfg["layers_per_block"] + 1):
+                h = self._resnet(h, f"up_blocks.{i}.resnets.{j}", step, x2=skips.pop())
+                if cfg["has_attn_up"][i]:
+                    h = self._transformer(h, f"up_blocks.{i}.attentions.{j}", ctx_kv)
+            if i < len(boc) - 1:
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"])
+        n = ops.groupnorm(h, w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.G, 1e-5, silu=True)
+        return ops.conv3x3(n, w["conv_out.weight"], bias=w["conv_out.bias"], block_n=32)
+
+
+# ================================================================================================================
+class VAEDecoderB200:
+    """AutoencoderKL.decode + the uint8 epilogue of gill/custom_sd.py:385-392 on B200 kernels (NHWC fp16)."""
+
+    def __init__(self, sd: SD, cfg=None, device="cuda", dtype=torch.float16):
+        self.cfg = cfg or VAE_CFG
+        self.dev, self.dt = torch.device(device), dtype
+        self.G = self.cfg["norm_groups"]
+        self.w: Dict[str, torch.Tensor] = {}
+        f32 = torch.float32
+        for k, v in sd.items():
+            if k.endswith("conv_shortcut.weight") or k == "post_quant_conv.weight":
+                self.w[k] = v.reshape(v.shape[0], v.shape[1]).to(self.dev, dtype).contiguous()
+            elif v.dim() == 4:
+                self.w[k] = _conv_w(v, dtype).to(self.dev)
+            elif v.dim() == 2:
+                self.w[k] = v.to(self.dev, dtype).contiguous()
+            else:
+                self.w[k] = v.to(self.dev, f32).contiguous()
+        # fold latents / scaling_factor and the 1x1 post_quant_conv into one tiny 4x4 map applied before conv_in
+        lc = self.cfg["latent_channels"]
+        pq = sd["post_quant_conv.weight"].reshape(lc, lc).float() / self.cfg["scaling_factor"]
+        self.pq_w = pq.to(self.dev)
+        self.pq_b = sd["post_quant_conv.bias"].float().to(self.dev)
+        w = self.w["decoder.conv_in.weight"]  # [512, 36] -> K padded to 64
+        wp = torch.zeros((w.shape[0], 64), dtype=w.dtype, device=self.dev)
+        wp[:, : w.shape[1]] = w
+        self.w["decoder.conv_in.weight"] = wp
+        w = self.w["decoder.conv_out.weight"]  # [3, 9*128] -> 8 rows so the epilogue can use vector stores
+        wp = torch.zeros((8, w.shape[1]), dtype=w.dtype, device=self.dev)
+        wp[: w.shape[0]] = w
+        self.w["decoder.conv_out.weight"] = wp
+        b = torch.zeros(8, dtype=f32, device=self.dev)
+        b[: self.cfg["out_channels"]] = self.w["decoder.conv_out.bias"]
+        self.w["decoder.conv_out.bias"] = b
+
+    def _resnet(self, x, p):
+        w, G = self.w, self.G
+        B, H, W, _ = x.shape
+        n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-6, silu=True)
+        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"])
+        n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-6, silu=True)
+        if (p + ".conv_shortcut.weight") in w:
+            sc = ops.gemm(x.view(B * H * W, -1), w[p + ".conv_shortcut.weight"],
+                          bias=w[p + ".conv_shortcut.bias"]).view(B, H, W, -1)
+        else:
+            sc = x
+        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc)
+
+    def _mid_attention(self, x):
+        """Single-head attention over H*W tokens with head dim 512: too wide for the fused kernel's smem tiles, and
+        it runs once per image, so it is three GEMMs around a row softmax (scores kept fp32)."""
+        w, a = self.w, "decoder.mid_block.attentions.0"
+        B, H, W, C = x.shape
+        L = H * W
+        n = ops.groupnorm(x, w[a + ".group_norm.weight"], w[a + ".group_norm.bias"], self.G, 1e-6).view(B * L, C)
+        q = ops.gemm(n, w[a + ".to_q.weight"], bias=w[a + ".to_q.bias"])
+        k = ops.gemm(n, w[a + ".to_k.weight"], bias=w[a + ".to_k.bias"])
+        o = torch.empty((B * L, C), device=x.device, dtype=x.dtype)
+        for b in range(B):
+            nb = n[b * L : (b + 1) * L]
+            vT = ops.gemm(w[a + ".to_v.weight"], nb, bias=w[a + ".to_v.bias"], bias_along_m=True)   # [C, L] = V^T
+            s = ops.gemm(q[b * L : (b + 1) * L], k[b * L : (b + 1) * L], out_dtype=torch.float32)   # [L, L]
+            pr = ops.softmax_rows(s, C ** -0.5, x.dtype)
+            ops.gemm(pr, vT, out=o[b * L : (b + 1) * L])
+        out = ops.gemm(o, w[a + ".to_out.0.weight"], bias=w[a + ".to_out.0.bias"], residual=x.view(B * L, C))
+        return out.view(B, H, W, C)
+
+    def decode_u8(self, latents: torch.Tensor) -> torch.Tensor:
+        """latents NHWC [B,h,w,4] (fp32 or fp16) -> uint8 NHWC [B,8h,8w,3]."""
+        cfg, w = self.cfg, self.w
+        boc = cfg["block_out_channels"]
+        B, H, W, lc = latents.shape
+        # latents/0.18215 -> post_quant_conv: a 4x4 channel map on 16 K elements per image (host-side torch glue)
+        z = (latents.float().reshape(-1, lc) @ self.pq_w.T + self.pq_b).to(self.dt).view(B, H, W, lc).contiguous()
+        cols = ops.im2col3x3(z, 1, ld_out=64)
+        h = ops.gemm(cols, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"]).view(B, H, W, boc[-1])
+        h = self._resnet(h, "decoder.mid_block.resnets.0")
+        h = self._mid_attention(h)
+        h = self._resnet(h, "decoder.mid_block.resnets.1")
+        for i in range(len(boc)):
+            for j in range(cfg["layers_per_block"] + 1):
+                h = self._resnet(h, f"decoder.up_blocks.{i}.resnets.{j}")
+            if i < len(boc) - 1:
+                p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"])
+        n = ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], self.G, 1e-6,
+                          silu=True)
+        img = ops.conv3x3(n, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"], block_n=32)
+        return ops.image_to_u8(img, cfg["out_channels"])
+
+
+# ================================================================================================================
+class StableDiffusionB200:
+    """Callable with the `sd_pipe` signature GILL uses (gill/models.py:730; gill/custom_sd.py:477-496)."""
+
+    def __init__(self, unet: UNetB200, vae: VAEDecoderB200, negative_prompt_embeds: torch.Tensor):
+        """negative_prompt_embeds: the (77,768) CLIP-text embedding of "" that gill/custom_sd.py:319-357 recomputes on
+        every call; it is a constant of the pipeline, so it is supplied once here."""
+        self.unet, self.vae = unet, vae
+        self.device = unet.dev
+        self.neg = negative_prompt_embeds.to(unet.dev, unet.dt).reshape(1, 77, -1)
+        self.latent_hw = 64
+        self._graphs = {}
+
+    @torch.no_grad()
+    def denoise(self, prompt_embeds: torch.Tensor, latents_nchw: torch.Tensor, guidance_scale: float = 7.5,
+                num_inference_steps: int = 50, trace: Optional[list] = None) -> torch.Tensor:
+        """gill/custom_sd.py:606-651. Returns the final latents, NHWC fp32 [b,h,w,4]."""
+        b = prompt_embeds.shape[0]
+        table = plms_table(num_inference_steps)
+        self.unet.prepare_timesteps([t for t, _, _, _ in table])
+        ctx = torch.cat([self.neg.expand(b, -1, -1), prompt_embeds.to(self.unet.dt)], 0)      # custom_sd.py:371
+        ctx_kv = self.unet.precompute_ctx(ctx)
+        lat = latents_nchw.float().permute(0, 2, 3, 1).contiguous()                             # NHWC fp32
+        n = lat.numel()
+        ets = torch.empty((4, n), device=lat.device, dtype=torch.float32)
+        cur = torch.empty(n, device=lat.device, dtype=torch.float32)
+        pair = torch.cat([lat, lat], 0).to(self.unet.dt)                                        # custom_sd.py:630
+        head = 0
+        for i, (t, cs, ce, mode) in enumerate(table):                                           # custom_sd.py:628
+            eps = self.unet.forward(pair, i, ctx_kv)                                            # :633-638
+            ops.plms_step(eps, guidance_scale, ets, head, mode, cs, ce, lat, cur, pair)         # :641-646
+            if mode != 1:
+                head = (head + 1) & 3
+            if trace is not None:
+                trace.append(lat.clone())
+        return lat
+
+    @torch.no_grad()
+    def __call__(self, prompt=None, prompt_embeds: Optional[torch.Tensor] = None, generator=None,
+                 guidance_scale: float = 7.5, num_inference_steps: int = 50, latents: Optional[torch.Tensor] = None,
+                 output_type: str = "pil", height: int = 512, width: int = 512, **unused):
+        if prompt_embeds is None:
+            raise ValueError("gill_b200 StableDiffusion takes `prompt_embeds` (GILL never passes a text prompt; "
+                             "gill/models.py:730)")
+        if prompt_embeds.dim() != 3 or prompt_embeds.shape[1] != 77:
+            raise ValueError(f"prompt_embeds must be (b, 77, 768), got {tuple(prompt_embeds.shape)}")
+        if height % 8 != 0 or width % 8 != 0:                                                    # custom_sd.py:424
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        b = prompt_embeds.shape[0]
+        shape = (b, 4, height // 8, width // 8)
+        if latents is None:                                                                      # custom_sd.py:466-470
+            latents = torch.randn(shape, generator=generator, device=self.device, dtype=torch.float16)
+        elif tuple(latents.shape) != shape:
+            raise ValueError(f"Unexpected latents shape, got {tuple(latents.shape)}, expected {shape}")
+        lat = self.denoise(prompt_embeds.to(self.device), latents.to(self.device), guidance_scale, num_inference_steps)
+        u8 = self.vae.decode_u8(lat)                                                            # custom_sd.py:654
+        if output_type == "uint8":
+            return _Out(u8)
+        arr = u8.cpu().numpy()                                                                  # custom_sd.py:391
+        if output_type == "np":
+            return _Out(arr.astype("float32") / 255.0)
+        from PIL import Image
+
+        return _Out([Image.fromarray(a) for a in arr])                                           # custom_sd.py:661

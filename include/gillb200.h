@@ -122,6 +122,51 @@ typedef struct gillb200_attn_args {
 
 int gillb200_attention(const gillb200_attn_args* args, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Normalisation / softmax (fp32 statistics, 16-byte vectorised).
+ *   layernorm : F.layer_norm over the last dim; optional bf16 residue output (split-precision GEMM operand).
+ *   groupnorm : nn.GroupNorm (+ optional SiLU) over an NHWC tensor that may be the channel concatenation of two
+ *               tensors (UNet up blocks, cat([h, skip])); writes the normalised concatenation.
+ * Replace the norms inside nn.Transformer (gill/layers.py:20-22), OPT (gill/models.py:465) and the UNet / VAE
+ * (gill/custom_sd.py:633-638, :388).
+ * ------------------------------------------------------------------------------------------------------------- */
+int gillb200_layernorm(const void* x, long long ldx, int in_dtype, const float* w, const float* b, float eps, int rows,
+                       int C, void* out, long long ldo, int out_dtype, void* out_lo, void* stream);
+long long gillb200_groupnorm_workspace_bytes(int B, int G);
+int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1, int dtype, int B, int HW, int G, const float* w,
+                       const float* b, float eps, int silu, void* out, int out_dtype, void* workspace, void* stream);
+int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype, float scale, long long rows, int n, void* out,
+                          long long ldo, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Small kernels around the tensor-core path.
+ *   gather_add_rows : out[i] = (x ? x[i] : 0) + table[idx[i] + idx_offset]  (embedding / learned-position lookup,
+ *                     gill/models.py:620, :529, :709 and OPTLearnedPositionalEmbedding behind models.py:465)
+ *   upsample2x      : nearest 2x, NHWC (UNet / VAE up blocks)
+ *   im2col3x3       : explicit patches for the stride-2 downsamplers and the 4-channel conv_in
+ *   plms_step       : classifier-free guidance + PNDM/PLMS update fused (gill/custom_sd.py:641-646)
+ *   image_to_u8     : (x/2+0.5).clamp(0,1) -> uint8 NHWC (gill/custom_sd.py:389-391 + numpy_to_pil)
+ *   l2norm_rows     : x / ||x|| (gill/models.py:674)
+ *   cast_add        : out = cast(x + y[i % y_period]) with optional bf16 residue (gill/layers.py:32 `x + input_embs`)
+ *   attn_small_f32  : fp32 attention for the GILLMapper's short sequences (nn.MultiheadAttention, layers.py:43)
+ * ------------------------------------------------------------------------------------------------------------- */
+int gillb200_gather_add_rows(const void* x, const void* table, const long long* idx, long long idx_offset,
+                             long long rows, int D, int dtype, void* out, void* stream);
+int gillb200_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream);
+int gillb200_im2col3x3(const void* x, int B, int H, int W, int C, int stride, void* out, long long ld_out, void* stream);
+int gillb200_plms_step(const void* eps_pair, int eps_dtype, float guidance, float* ets, int head, int mode,
+                       float c_sample, float c_eps, float* latents, float* cur_sample, void* lat16_pair, int lat16_dtype,
+                       long long n, void* stream);
+int gillb200_image_to_u8(const void* x, int dtype, long long pixels, int ldx, int channels, void* out, void* stream);
+int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int n, void* out, long long ldo, int out_dtype,
+                         void* stream);
+int gillb200_cast_add(const void* x, int x_dtype, const void* y, int y_dtype, long long y_period, void* out,
+                      int out_dtype, void* out_lo, long long n, void* stream);
+int gillb200_attn_small_f32(const float* q, long long ldq, long long q_bs, const float* k, long long ldk, long long k_bs,
+                            const float* v, long long ldv, long long v_bs, int B, int H, int hd, int Lq, int Lk,
+                            float scale, void* out, long long ldo, long long o_bs, int out_dtype, void* out_lo,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
