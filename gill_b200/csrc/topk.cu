@@ -127,20 +127,27 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
 #pragma unroll
         for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
         if (__any_sync(0xffffffffu, mx > tv[KMAX - 1])) {
+          // Slow path. Per-lane bitmask of columns above this lane's threshold, OR-reduced over the warp; then a real
+          // loop over only the columns that hit, re-reading that single column from TMEM (the TMEM address is a
+          // run-time operand, so no dynamic register indexing and nothing for the compiler to flatten).
+          uint32_t m = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float s = __uint_as_float(r[j]);
+          for (int j = 0; j < 32; ++j) m |= (__uint_as_float(r[j]) > tv[KMAX - 1] ? 1u : 0u) << j;
+          uint32_t hits = __reduce_or_sync(0xffffffffu, m);
+#pragma unroll 1
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            float s = __uint_as_float(tmem_ld_32x32b_x1(taddr + c + j));
+            tmem_wait_ld();
             const long long nloc = n0 + c + j;
-            const bool pass = s > tv[KMAX - 1] && nloc < e.n_local;
-            if (__any_sync(0xffffffffu, pass)) {  // warp-uniform: the insert body only runs for columns that hit
-              if (pass) {
-                if (e.n_exclude > 0) {
-                  const long long gidx = e.index_base + nloc;
-                  for (int x = 0; x < e.n_exclude; ++x)
-                    if (e.exclude[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
-                }
-                topk_insert(tv, ti, s, static_cast<int>(nloc));
+            if (s > tv[KMAX - 1] && nloc < e.n_local) {
+              if (e.n_exclude > 0) {
+                const long long gidx = e.index_base + nloc;
+                for (int x = 0; x < e.n_exclude; ++x)
+                  if (e.exclude[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
               }
+              topk_insert(tv, ti, s, static_cast<int>(nloc));
             }
           }
         }

@@ -393,7 +393,8 @@ def denoise_loop(unet_sd: SD, prompt_embeds: torch.Tensor, negative_embeds: torc
     sched = PNDM()
     timesteps = sched.set_timesteps(num_inference_steps)               # custom_sd.py:607
     latents = latents * sched.init_noise_sigma                          # custom_sd.py:472
-    ctx = torch.cat([negative_embeds, prompt_embeds])                   # custom_sd.py:371
+    neg = negative_embeds.expand(prompt_embeds.shape[0], -1, -1)        # custom_sd.py:351-357 (repeat per prompt)
+    ctx = torch.cat([neg, prompt_embeds])                               # custom_sd.py:371
     trace = []
     for t in timesteps:                                                 # custom_sd.py:628
         inp = torch.cat([latents] * 2)                                  # :630 (scale_model_input is identity)
