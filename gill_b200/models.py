@@ -1,0 +1,564 @@
+"""Drop-in for the inference surface of the reference's `gill/models.py`: `GILLArgs`, `GILLModel` (`generate`),
+`GILL` (`generate_for_images_and_texts`) and `load_gill`, executing on the libgillb200 kernels.
+
+Same names, argument order, defaults, return structure and error behaviour as the reference (file:line cited inline).
+Differences that are deliberate and documented in DESIGN.md:
+  * the three frozen third-party models cannot be downloaded here, so they are injected: `lm` (an `OPTB200`),
+    `sd_pipe` (a `StableDiffusionB200`) and optionally `visual_model` (CLIP vision tower: out of scope, SURVEY §8f-1;
+    prompts may instead carry already CLIP-encoded images as tensors);
+  * `generate` speculatively appends the 8 [IMG] embeddings to every forward: OPT is causal, so the logits at the last
+    real position are unchanged, and when [IMG0] is emitted the same forward already contains the next step's hidden
+    states -- one prefill replaces the reference's two no-cache passes on the image-emission path;
+  * `generate_for_images_and_texts_batch` runs several independent prompt lists through the same path at once.
+"""
+import glob
+import json
+import os
+import pickle as pkl
+from collections import namedtuple
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import layers, ops, retrieval
+from .opt import OPTB200
+
+try:  # PIL is only needed for image prompts / PIL outputs
+    from PIL import Image, UnidentifiedImageError
+except Exception:  # pragma: no cover
+    Image, UnidentifiedImageError = None, OSError
+
+
+def truncate_caption(caption: str) -> str:
+    """Truncate captions at periods and newlines (behaviour of gill/utils.py:32-40)."""
+    caption = caption.strip("\n")
+    cut = caption.find("\n") + 1
+    if cut <= 0:
+        cut = caption.find(".") + 1
+    return caption[:cut] if cut > 0 else caption
+
+
+def get_image_from_url(url: str):
+    """gill/utils.py:24-29."""
+    import requests
+    from io import BytesIO
+
+    response = requests.get(url)
+    img = Image.open(BytesIO(response.content))
+    return img.resize((224, 224)).convert("RGB")
+
+
+class GILLArgs:  # gill/models.py:21-36
+    freeze_lm: bool = True
+    freeze_vm: bool = True
+    opt_version: str = "facebook/opt-6.7b"
+    visual_encoder: str = "openai/clip-vit-large-patch14"
+    n_visual_tokens: int = 1
+    task: str = "captioning"
+    ret_emb_dim: Optional[int] = 256
+    gen_emb_dim: Optional[int] = 256
+    text_emb_layers: List[int] = [-1]
+    gen_token_idx: List[int] = [0]
+    retrieval_token_idx: List[int] = [0]
+    text_fc_mode: str = "gill_mapper"
+    ret_text_fc_mode: str = "linear"
+    num_tokens: int = 8
+    num_clip_tokens: int = 77
+
+
+class _InputEmbeddings:
+    """`self.input_embeddings` (gill/models.py:75): callable ids -> embeddings over the OPT table, `.weight` exposed."""
+
+    def __init__(self, lm: OPTB200):
+        self.lm = lm
+
+    @property
+    def weight(self):
+        return self.lm.embed
+
+    @property
+    def embedding_dim(self):
+        return self.lm.D
+
+    def __call__(self, ids: torch.Tensor) -> torch.Tensor:
+        return self.lm.embed_tokens(ids)
+
+
+class _LinearB200(nn.Linear):
+    """nn.Linear parameters, forward on the tcgen05 GEMM (split-precision activations, fp32 accumulate)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        hi = torch.empty(x2.shape, device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+        ops.cast_add(x2, None, torch.bfloat16, out=hi, out_lo=lo)
+        w = self.weight.detach().to(torch.bfloat16).contiguous()
+        b = self.bias.detach().float().contiguous() if self.bias is not None else None
+        o = ops.gemm(hi, w, a2=lo, a2_mode=2, bias=b, out_dtype=torch.float32)
+        return o.view(*shp[:-1], -1).to(x.dtype)
+
+
+class GILLModel(nn.Module):
+    def __init__(self, tokenizer, args: GILLArgs = GILLArgs(), lm: Optional[OPTB200] = None, visual_model=None,
+                 feature_extractor=None, visual_hidden_size: int = 1024):
+        super().__init__()
+        self.tokenizer = tokenizer
+        self.feature_extractor = feature_extractor
+        self.image_token = getattr(tokenizer, "cls_token_id", None)
+        self.args = args
+        self.num_tokens = args.num_tokens
+        self.num_clip_tokens = args.num_clip_tokens
+        if lm is None:
+            raise ValueError("gill_b200.GILLModel needs an OPTB200 `lm` (pretrained OPT weights cannot be fetched "
+                             "offline; build one with OPTB200(state_dict, ...) or OPTB200.random_init(...))")
+        self.lm = lm
+        self.opt_version = args.opt_version
+        self.retrieval_token_idx = args.retrieval_token_idx
+        self.gen_token_idx = args.gen_token_idx
+        if lm.embed.shape[0] != len(tokenizer):                                    # models.py:73
+            raise ValueError(f"OPT embedding table has {lm.embed.shape[0]} rows but the tokenizer has {len(tokenizer)}"
+                             " tokens; resize the table (resize_token_embeddings) before constructing OPTB200")
+        self.input_embeddings = _InputEmbeddings(lm)                               # models.py:75
+        self.visual_model = visual_model
+        self.visual_model_name = args.visual_encoder
+        hidden_size = visual_hidden_size
+        in_dim = lm.D
+        embedding_dim = in_dim * args.n_visual_tokens                              # models.py:98
+        self.ret_text_hidden_fcs = nn.ModuleList([])
+        self.gen_text_hidden_fcs = nn.ModuleList([])
+        for layer_idx in args.text_emb_layers:                                     # models.py:102-120
+            if layer_idx == -1 or layer_idx == lm.L:
+                self.ret_text_hidden_fcs.append(layers.TextFcLayer(
+                    in_dim, args.ret_emb_dim, num_input_tokens=args.num_tokens, num_output_tokens=1,
+                    mode=args.ret_text_fc_mode))
+                self.gen_text_hidden_fcs.append(layers.TextFcLayer(
+                    in_dim, args.gen_emb_dim, num_input_tokens=args.num_tokens,
+                    num_output_tokens=args.num_clip_tokens, mode=args.text_fc_mode))
+            else:
+                raise ValueError(f"Only the last hidden layer is available from the B200 OPT forward "
+                                 f"(text_emb_layers={args.text_emb_layers}); the shipped model uses [-1].")
+        self.visual_embeddings = _LinearB200(hidden_size, embedding_dim)           # models.py:122
+        self.visual_fc = _LinearB200(hidden_size, args.ret_emb_dim)                # models.py:125
+        self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))         # models.py:126
+
+    # -------------------------------------------------------------------------------------------- visual prefix
+    def get_visual_embs(self, pixel_values: torch.Tensor, mode: str = "captioning"):
+        """gill/models.py:129-152. `pixel_values` may be raw pixels (needs a CLIP `visual_model`) or already pooled
+        CLIP features [n, hidden] (BASELINE config 5 feeds CLIP-encoded images)."""
+        if mode not in ["captioning", "retrieval", "generation"]:
+            raise ValueError(f"mode should be one of ['captioning', 'retrieval', 'generation'], got {mode} instead.")
+        if pixel_values.dim() == 2:
+            encoder_outputs = pixel_values
+        else:
+            if self.visual_model is None:
+                raise NotImplementedError("the CLIP vision tower is outside the B200 hot path (SURVEY.md §8f-1); pass "
+                                          "pooled CLIP features [n, hidden] or a visual_model")
+            encoder_outputs = self.visual_model(pixel_values).pooler_output
+        if mode == "captioning":
+            v = self.visual_embeddings(encoder_outputs)
+            return torch.reshape(v, (v.shape[0], self.args.n_visual_tokens, -1))
+        if mode == "retrieval":
+            v = self.visual_fc(encoder_outputs)
+            return torch.reshape(v, (v.shape[0], 1, -1))
+        return torch.zeros((pixel_values.shape[0], 1, 768), device=pixel_values.device)
+
+    def train(self, mode=True):  # gill/models.py:155-161 (returns None, like the reference)
+        super(GILLModel, self).train(mode=mode)
+
+    # -------------------------------------------------------------------------------------------- decode
+    def _postprocess_logits(self, logits, i, min_word_tokens, ret_scale_factor, gen_scale_factor, filter_value):
+        """gill/models.py:475-489 (in place, same order of operations)."""
+        logits[:, self.retrieval_token_idx[1:]] = filter_value
+        logits[:, self.gen_token_idx[1:]] = filter_value
+        if (self.retrieval_token_idx or self.gen_token_idx) and self.retrieval_token_idx[0] != -1 \
+                and self.gen_token_idx[0] != -1:
+            if i < min_word_tokens:
+                logits[:, self.retrieval_token_idx] = filter_value
+                logits[:, self.gen_token_idx] = filter_value
+            else:
+                if ret_scale_factor > 1:
+                    logits[:, self.retrieval_token_idx[0]] = logits[:, self.retrieval_token_idx[0]].abs() * ret_scale_factor
+                if gen_scale_factor > 1:
+                    logits[:, self.gen_token_idx[0]] = logits[:, self.gen_token_idx[0]].abs() * gen_scale_factor
+        return logits
+
+    def generate(self, embeddings=torch.FloatTensor, max_len: int = 32, temperature: float = 0.0, top_p: float = 1.0,
+                 min_word_tokens: int = 0, ret_scale_factor: float = 1.0, gen_scale_factor: float = 1.0,
+                 filter_value: float = -float("Inf"), speculative: bool = True):
+        """gill/models.py:443-532. Returns (out ids [N,T'], [hidden_states[-1] per step], [last logits per step]).
+
+        speculative=True (default): each forward runs over [embeddings | 8 speculative [IMG] embeddings]. Causality
+        makes the first T positions identical to the reference's forward; if step i emits [IMG0] (batch 1), step i+1's
+        forward IS the speculative one and is not recomputed."""
+        import torch.nn.functional as F
+
+        with torch.no_grad():
+            out = None
+            output_embeddings, output_logits = [], []
+            dev = self.lm.dev
+            embeddings = embeddings.to(dev)
+            img_ids = torch.tensor(self.retrieval_token_idx, dtype=torch.int64, device=dev)
+            can_spec = speculative and embeddings.shape[0] == 1 and self.retrieval_token_idx[0] != -1 \
+                and self.retrieval_token_idx == self.gen_token_idx
+            img_embs = self.input_embeddings(img_ids[None, :]) if can_spec else None
+            cached = None  # (hidden_states over T+8, logits at position T+7) carried over from a speculative hit
+            for i in range(max_len):
+                T = embeddings.shape[1]
+                if cached is not None:
+                    hs, logits = cached
+                    cached = None
+                    spec_hs = None
+                elif can_spec:
+                    full = torch.cat([embeddings, img_embs.to(embeddings.dtype)], dim=1)
+                    hs_full, lg2 = self.lm.forward(full, logit_positions=[T - 1, T + self.num_tokens - 1])
+                    hs, logits = hs_full[:, :T], lg2[:, 0]
+                    spec_hs = (hs_full, lg2[:, 1])
+                else:
+                    hs, lg = self.lm.forward(embeddings, logit_positions=[T - 1])
+                    logits, spec_hs = lg[:, 0], None
+                for idx in self.args.text_emb_layers:
+                    output_embeddings.append(hs)                                          # models.py:467-468
+                logits = logits.float().clone()                                            # models.py:470
+                if top_p == 1.0:
+                    logits = logits.cpu()                                                  # models.py:471-472
+                output_logits.append(logits)
+                self._postprocess_logits(logits, i, min_word_tokens, ret_scale_factor, gen_scale_factor, filter_value)
+                if temperature == 0.0:
+                    if top_p != 1.0:
+                        raise ValueError("top_p cannot be set if temperature is 0 (greedy decoding).")  # :493
+                    next_token = torch.argmax(logits, keepdim=True, dim=-1)                # models.py:494
+                else:
+                    logits = logits / temperature                                          # models.py:496
+                    if top_p < 1.0:                                                        # models.py:499-512
+                        assert top_p > 0, f"top_p should be above 0, got {top_p} instead."
+                        sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+                        cumulative_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
+                        sorted_indices_to_remove = cumulative_probs > top_p
+                        sorted_indices_to_remove[..., 1:] = sorted_indices_to_remove[..., :-1].clone()
+                        sorted_indices_to_remove[..., 0] = 0
+                        for j in range(sorted_indices.shape[0]):
+                            indices_to_remove = sorted_indices[j, sorted_indices_to_remove[j, :]]
+                            logits[j, indices_to_remove] = filter_value
+                    token_weights = logits.exp()                                           # models.py:514
+                    next_token = torch.multinomial(token_weights, 1)                       # models.py:515
+                hit = next_token.shape[0] == 1 and next_token.item() == self.retrieval_token_idx[0]
+                if hit:                                                                    # models.py:518-520
+                    assert self.retrieval_token_idx == self.gen_token_idx, (self.retrieval_token_idx, self.gen_token_idx)
+                    next_token = torch.tensor(self.retrieval_token_idx)[None, :].long().to(dev)
+                    if spec_hs is not None:
+                        cached = spec_hs
+                else:
+                    next_token = next_token.long().to(dev)
+                out = next_token if out is None else torch.cat([out, next_token], dim=-1)  # models.py:524-527
+                next_embedding = self.input_embeddings(next_token)                         # models.py:529
+                embeddings = torch.cat([embeddings, next_embedding.to(embeddings.dtype)], dim=1)
+        return out, output_embeddings, output_logits
+
+
+class GILL(nn.Module):
+    def __init__(self, tokenizer, model_args: Optional[GILLArgs] = None, path_array: Optional[List[str]] = None,
+                 emb_matrix: Optional[torch.Tensor] = None, load_sd: bool = False, num_gen_images: int = 1,
+                 decision_model_path: Optional[str] = None, *, lm: Optional[OPTB200] = None, sd_pipe=None,
+                 visual_model=None, feature_extractor=None):
+        super().__init__()
+        self.model = GILLModel(tokenizer, model_args, lm=lm, visual_model=visual_model,
+                               feature_extractor=feature_extractor)
+        self.path_array = path_array
+        self.emb_matrix = emb_matrix
+        self.load_sd = load_sd
+        self.num_gen_images = num_gen_images
+        self.idx2dec = {0: "gen", 1: "ret", 2: "same"}
+        self.decision_model = None
+        if load_sd:                                                                        # models.py:549-551
+            if sd_pipe is None:
+                raise ValueError("load_sd=True needs an `sd_pipe` (StableDiffusionB200); SD-1.5 weights cannot be "
+                                 "downloaded offline")
+            self.sd_pipe = sd_pipe
+        if decision_model_path is not None:                                                # models.py:553-561
+            print("Loading decision model...")
+            self.decision_model = nn.Sequential(*[nn.Dropout(0.5), _LinearB200(4096, 2)])
+            mlp_checkpoint = torch.load(decision_model_path, map_location="cpu")
+            self.decision_model.load_state_dict(mlp_checkpoint["state_dict"], strict=True)
+            self.decision_model.eval()
+
+    def __call__(self, images, tgt_tokens=None, caption_len=None, generate: bool = False, num_words: int = 32,
+                 temperature: float = 1.0, top_p: float = 1.0, ret_scale_factor: float = 1.0,
+                 gen_scale_factor: float = 1.0, min_word_tokens: int = 0, mode: str = "captioning",
+                 concat_captions: bool = False, input_prefix: Optional[str] = None):
+        if generate:                                                                       # models.py:568-571
+            return self.model.generate(images, num_words, temperature=temperature, top_p=top_p,
+                                       min_word_tokens=min_word_tokens, ret_scale_factor=ret_scale_factor,
+                                       gen_scale_factor=gen_scale_factor)
+        raise NotImplementedError("the training forward (gill/models.py:164-441) is outside the B200 hot path")
+
+    # -------------------------------------------------------------------------------------------- prompt encoding
+    def _encode_prompts(self, prompts: List, always_add_bos: bool):
+        """gill/models.py:600-626. Extra prompt types: a tensor [hidden] / [n, hidden] of pooled CLIP features, or a
+        tensor [n_visual_tokens, D] of ready visual-prefix embeddings."""
+        m = self.model
+        dev, dt = m.lm.dev, m.lm.dt
+        input_embs, input_ids = [], []
+        add_bos = True
+        for p in prompts:
+            if Image is not None and isinstance(p, Image.Image):
+                if m.feature_extractor is None:
+                    raise NotImplementedError("PIL prompts need a feature_extractor + CLIP visual_model "
+                                              "(SURVEY.md §8f-1); pass CLIP-encoded tensors instead")
+                pixel_values = m.feature_extractor(p.convert("RGB"), return_tensors="pt").pixel_values[0, ...]
+                pixel_values = pixel_values.to(device=dev, dtype=dt)[None, ...]
+                input_embs.append(m.get_visual_embs(pixel_values, mode="captioning").to(dt))
+            elif isinstance(p, torch.Tensor):
+                t = p.to(dev)
+                if t.shape[-1] == m.lm.D:
+                    input_embs.append(t.reshape(1, -1, m.lm.D).to(dt))
+                else:
+                    input_embs.append(m.get_visual_embs(t.reshape(-1, t.shape[-1]).to(dt), mode="captioning")
+                                      .reshape(1, -1, m.lm.D).to(dt))
+            elif type(p) == str:
+                text_ids = m.tokenizer(p, add_special_tokens=add_bos, return_tensors="pt").input_ids.to(dev)
+                if not always_add_bos:
+                    add_bos = False
+                input_embs.append(m.input_embeddings(text_ids))
+                input_ids.append(text_ids)
+            else:
+                raise ValueError(f"Input prompts should be either PIL.Image.Image or str types, got {type(p)} instead.")
+        return torch.cat(input_embs, dim=1), (torch.cat(input_ids, dim=1) if input_ids else None)
+
+    # -------------------------------------------------------------------------------------------- the hot path
+    def generate_for_images_and_texts(
+            self, prompts: List, num_words: int = 0, min_word_tokens: int = 0, ret_scale_factor: float = 1.0,
+            gen_scale_factor: float = 1.0, top_p: float = 1.0, temperature: float = 0.0, max_num_rets: int = 1,
+            generator=None, always_add_bos: bool = False, guidance_scale: float = 7.5, num_inference_steps: int = 50):
+        """gill/models.py:582-762: encode prompts, decode, and for each emitted [IMG0] run retrieval, the decision
+        head, the GILLMapper and Stable Diffusion. Same return structure as the reference."""
+        m = self.model
+        with torch.no_grad():
+            input_embs, input_ids = self._encode_prompts(prompts, always_add_bos)
+            if num_words == 0:
+                raise NotImplementedError("Generation not implemented for num_words=0.")     # models.py:629
+            elif num_words > 0:
+                generated_ids, generated_embeddings, _ = m.generate(
+                    input_embs, num_words, min_word_tokens=min_word_tokens, temperature=temperature, top_p=top_p,
+                    ret_scale_factor=ret_scale_factor, gen_scale_factor=gen_scale_factor)
+                embeddings = generated_embeddings[-1][:, input_embs.shape[1]:]                # models.py:633
+                newline_token_id = m.tokenizer("\n", add_special_tokens=False).input_ids[0]   # models.py:636-644
+                trunc_idx = 0
+                for j in range(generated_ids.shape[1]):
+                    if generated_ids[0, j] == newline_token_id:
+                        trunc_idx = j
+                        break
+                if trunc_idx > 0:
+                    generated_ids = generated_ids[:, :trunc_idx]
+                    embeddings = embeddings[:, :trunc_idx]
+            else:
+                raise ValueError
+
+            return_outputs = []
+            ids_host = generated_ids[0].tolist()
+            all_ret_idx = [i for i, x in enumerate(ids_host) if x == m.retrieval_token_idx[0]][:max_num_rets]  # :651
+            seen_image_idx = []
+            last_ret_idx = 0
+            if len(all_ret_idx) == 0:
+                caption = m.tokenizer.batch_decode(generated_ids, skip_special_tokens=True)[0]
+                return_outputs.append(truncate_caption(caption))
+            else:
+                for ret_idx in all_ret_idx:
+                    assert ids_host[ret_idx:ret_idx + m.num_tokens] == m.retrieval_token_idx, \
+                        (ids_host[ret_idx:ret_idx + m.num_tokens], m.retrieval_token_idx)     # models.py:661
+                    raw_emb = embeddings[:, ret_idx:ret_idx + m.num_tokens, :]                # (1, 8, 4096)
+                    assert len(m.args.text_emb_layers) == 1
+                    image_outputs = {"gen": [], "ret": [], "decision": None}
+                    ret_emb = None
+                    if self.emb_matrix is not None:
+                        ret_emb = m.ret_text_hidden_fcs[0](raw_emb.float(), None)[:, 0, :]    # models.py:673
+                        ret_emb = ops.l2norm_rows(ret_emb.float().contiguous(), self.emb_matrix.dtype)  # :674-675
+                        _, top_image_idx = retrieval.retrieval_topk(self.emb_matrix, ret_emb, 3,
+                                                                    exclude_idx=seen_image_idx)       # :676-683
+                        top_vals = _.cpu()[0].tolist()
+                        for rank_i, img_idx in enumerate(top_image_idx[0].tolist()):
+                            try:                                                               # models.py:686-693
+                                seen_image_idx.append(img_idx)
+                                img = get_image_from_url(self.path_array[img_idx])
+                                image_outputs["ret"].append((img, "ret", top_vals[rank_i]))
+                                if len(image_outputs) == max_num_rets:   # (sic) dict length, as in the reference
+                                    break
+                            except (UnidentifiedImageError, ConnectionError, OSError):
+                                pass
+                            except Exception as e:  # requests' own ConnectionError is an OSError subclass
+                                if e.__class__.__name__ != "ConnectionError":
+                                    raise
+                        if self.decision_model is not None:                                    # models.py:696-701
+                            decision_emb = raw_emb[:, 0, :]
+                            assert decision_emb.shape[1] == 4096, decision_emb.shape
+                            decision_logits = self.decision_model(decision_emb.float())
+                            probs = decision_logits.softmax(dim=-1).cpu().float().numpy().tolist()
+                            image_outputs["decision"] = [self.idx2dec[decision_logits.argmax().item()]] + probs
+                    else:
+                        image_outputs["decision"] = ["gen", [0, 1]]                            # models.py:704
+
+                    gen_prefix = "".join([f"[IMG{i}]" for i in range(m.args.num_tokens)])     # models.py:707-710
+                    gen_prefx_ids = m.tokenizer(gen_prefix, add_special_tokens=False,
+                                                return_tensors="pt").input_ids.to(m.lm.dev)
+                    gen_prefix_embs = m.input_embeddings(gen_prefx_ids)
+                    gen_emb = m.gen_text_hidden_fcs[0](raw_emb.float(), gen_prefix_embs.float())  # (1, 77, 768)
+                    if gen_emb.shape[1] != 77:                                                 # models.py:712-719
+                        print(f"Padding {gen_emb.shape} with zeros")
+                        bs, clip_emb = gen_emb.shape[0], 768
+                        gen_emb = gen_emb.reshape(bs, -1, clip_emb)
+                        seq_len = gen_emb.shape[1]
+                        gen_emb = torch.cat([gen_emb, torch.zeros((bs, 77 - seq_len, clip_emb), device=gen_emb.device,
+                                                                  dtype=gen_emb.dtype)], dim=1)
+                        print("Padded to", gen_emb.shape)
+                    gen_emb = gen_emb.repeat(self.num_gen_images, 1, 1)                        # models.py:721
+
+                    if self.load_sd:                                                           # models.py:724-731
+                        gen_max_bs = 8
+                        gen_images = []
+                        for i in range(0, self.num_gen_images, gen_max_bs):
+                            gen_images.extend(self.sd_pipe(
+                                prompt_embeds=gen_emb[i:i + gen_max_bs], generator=generator,
+                                guidance_scale=guidance_scale, num_inference_steps=num_inference_steps).images)
+                        if self.emb_matrix is not None and m.visual_model is not None:         # models.py:733-751
+                            all_gen_pixels = []
+                            for img in gen_images:
+                                pv = m.feature_extractor(img.resize((224, 224)).convert("RGB"),
+                                                         return_tensors="pt").pixel_values[0, ...]
+                                all_gen_pixels.append(pv.to(device=m.lm.dev, dtype=m.lm.dt))
+                            all_gen_pixels = torch.stack(all_gen_pixels, dim=0)
+                            gen_visual_embs = m.get_visual_embs(all_gen_pixels, mode="retrieval")
+                            gen_visual_embs = gen_visual_embs / gen_visual_embs.norm(dim=-1, keepdim=True)
+                            gen_visual_embs = gen_visual_embs.type(self.emb_matrix.dtype)
+                            gen_rank_scores = (gen_visual_embs @ ret_emb.T).squeeze()
+                            sorted_score_idx = torch.argsort(-gen_rank_scores)
+                            if self.num_gen_images > 1:
+                                image_outputs["gen"] = [(gen_images[idx], gen_rank_scores[idx].item())
+                                                        for idx in sorted_score_idx]
+                            else:
+                                image_outputs["gen"] = [(gen_images[0], gen_rank_scores.item())]
+                        else:
+                            # no bank (reference behaviour, models.py:753) or no CLIP tower to re-rank with (§8f-1)
+                            image_outputs["gen"] = [(gen_images[0], 0)]
+                    else:
+                        image_outputs["gen"] = [gen_emb]                                       # models.py:755
+
+                    caption = m.tokenizer.batch_decode(generated_ids[:, last_ret_idx:ret_idx],
+                                                       skip_special_tokens=True)[0]            # models.py:757-760
+                    last_ret_idx = ret_idx + 1
+                    return_outputs.append(truncate_caption(caption) + f" {gen_prefix}")
+                    return_outputs.append(image_outputs)
+        return return_outputs
+
+    # -------------------------------------------------------------------------------------------- batched emission
+    @torch.no_grad()
+    def emit_images_batch(self, input_embs: torch.Tensor, latents: Optional[torch.Tensor] = None, generator=None,
+                          guidance_scale: float = 7.5, num_inference_steps: int = 50, top_k: int = 0,
+                          output_type: str = "uint8"):
+        """B independent prompts of equal length through the forced-emission path the evals use
+        (`num_words=2, gen_scale_factor=1e5`, evals/generate_vist_images.py:72-73): one OPT prefill over
+        [prompt | 8 [IMG] embeddings], GILLMapper on the 8 [IMG] hidden states, optional retrieval top-k, SD in chunks
+        of 8 (models.py:726). Per-sample equivalent of `generate_for_images_and_texts`; returns a dict with
+        'images' (uint8 NHWC), 'gen_emb' [B,77,768], 'forced_ok' (bool per prompt: argmax after scaling is [IMG0]),
+        and optionally 'ret' = (values, indices)."""
+        m = self.model
+        B, P, D = input_embs.shape
+        img_ids = torch.tensor(m.retrieval_token_idx, dtype=torch.int64, device=m.lm.dev)
+        img_embs = m.input_embeddings(img_ids[None, :])                                        # (1, 8, D)
+        full = torch.cat([input_embs.to(m.lm.dev, m.lm.dt), img_embs.expand(B, -1, -1).to(m.lm.dt)], dim=1)
+        hs, lg = m.lm.forward(full, logit_positions=[P - 1])
+        logits = lg[:, 0].float()
+        m._postprocess_logits(logits, 0, 0, 1.0, 1e5, -float("Inf"))
+        forced_ok = logits.argmax(dim=-1) == m.retrieval_token_idx[0]
+        raw_emb = hs[:, P:P + m.num_tokens, :].float().contiguous()                             # (B, 8, D)
+        out = {"forced_ok": forced_ok}
+        if top_k > 0 and self.emb_matrix is not None:
+            ret_emb = m.ret_text_hidden_fcs[0](raw_emb, None)[:, 0, :]
+            q = ops.l2norm_rows(ret_emb.float().contiguous(), self.emb_matrix.dtype)
+            out["ret"] = retrieval.retrieval_topk(self.emb_matrix, q, top_k)
+        gen_emb = m.gen_text_hidden_fcs[0](raw_emb, img_embs.float())                          # (B, 77, 768)
+        out["gen_emb"] = gen_emb
+        if self.load_sd:
+            imgs = []
+            for i in range(0, B, 8):                                                           # models.py:726-731
+                lat = None if latents is None else latents[i:i + 8]
+                imgs.append(self.sd_pipe(prompt_embeds=gen_emb[i:i + 8], generator=generator, latents=lat,
+                                         guidance_scale=guidance_scale, num_inference_steps=num_inference_steps,
+                                         output_type=output_type).images)
+            out["images"] = torch.cat(imgs, 0) if output_type == "uint8" else sum(imgs, [])
+        return out
+
+    def get_log_likelihood_scores(self, prompts: List):
+        raise NotImplementedError("get_log_likelihood_scores (gill/models.py:764-807) needs full-vocabulary logits at "
+                                  "every position; it is not on the image-emission hot path")
+
+
+def load_gill(model_dir: str, load_ret_embs: bool = True, decision_model_fn: str = "decision_model.pth.tar", *,
+              tokenizer=None, lm: Optional[OPTB200] = None, sd_pipe=None, visual_model=None, feature_extractor=None,
+              device: str = "cuda") -> GILL:
+    """gill/models.py:810-902. Reads model_args.json, pretrained_ckpt.pth.tar (keys `module.model.*`) and the
+    cc3m*.npy pickles exactly like the reference. The frozen third-party models are injected (see module docstring)."""
+    model_args_path = os.path.join(model_dir, "model_args.json")
+    model_ckpt_path = os.path.join(model_dir, "pretrained_ckpt.pth.tar")
+    embs_paths = [s for s in glob.glob(os.path.join(model_dir, "cc3m*.npy"))]
+    if not os.path.exists(model_args_path):
+        raise ValueError(f"model_args.json does not exist in {model_dir}.")
+    if not os.path.exists(model_ckpt_path):
+        raise ValueError(f"pretrained_ckpt.pth.tar does not exist in {model_dir}.")
+    if not load_ret_embs or len(embs_paths) == 0:
+        if len(embs_paths) == 0:
+            print(f"cc3m.npy files do not exist in {model_dir}.")
+        print("Running the model without retrieval.")
+        path_array, emb_matrix = None, None
+    else:
+        path_array, emb_matrix = [], []
+        for p in embs_paths:                                                                   # models.py:831-835
+            with open(p, "rb") as wf:
+                train_embs_data = pkl.load(wf)
+                path_array.extend(train_embs_data["paths"])
+                emb_matrix.extend(train_embs_data["embeddings"])
+        emb_matrix = np.stack(emb_matrix, axis=0)
+        assert len(path_array) == emb_matrix.shape[0], (len(path_array), emb_matrix.shape)
+
+    with open(model_args_path, "r") as f:
+        model_kwargs = json.load(f)
+    if tokenizer is None:
+        from transformers import AutoTokenizer
+
+        tokenizer = AutoTokenizer.from_pretrained(model_kwargs["opt_version"], use_fast=False)   # models.py:845
+        if tokenizer.pad_token is None:
+            tokenizer.pad_token_id = tokenizer.eos_token_id
+        tokenizer.add_special_tokens({"cls_token": "<|image|>"})
+        for i in range(model_kwargs["num_tokens"]):
+            tokenizer.add_tokens(f"[IMG{i}]")
+    model_kwargs["retrieval_token_idx"] = []
+    for i in range(model_kwargs["num_tokens"]):                                                # models.py:853-860
+        ret_token_idx = tokenizer(f"[IMG{i}]", add_special_tokens=False).input_ids
+        assert len(ret_token_idx) == 1, ret_token_idx
+        model_kwargs["retrieval_token_idx"].append(ret_token_idx[0])
+    model_kwargs["gen_token_idx"] = model_kwargs["retrieval_token_idx"]                        # models.py:862
+    args = namedtuple("args", model_kwargs)(**model_kwargs)
+    decision_model_path = os.path.join(model_dir, decision_model_fn) if decision_model_fn is not None else None
+    if decision_model_path is not None and not os.path.exists(decision_model_path):
+        decision_model_path = None
+
+    model = GILL(tokenizer, args, path_array=path_array, emb_matrix=emb_matrix, load_sd=sd_pipe is not None,
+                 num_gen_images=1, decision_model_path=decision_model_path, lm=lm, sd_pipe=sd_pipe,
+                 visual_model=visual_model, feature_extractor=feature_extractor)
+    model = model.eval()
+    model = model.bfloat16()
+    model = model.to(device)
+
+    checkpoint = torch.load(model_ckpt_path, map_location="cpu")                               # models.py:880-884
+    state_dict = {k.replace("module.", ""): v for k, v in checkpoint["state_dict"].items()}
+    img_token_embeddings = state_dict["model.input_embeddings.weight"].cpu().detach()
+    del state_dict["model.input_embeddings.weight"]
+    model.load_state_dict(state_dict, strict=False)
+    with torch.no_grad():                                                                      # models.py:890-893
+        if "share_ret_gen" in model_kwargs:
+            assert model_kwargs["share_ret_gen"], "Model loading only supports share_ret_gen=True for now."
+        lm.embed[-model_kwargs["num_tokens"]:, :].copy_(img_token_embeddings.to(lm.embed.dtype))
+    if load_ret_embs and len(embs_paths) > 0:                                                  # models.py:895-900
+        model.emb_matrix = retrieval.prepare_bank(emb_matrix, model.model.logit_scale.detach())
+    return model

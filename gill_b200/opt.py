@@ -72,8 +72,9 @@ class OPTB200:
         return ops.gather_add_rows(self.embed, flat).view(*ids.shape, self.D)
 
     @torch.no_grad()
-    def forward(self, inputs_embeds: torch.Tensor, need_logits: bool = True):
-        """inputs_embeds [B,T,D] -> (hidden_states[-1] [B,T,D] in the model dtype, last-position logits [B,V] fp32)."""
+    def forward(self, inputs_embeds: torch.Tensor, need_logits: bool = True, logit_positions=None):
+        """inputs_embeds [B,T,D] -> (hidden_states[-1] [B,T,D] in the model dtype, logits fp32).
+        logits: [B,V] at the last position, or [B,len(logit_positions),V] at the requested positions."""
         B, T, D = inputs_embeds.shape
         H, hd = self.H, self.hd
         x = inputs_embeds.to(self.dev, self.dt).contiguous().view(B * T, D)
@@ -90,7 +91,10 @@ class OPTB200:
             h = ops.gemm(f, ly["fc2_w"], bias=ly["fc2_b"], residual=h, out_dtype=torch.float32)
         hs = ops.layernorm(h, self.lnf_w, self.lnf_b, 1e-5, out_dtype=self.dt).view(B, T, D)
         logits = None
-        if need_logits:
+        if logit_positions is not None:
+            sel = hs[:, list(logit_positions), :].reshape(B * len(logit_positions), D).contiguous()
+            logits = ops.gemm(sel, self.embed, out_dtype=torch.float32).view(B, len(logit_positions), -1)
+        elif need_logits:
             last = hs[:, -1, :].contiguous()
             logits = ops.gemm(last, self.embed, out_dtype=torch.float32)          # tied lm_head, last position only
         return hs, logits
