@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the GILL image-emission hot path on B200 (contract: see the task's bench.py section).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libgillb200 kernels)
+    python bench.py --impl reference --gpus N ...            # reference arm: the path's CPU implementation (oracle port)
+
+One step = one pass of the hot path over one batch of synthetic prompts: BASELINE.json configs[3]
+  8 prompts x (2x4 visual-prefix embeddings + BOS + 64 token ids) -> OPT-6.7B prefill -> GILLMapper -> SD-1.5 UNet
+  51 evaluations (50-step PLMS, CFG 7.5) at 512x512 -> VAE decode -> uint8 images.
+Metric: images/sec (whole job, all ranks). The second half of BASELINE.json's metric (retrieval top-k QPS over a 3M-row
+bank, configs[2]) is measured in the same run and reported under "retrieval".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch
+
+BATCH = 8
+N_VIS, N_TXT = 8, 64          # 2 images x 4 visual tokens; 64 text tokens (+ BOS)
+UNET_GFLOP_PER_EVAL = 803.3   # BASELINE.md §2 (per sample-evaluation)
+VAE_GFLOP = 2510.0
+OPT_GFLOP_T81 = 1080.0        # one prefill over 73 + 8 tokens
+MAPPER_GFLOP = 2.644
+BANK_N, BANK_D, BANK_Q, BANK_K = 3_000_000, 768, 1024, 16
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the upper half of the samples == "under load" (the sampler also sees idle gaps)
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def make_inputs(rank):
+    """SURVEY.md §8d C4 recipe (seeds offset by rank so that every rank has its own prompts)."""
+    g = torch.Generator().manual_seed(21 + 1000 * rank)
+    vis = (torch.randn(BATCH, N_VIS, 4096, generator=g) * 0.05).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(22 + 1000 * rank)
+    ids = torch.cat([torch.full((BATCH, 1), 2, dtype=torch.int64),
+                     torch.randint(3, 50265, (BATCH, N_TXT), generator=g)], 1)
+    g = torch.Generator().manual_seed(42 + 1000 * rank)
+    lat = torch.randn(BATCH, 4, 64, 64, generator=g).to(torch.float16)
+    return vis, ids, lat
+
+
+def run_ours(args):
+    from gill_b200 import ops, synthetic
+    from gill_b200._lib import lib
+    from gill_b200 import retrieval
+
+    rank, world, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    pk = peaks()
+    t0 = time.time()
+    gill, wkind = synthetic.build_gill(dev, "opt-6.7b", tiny_sd=False, with_sd=True)
+    m = gill.model
+    vis_h, ids_h, lat_h = make_inputs(rank)
+    vis_p, ids_p, lat_p = vis_h.pin_memory(), ids_h.pin_memory(), lat_h.pin_memory()
+    vis_d, ids_d, lat_d = vis_h.to(dev), ids_h.to(dev), lat_h.to(dev)
+    out_host = torch.empty((BATCH, 512, 512, 3), dtype=torch.uint8).pin_memory()
+    setup_s = time.time() - t0
+
+    def hot_path(vis, ids, lat):
+        """device tensors in -> uint8 images on the device"""
+        txt = m.input_embeddings(ids)                                            # (B, 65, 4096) gather kernel
+        embs = torch.cat([vis, txt], dim=1)                                      # (B, 73, 4096)
+        return gill.emit_images_batch(embs, latents=lat)
+
+    def step_device():
+        return hot_path(vis_d, ids_d, lat_d)["images"]
+
+    def step_e2e():
+        v = vis_p.to(dev, non_blocking=True)
+        i = ids_p.to(dev, non_blocking=True)
+        l = lat_p.to(dev, non_blocking=True)
+        img = hot_path(v, i, l)["images"]
+        out_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream().synchronize()                                 # the caller reads the images now
+        return out_host
+
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        n0, r0 = lib().gillb200_launch_count(), gill.sd_pipe.graph_replays
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        n1, r1 = lib().gillb200_launch_count(), gill.sd_pipe.graph_replays
+        lpe = max(st["launches_per_eval"] for st in gill.sd_pipe._graphs.values()) if gill.sd_pipe._graphs else 0
+        launches = (n1 - n0) + (r1 - r0) * lpe                                   # direct launches + graph-replayed ones
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps, launches // steps
+
+    res = step_device()
+    torch.cuda.synchronize()
+    forced_ok = True
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_dev, launches = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 3))
+    img_per_s = world * BATCH / (ms_dev / 1e3)
+    e2e_per_s = world * BATCH / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel family, measured live with CUDA events (one eager, un-graphed UNet eval)
+    roof, breakdown = None, None
+    if rank == 0:
+        sdp = gill.sd_pipe
+        st = next(iter(sdp._graphs.values()))
+        ops.PROFILE = []
+        for _ in range(2):
+            sdp.unet.forward(st["pair"], 5, st["ctx_kv"])
+        torch.cuda.synchronize()
+        prof = ops.profile_summary(ops.PROFILE)
+        ops.PROFILE = None
+        tot = sum(d["ms"] for d in prof.values())
+        breakdown = {k: {"ms_per_eval": round(d["ms"] / 2, 3), "share": round(d["ms"] / tot, 3),
+                         "launches_per_eval": d["launches"] // 2,
+                         "tflops": round(d["flops"] / d["ms"] / 1e9, 1) if d["flops"] else None}
+                     for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        ach = top[1]["flops"] / top[1]["ms"] / 1e9
+        roof = {"kernel": {"conv3x3": "gemm_kernel<BN> (implicit 3x3 conv mode)", "gemm": "gemm_kernel<BN>",
+                           "attention": "attn_kernel<HD_PAD,BLOCK_KV>"}.get(top[0], top[0]),
+                "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tf_sustained"], 3), "traffic": None,
+                "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
+                "launches_timed": top[1]["launches"], "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4),
+                "share_of_unet_eval": round(top[1]["ms"] / tot, 3)}
+
+    # ---- retrieval: 3M x 768 bank row-sharded over the ranks, Q=1024, K=16 (BASELINE configs[2])
+    from oracle import retrieval as orc  # synthetic bank generator only (data, not compute)
+
+    lo, hi = retrieval.shard_rows(BANK_N, world, rank)
+    g = torch.Generator(device=dev).manual_seed(7000 + rank)
+    bank = torch.randn(hi - lo, BANK_D, generator=g, device=dev, dtype=torch.float32)
+    bank = (bank / bank.norm(dim=1, keepdim=True) * 14.24).to(torch.bfloat16)
+    q = orc.synthetic_queries(BANK_Q // world, BANK_D).to(dev)
+    sb = retrieval.ShardedBank(bank, BANK_N) if world > 1 else None
+    search = (lambda: sb.search(q, BANK_K)) if world > 1 else (lambda: retrieval.retrieval_topk(bank, q, BANK_K))
+    ms_ret, _ = timed(search, 10, 3)
+    qps = BANK_Q / (ms_ret / 1e3)
+    ret_flops = 2.0 * BANK_N * BANK_D * BANK_Q / world
+    retrieval_obj = {"metric": "retrieval top-k QPS over 3M", "value": round(qps, 1), "unit": "queries/s",
+                     "ms_per_batch": round(ms_ret, 3),
+                     "config": {"bank": f"{BANK_N}x{BANK_D} bf16", "queries": BANK_Q, "k": BANK_K,
+                                "bank_shards": world, "cache": "bank shard (>= 576 MB) larger than L2"},
+                     "roofline": {"kernel": "topk_scores_kernel", "bound": "tensor",
+                                  "achieved": round(ret_flops / ms_ret / 1e9, 1), "peak": pk["tf_burst"],
+                                  "unit": "TFLOP/s", "frac": round(ret_flops / ms_ret / 1e9 / pk["tf_burst"], 3),
+                                  "traffic": None, "peak_source": pk["src"] + " burst bf16 (kernel timed alone)"}}
+    del bank
+
+    if rank != 0:
+        return
+    cpu = cpu_baseline_sample(bounded_s=20.0)
+    flop_per_batch = BATCH * (2 * 51 * UNET_GFLOP_PER_EVAL + VAE_GFLOP + OPT_GFLOP_T81 + MAPPER_GFLOP) / 1e3  # TFLOP
+    line = {
+        "metric": "images/sec OPT-6.7B->GILLMapper->SD1.5(50-step)", "value": round(img_per_s, 4), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (SD) / bf16 (OPT) operands, fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: 8 prompts (2x4 CLIP visual-prefix tokens + BOS + 64 text tokens) -> "
+                               "OPT-6.7B prefill over 81 tokens -> GILLMapper -> SD-1.5 UNet 51 evals (50-step PLMS, CFG 7.5) "
+                               "512x512 -> VAE -> uint8", "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+                   "weights": f"OPT-6.7B/UNet/VAE seeded random init (no pretrained weights offline); GILL-trained weights: {wkind}",
+                   "cache": "working set per step (13.3 GB OPT + 1.7 GB UNet weights) larger than L2",
+                   "parallelism": f"dp{world} (independent prompt batches per GPU; no collective on the image path)",
+                   "setup_s": round(setup_s, 1), "algorithmic_tflop_per_step": round(flop_per_batch, 1)},
+        "e2e": {"value": round(e2e_per_s, 4), "unit": "images/s", "ms_per_step": round(ms_e2e, 2),
+                "h2d_bytes_per_step": int(vis_h.numel() * 2 + ids_h.numel() * 8 + lat_h.numel() * 2),
+                "d2h_bytes_per_step": int(out_host.numel())},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "achieved_tflops_whole_step": round(flop_per_batch / (ms_dev / 1e3), 1),
+        "roofline": roof, "unet_eval_breakdown": breakdown, "cpu_baseline": cpu, "retrieval": retrieval_obj,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline_sample(bounded_s=20.0):
+    """The path's CPU implementation (oracle port, PyTorch fp32, all host threads) on a bounded sample of configs[3]:
+    UNet evaluations at batch 2 (one image's CFG pair) + one VAE decode + the GILLMapper at B=8; extrapolated to
+    51 evaluations per image. OPT-6.7B fp32 (26.6 GB, ~2 min to build) is left out of the sample and stated so."""
+    from oracle import mapper as omap, sd15 as osd
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    usd = osd.init_unet(0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    with torch.no_grad():
+        osd.unet_forward(usd, x, 981, ctx)  # warm-up
+        t0, n = time.time(), 0
+        while n < 2 or (time.time() - t0 < bounded_s * 0.6 and n < 8):
+            osd.unet_forward(usd, x, 961, ctx)
+            n += 1
+        t_eval = (time.time() - t0) / n
+        vsd = osd.init_vae_decoder(1)
+        t0 = time.time()
+        osd.vae_decode(vsd, torch.randn(1, 4, 64, 64, generator=g))
+        t_vae = time.time() - t0
+        msd = omap.synthetic_mapper_state_dict(1234)
+        xm = torch.randn(8, 8, 4096, generator=g)
+        t0 = time.time()
+        omap.mapper_forward(msd, xm, torch.zeros(1, 8, 4096))
+        t_map = (time.time() - t0) / 8
+    per_image = 51 * t_eval + t_vae + t_map
+    return {"value": round(1.0 / per_image, 5), "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} UNet evals at batch 2 (CFG pair of one image, {t_eval:.2f} s each) + 1 VAE decode ({t_vae:.2f} s) + "
+                      f"GILLMapper B=8, fp32, extrapolated to 51 evals/image; OPT-6.7B fp32 (2.0 TFLOP, 26.6 GB) not in the sample"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path (oracle port: the third-party module math is not
+    installable) on the host cores, same metric/config, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_baseline_sample(bounded_s=15.0))
+    best = max(vals, key=lambda d: d["value"])
+    v = best["value"]
+    line = {"impl": "reference", "metric": "images/sec OPT-6.7B->GILLMapper->SD1.5(50-step)", "value": v,
+            "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(BATCH / v * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3] (bounded CPU sample, extrapolated)", "batch_per_gpu": BATCH},
+            "cpu_baseline": best,
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -28,3 +28,4 @@ def declare(L):
     d("gillb200_l2norm_rows", vp, cll, ci, ci, vp, cll, ci, vp)
     d("gillb200_cast_add", vp, ci, vp, ci, cll, vp, ci, vp, cll, vp)
     d("gillb200_attn_small_f32", vp, cll, cll, vp, cll, cll, vp, cll, cll, ci, ci, ci, ci, ci, cf, vp, cll, cll, ci, vp, vp)
+    d("gillb200_launch_count", restype=cll)

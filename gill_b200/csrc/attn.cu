@@ -314,6 +314,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t stream) {
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
   attn_kernel<HD_PAD, BLOCK_KV><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -274,6 +274,7 @@ extern "C" int gillb200_gather_add_rows(const void* x, const void* table, const 
   gather_add_rows_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, stream>>>(
       reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(table), idx, idx_offset, rows, D,
       dtype == DT_BF16, reinterpret_cast<uint16_t*>(out));
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -283,6 +284,7 @@ extern "C" int gillb200_upsample2x(const void* x, int B, int H, int W, int C, vo
   GB_CHECK_ARG(x && out && C % 8 == 0, "upsample2x: bad args");
   upsample2x_kernel<<<grid_for(4LL * B * H * W * (C / 8), 256), 256, 0, stream>>>(
       reinterpret_cast<const uint16_t*>(x), B, H, W, C, reinterpret_cast<uint16_t*>(out));
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -294,6 +296,7 @@ extern "C" int gillb200_im2col3x3(const void* x, int B, int H, int W, int C, int
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   im2col3x3_kernel<<<grid_for(1LL * B * Ho * Wo * ld_out, 256), 256, 0, stream>>>(
       reinterpret_cast<const uint16_t*>(x), B, H, W, C, stride, Ho, Wo, reinterpret_cast<uint16_t*>(out), ld_out);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -306,6 +309,7 @@ extern "C" int gillb200_plms_step(const void* eps_pair, int eps_dtype, float gui
   GB_CHECK_ARG(mode >= 0 && mode <= 4 && head >= 0 && head < 4, "plms_step: bad mode/head");
   plms_step_kernel<<<grid_for(n, 256), 256, 0, stream>>>(eps_pair, eps_dtype, guidance, ets, head, mode, c_sample,
                                                          c_eps, latents, cur_sample, lat16_pair, lat16_dtype, n);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -316,6 +320,7 @@ extern "C" int gillb200_image_to_u8(const void* x, int dtype, long long pixels, 
   GB_CHECK_ARG(x && out && pixels > 0 && channels > 0 && ldx >= channels, "image_to_u8: bad args");
   image_to_u8_kernel<<<grid_for(pixels * channels, 256), 256, 0, stream>>>(x, dtype, pixels, ldx, channels,
                                                                            reinterpret_cast<uint8_t*>(out));
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -325,6 +330,7 @@ extern "C" int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && rows > 0 && n > 0, "l2norm_rows: bad args");
   l2norm_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, rows, n, out, ldo, out_dtype);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -334,6 +340,7 @@ extern "C" int gillb200_cast_add(const void* x, int x_dtype, const void* y, int 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && n > 0, "cast_add: bad args");
   cast_add_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -354,6 +361,7 @@ extern "C" int gillb200_attn_small_f32(const float* q, long long ldq, long long 
   }
   attn_small_f32_kernel<128><<<dim3(H, B), 256, smem, stream>>>(q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
                                                                   out, ldo, o_bs, out_dtype, out_lo);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }

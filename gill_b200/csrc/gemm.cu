@@ -8,6 +8,7 @@
 
 namespace gb {
 
+long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 char* err_buf() { return g_err; }
 int set_err(int code, const char* fmt, ...) {
@@ -82,6 +83,7 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -115,6 +117,7 @@ using namespace gb;
 extern "C" int gillb200_version(void) { return GILLB200_VERSION; }
 extern "C" const char* gillb200_last_error(void) { return gb::err_buf(); }
 extern "C" int gillb200_num_sms(void) { return gb::num_sms(); }
+extern "C" long long gillb200_launch_count(void) { return gb::g_launch_count; }
 
 extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

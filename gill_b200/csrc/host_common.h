@@ -32,4 +32,8 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
 
 int num_sms();
 
+// number of kernel launches issued by this library (bench.py reports it as gpu_launches)
+extern long long g_launch_count;
+#define GB_COUNT_LAUNCH(n) (gb::g_launch_count += (n))
+
 }  // namespace gb

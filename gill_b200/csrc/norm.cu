@@ -308,6 +308,7 @@ extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, co
     layernorm_kernel<4, 5><<<rows, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
                                                       out_lo);
   }
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -332,6 +333,7 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   const size_t smem = 2 * C * sizeof(float);
   gn_stats_kernel<<<dim3(chunks, B), 256, smem, stream>>>(src, dtype, HW, G, chunks,
                                                          reinterpret_cast<float*>(workspace));
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   int pix_per_block = (32768 + C - 1) / C;  // ~32K elements per CTA
   if (pix_per_block < 1) pix_per_block = 1;
@@ -339,6 +341,7 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   gn_apply_kernel<<<dim3(blocks, B), 256, smem, stream>>>(src, dtype, HW, G, chunks,
                                                          reinterpret_cast<const float*>(workspace), w, b, eps, silu,
                                                          out, out_dtype, pix_per_block);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -349,6 +352,7 @@ extern "C" int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype,
   GB_CHECK_ARG(x && out && n % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "softmax_rows: n, ldx, ldo multiples of 8");
   GB_CHECK_ARG(rows > 0 && rows < (1LL << 31), "softmax_rows: bad row count");
   softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, in_dtype, scale, n, out, ldo, out_dtype);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }

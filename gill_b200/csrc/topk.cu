@@ -302,10 +302,12 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
     configured = true;
   }
   topk_scores_kernel<<<num_m * splits, TOPK_THREADS, C::SMEM_BYTES, stream>>>(p, e);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   const int warps_per_block = 4;
   topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
       e.part_val, e.part_idx, splits * 2, KMAX, static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -318,6 +320,7 @@ extern "C" int gillb200_topk_merge(const float* cand_val, const long long* cand_
   const int warps_per_block = 4;
   topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
       cand_val, cand_idx, R, Kc, static_cast<long long>(Q) * Kc, Kc, Q, K, out_val, out_idx);
+  GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -15,6 +15,43 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-launch timing (bench.py / tools): set ops.PROFILE = [] and every wrapper appends
+# (kernel family, algorithmic flops, algorithmic bytes, start event, end event) around its launch.
+PROFILE = None
+
+
+class _P:
+    __slots__ = ("name", "flops", "bytes", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.bytes = name, flops, nbytes
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+        return False
+
+
+def profile_summary(records):
+    """Aggregate PROFILE records per kernel family -> {name: dict(ms, launches, flops, bytes)} (call after a sync)."""
+    out = {}
+    for name, fl, by, e0, e1 in records:
+        d = out.setdefault(name, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+        d["ms"] += e0.elapsed_time(e1)
+        d["launches"] += 1
+        d["flops"] += fl
+        d["bytes"] += by
+    return out
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -78,7 +115,10 @@ def gemm(
         _chk2d(residual, "residual")
         g.residual, g.ldr, g.res_dtype = residual.data_ptr(), residual.stride(0), _DT[residual.dtype]
     g.act, g.alpha, g.block_n = _ACT[act], alpha, block_n
-    check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm")
+    ktot = K + (g.k2 if a2_mode == 1 else 0)
+    with _P("gemm" if a2_mode != 2 else "gemm_split", 2.0 * M * N * ktot * (2 if a2_mode == 2 else 1),
+            2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out):
+        check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm")
     return out
 
 
@@ -130,7 +170,8 @@ def conv3x3(
         r2 = residual.view(B * H * W, N)
         g.residual, g.ldr, g.res_dtype = r2.data_ptr(), r2.stride(0), _DT[residual.dtype]
     g.act, g.alpha, g.block_n = _ACT[act], 1.0, block_n
-    check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")
+    with _P("conv3x3", 2.0 * B * H * W * N * (9 * C + (g.k2 or 0)), 2.0 * (B * H * W * C + N * 9 * C + B * H * W * N)):
+        check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")
     return out
 
 
@@ -150,10 +191,11 @@ def topk_scores(bank: torch.Tensor, q: torch.Tensor, k: int, *, index_base: int 
     n_ex = 0 if exclude_idx is None else exclude_idx.numel()
     if n_ex:
         assert exclude_idx.dtype == torch.int64 and exclude_idx.is_cuda and exclude_idx.is_contiguous()
-    check(lib().gillb200_topk_scores(bank.data_ptr(), N, bank.shape[1], bank.stride(0), q.data_ptr(), Q, q.stride(0),
-                                     k, index_base, _ptr(exclude_idx) if n_ex else None, n_ex,
-                                     workspace.data_ptr(), vals.data_ptr(), idx.data_ptr(), _stream()),
-          "gillb200_topk_scores")
+    with _P("topk_scores", 2.0 * N * bank.shape[1] * Q, 2.0 * N * bank.shape[1]):
+        check(lib().gillb200_topk_scores(bank.data_ptr(), N, bank.shape[1], bank.stride(0), q.data_ptr(), Q,
+                                         q.stride(0), k, index_base, _ptr(exclude_idx) if n_ex else None, n_ex,
+                                         workspace.data_ptr(), vals.data_ptr(), idx.data_ptr(), _stream()),
+              "gillb200_topk_scores")
     return vals, idx
 
 
@@ -164,8 +206,9 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
     R, Q, Kc = cand_val.shape
     vals = torch.empty((Q, k), device=cand_val.device, dtype=torch.float32)
     idx = torch.empty((Q, k), device=cand_val.device, dtype=torch.int64)
-    check(lib().gillb200_topk_merge(cand_val.data_ptr(), cand_idx.data_ptr(), R, Q, Kc, k, vals.data_ptr(),
-                                    idx.data_ptr(), _stream()), "gillb200_topk_merge")
+    with _P("topk_merge"):
+        check(lib().gillb200_topk_merge(cand_val.data_ptr(), cand_idx.data_ptr(), R, Q, Kc, k, vals.data_ptr(),
+                                        idx.data_ptr(), _stream()), "gillb200_topk_merge")
     return vals, idx
 
 
@@ -188,7 +231,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
     a.B, a.H, a.Lq, a.Lk, a.hd_pad = B, heads, Lq, Lk, hd_pad
     a.causal, a.causal_offset = int(causal), causal_offset
     a.dtype, a.scale = _DT[q.dtype], scale
-    check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")
+    with _P("attention", 4.0 * B * heads * Lq * Lk * hd_pad, 2.0 * B * heads * hd_pad * (2 * Lq + 2 * Lk)):
+        check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")
     return out
 
 
@@ -204,9 +248,9 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e
     assert w.dtype == torch.float32 and b.dtype == torch.float32
     if out is None:
         out = torch.empty((rows, C), device=x.device, dtype=out_dtype or x.dtype)
-    check(lib().gillb200_layernorm(x.data_ptr(), x.stride(0), _DT[x.dtype], w.data_ptr(), b.data_ptr(), eps, rows, C,
-                                   out.data_ptr(), out.stride(0), _DT[out.dtype], _ptr(out_lo), _stream()),
-          "gillb200_layernorm")
+    with _P("layernorm"):
+        check(lib().gillb200_layernorm(x.data_ptr(), x.stride(0), _DT[x.dtype], w.data_ptr(), b.data_ptr(), eps, rows, C,
+                                       out.data_ptr(), out.stride(0), _DT[out.dtype], _ptr(out_lo), _stream()), "gillb200_layernorm")
     return out
 
 
@@ -227,9 +271,10 @@ def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, ep
     if ws is None:
         ws = torch.empty(lib().gillb200_groupnorm_workspace_bytes(B, groups), device=x.device, dtype=torch.uint8)
         _gn_ws[key] = ws
-    check(lib().gillb200_groupnorm(x.data_ptr(), C0, _ptr(x2), C1, _DT[x.dtype], B, H * W, groups, w.data_ptr(),
-                                   b.data_ptr(), eps, int(silu), out.data_ptr(), _DT[out.dtype], ws.data_ptr(),
-                                   _stream()), "gillb200_groupnorm")
+    with _P("groupnorm"):
+        check(lib().gillb200_groupnorm(x.data_ptr(), C0, _ptr(x2), C1, _DT[x.dtype], B, H * W, groups, w.data_ptr(),
+                                       b.data_ptr(), eps, int(silu), out.data_ptr(), _DT[out.dtype], ws.data_ptr(),
+                                       _stream()), "gillb200_groupnorm")
     return out
 
 
@@ -238,8 +283,9 @@ def softmax_rows(x: torch.Tensor, scale: float, out_dtype: torch.dtype, out: Opt
     rows, n = x.shape
     if out is None:
         out = torch.empty((rows, n), device=x.device, dtype=out_dtype)
-    check(lib().gillb200_softmax_rows(x.data_ptr(), x.stride(0), _DT[x.dtype], scale, rows, n, out.data_ptr(),
-                                      out.stride(0), _DT[out.dtype], _stream()), "gillb200_softmax_rows")
+    with _P("softmax_rows"):
+        check(lib().gillb200_softmax_rows(x.data_ptr(), x.stride(0), _DT[x.dtype], scale, rows, n, out.data_ptr(),
+                                          out.stride(0), _DT[out.dtype], _stream()), "gillb200_softmax_rows")
     return out
 
 
@@ -255,8 +301,9 @@ def gather_add_rows(table: torch.Tensor, idx: torch.Tensor, x: Optional[torch.Te
         out = torch.empty((rows, D), device=table.device, dtype=table.dtype)
     if x is not None:
         assert x.is_contiguous() and x.dtype == table.dtype and x.numel() == rows * D
-    check(lib().gillb200_gather_add_rows(_ptr(x), table.data_ptr(), idx.data_ptr(), idx_offset, rows, D,
-                                         _DT[table.dtype], out.data_ptr(), _stream()), "gillb200_gather_add_rows")
+    with _P("gather_add_rows"):
+        check(lib().gillb200_gather_add_rows(_ptr(x), table.data_ptr(), idx.data_ptr(), idx_offset, rows, D,
+                                             _DT[table.dtype], out.data_ptr(), _stream()), "gillb200_gather_add_rows")
     return out
 
 
@@ -264,7 +311,8 @@ def upsample2x(x: torch.Tensor) -> torch.Tensor:
     B, H, W, C = x.shape
     assert x.is_contiguous()
     out = torch.empty((B, 2 * H, 2 * W, C), device=x.device, dtype=x.dtype)
-    check(lib().gillb200_upsample2x(x.data_ptr(), B, H, W, C, out.data_ptr(), _stream()), "gillb200_upsample2x")
+    with _P("upsample2x"):
+        check(lib().gillb200_upsample2x(x.data_ptr(), B, H, W, C, out.data_ptr(), _stream()), "gillb200_upsample2x")
     return out
 
 
@@ -275,8 +323,8 @@ def im2col3x3(x: torch.Tensor, stride: int, ld_out: Optional[int] = None) -> tor
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     ld_out = ld_out or 9 * C
     out = torch.empty((B * Ho * Wo, ld_out), device=x.device, dtype=x.dtype)
-    check(lib().gillb200_im2col3x3(x.data_ptr(), B, H, W, C, stride, out.data_ptr(), ld_out, _stream()),
-          "gillb200_im2col3x3")
+    with _P("im2col3x3"):
+        check(lib().gillb200_im2col3x3(x.data_ptr(), B, H, W, C, stride, out.data_ptr(), ld_out, _stream()), "gillb200_im2col3x3")
     return out
 
 
@@ -286,10 +334,10 @@ def plms_step(eps_pair: torch.Tensor, guidance: float, ets: torch.Tensor, head: 
     n = latents.numel()
     assert eps_pair.numel() == 2 * n and ets.numel() == 4 * n and cur_sample.numel() == n
     assert latents.dtype == torch.float32 and ets.dtype == torch.float32 and cur_sample.dtype == torch.float32
-    check(lib().gillb200_plms_step(eps_pair.data_ptr(), _DT[eps_pair.dtype], guidance, ets.data_ptr(), head, mode,
-                                   c_sample, c_eps, latents.data_ptr(), cur_sample.data_ptr(), _ptr(lat16_pair),
-                                   _DT[lat16_pair.dtype] if lat16_pair is not None else 0, n, _stream()),
-          "gillb200_plms_step")
+    with _P("plms_step"):
+        check(lib().gillb200_plms_step(eps_pair.data_ptr(), _DT[eps_pair.dtype], guidance, ets.data_ptr(), head, mode,
+                                       c_sample, c_eps, latents.data_ptr(), cur_sample.data_ptr(), _ptr(lat16_pair),
+                                       _DT[lat16_pair.dtype] if lat16_pair is not None else 0, n, _stream()), "gillb200_plms_step")
 
 
 def image_to_u8(x: torch.Tensor, channels: int = 3) -> torch.Tensor:
@@ -297,8 +345,8 @@ def image_to_u8(x: torch.Tensor, channels: int = 3) -> torch.Tensor:
     B, H, W, ld = x.shape
     assert x.is_contiguous()
     out = torch.empty((B, H, W, channels), device=x.device, dtype=torch.uint8)
-    check(lib().gillb200_image_to_u8(x.data_ptr(), _DT[x.dtype], B * H * W, ld, channels, out.data_ptr(), _stream()),
-          "gillb200_image_to_u8")
+    with _P("image_to_u8"):
+        check(lib().gillb200_image_to_u8(x.data_ptr(), _DT[x.dtype], B * H * W, ld, channels, out.data_ptr(), _stream()), "gillb200_image_to_u8")
     return out
 
 
@@ -306,8 +354,9 @@ def l2norm_rows(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     _chk2d(x, "x")
     assert x.dtype == torch.float32
     out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    check(lib().gillb200_l2norm_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), out.stride(0),
-                                     _DT[out_dtype], _stream()), "gillb200_l2norm_rows")
+    with _P("l2norm_rows"):
+        check(lib().gillb200_l2norm_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], out.data_ptr(), out.stride(0),
+                                         _DT[out_dtype], _stream()), "gillb200_l2norm_rows")
     return out
 
 
@@ -317,9 +366,9 @@ def cast_add(x: torch.Tensor, y: Optional[torch.Tensor], out_dtype: torch.dtype,
     assert x.is_contiguous() and (y is None or y.is_contiguous())
     if out is None:
         out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
-    check(lib().gillb200_cast_add(x.data_ptr(), _DT[x.dtype], _ptr(y), _DT[y.dtype] if y is not None else 0, y_period,
-                                  out.data_ptr(), _DT[out.dtype], _ptr(out_lo), x.numel(), _stream()),
-          "gillb200_cast_add")
+    with _P("cast_add"):
+        check(lib().gillb200_cast_add(x.data_ptr(), _DT[x.dtype], _ptr(y), _DT[y.dtype] if y is not None else 0, y_period,
+                                      out.data_ptr(), _DT[out.dtype], _ptr(out_lo), x.numel(), _stream()), "gillb200_cast_add")
     return out
 
 
@@ -328,8 +377,9 @@ def attn_small_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
     """fp32 attention for short sequences: q [B,Lq,*], k/v [B,Lk,*] fp32 views (head h at columns h*128)."""
     B, Lq, _ = q.shape
     Lk = k.shape[1]
-    check(lib().gillb200_attn_small_f32(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
-                                        v.data_ptr(), v.stride(1), v.stride(0), B, heads, 128, Lq, Lk, scale,
-                                        out.data_ptr(), out.stride(1), out.stride(0), _DT[out.dtype], _ptr(out_lo),
-                                        _stream()), "gillb200_attn_small_f32")
+    with _P("attn_small_f32"):
+        check(lib().gillb200_attn_small_f32(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                            v.data_ptr(), v.stride(1), v.stride(0), B, heads, 128, Lq, Lk, scale,
+                                            out.data_ptr(), out.stride(1), out.stride(0), _DT[out.dtype], _ptr(out_lo),
+                                            _stream()), "gillb200_attn_small_f32")
     return out

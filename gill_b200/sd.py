@@ -249,24 +249,34 @@ class UNetB200:
         ah, al = split(act)
         self._temb_table = ops.gemm(ah, self.w["temb_proj_all.weight"], a2=al, a2_mode=2,
                                     bias=self.w["temb_proj_all.bias"], out_dtype=torch.float32)  # [n, sum_c]
+        self._temb_cur = torch.empty((1, self.temb_total), device=self.dev, dtype=torch.float32)
         self._temb_steps = key
 
-    def precompute_ctx(self, ctx: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Cross-attention K/V of all transformer layers for a batch of conditionings [B2,77,768]: once per prompt."""
+    def set_step(self, step: int):
+        """Select the schedule entry the next forward() uses: copies that row of the time-projection table into the
+        fixed buffer every resnet reads its per-channel bias from (fixed address => the forward is graph-replayable)."""
+        ops.cast_add(self._temb_table[step], None, torch.float32, out=self._temb_cur)
+
+    def precompute_ctx(self, ctx: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None):
+        """Cross-attention K/V of all transformer layers for a batch of conditionings [B2,77,768]: once per prompt.
+        `out` (from a previous call with the same batch size) is overwritten in place, keeping addresses stable."""
         B2, L, D = ctx.shape
         c2 = ctx.to(self.dt).reshape(B2 * L, D).contiguous()
-        out = {}
+        res = {} if out is None else out
         for p in self.tf_layers:
-            kv = ops.gemm(c2, self.w[f"{p}.transformer_blocks.0.attn2.kv"])
-            out[p] = kv.view(B2, L, -1)
-        return out
+            w = self.w[f"{p}.transformer_blocks.0.attn2.kv"]
+            if out is None:
+                res[p] = ops.gemm(c2, w).view(B2, L, -1)
+            else:
+                ops.gemm(c2, w, out=out[p].view(B2 * L, -1))
+        return res
 
     # ------------------------------------------------------------------------------------------------ blocks
-    def _resnet(self, x, p, step, x2=None):
+    def _resnet(self, x, p, x2=None):
         w, G = self.w, self.G
         B, H, W, _ = x.shape
         lo, hi = self._temb_off[p]
-        rb = self._temb_table[step : step + 1, lo:hi]
+        rb = self._temb_cur[:, lo:hi]
         n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-5, silu=True, x2=x2)
         h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], rowbias=rb)
         n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-5, silu=True)
@@ -317,9 +327,12 @@ class UNetB200:
         return o.view(B, H // 2, W // 2, -1)
 
     # ------------------------------------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor, step: int, ctx_kv: Dict[str, torch.Tensor]) -> torch.Tensor:
-        """x: NHWC [B2,H,W,4] fp16 latent pair; step: index into the prepared timestep table; returns eps NHWC."""
+    def forward(self, x: torch.Tensor, step: Optional[int], ctx_kv: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """x: NHWC [B2,H,W,4] fp16 latent pair; step: index into the prepared timestep table (None: keep the row
+        selected by the last set_step, as graph replays do); returns eps NHWC."""
         cfg, w = self.cfg, self.w
+        if step is not None:
+            self.set_step(step)
         boc = cfg["block_out_channels"]
         B, H, W, _ = x.shape
         cols = ops.im2col3x3(x, 1, ld_out=64)
@@ -327,19 +340,19 @@ class UNetB200:
         skips = [h]
         for i in range(len(boc)):
             for j in range(cfg["layers_per_block"]):
-                h = self._resnet(h, f"down_blocks.{i}.resnets.{j}", step)
+                h = self._resnet(h, f"down_blocks.{i}.resnets.{j}")
                 if cfg["has_attn_down"][i]:
                     h = self._transformer(h, f"down_blocks.{i}.attentions.{j}", ctx_kv)
                 skips.append(h)
             if i < len(boc) - 1:
                 h = self._conv_s2(h, f"down_blocks.{i}.downsamplers.0.conv")
                 skips.append(h)
-        h = self._resnet(h, "mid_block.resnets.0", step)
+        h = self._resnet(h, "mid_block.resnets.0")
         h = self._transformer(h, "mid_block.attentions.0", ctx_kv)
-        h = self._resnet(h, "mid_block.resnets.1", step)
+        h = self._resnet(h, "mid_block.resnets.1")
         for i in range(len(boc)):
             for j in range(cfg["layers_per_block"] + 1):
-                h = self._resnet(h, f"up_blocks.{i}.resnets.{j}", step, x2=skips.pop())
+                h = self._resnet(h, f"up_blocks.{i}.resnets.{j}", x2=skips.pop())
                 if cfg["has_attn_up"][i]:
                     h = self._transformer(h, f"up_blocks.{i}.attentions.{j}", ctx_kv)
             if i < len(boc) - 1:
@@ -453,24 +466,61 @@ class StableDiffusionB200:
         self.neg = negative_prompt_embeds.to(unet.dev, unet.dt).reshape(1, 77, -1)
         self.latent_hw = 64
         self._graphs = {}
+        self.use_graph = True      # replay one captured UNet evaluation per step instead of ~650 launches
+        self.graph_replays = 0     # bookkeeping for bench.py's gpu_launches
+
+    def _state(self, b: int, h: int, w: int):
+        """Static per-(batch, size) buffers: every pointer the denoising loop touches stays fixed across calls, so one
+        captured UNet evaluation can be replayed for all 51 steps of every call."""
+        key = (b, h, w)
+        st = self._graphs.get(key)
+        if st is None:
+            dev, n = self.device, b * h * w * 4
+            st = dict(lat=torch.empty((b, h, w, 4), device=dev, dtype=torch.float32),
+                      pair=torch.empty((2 * b, h, w, 4), device=dev, dtype=self.unet.dt),
+                      ets=torch.empty((4, n), device=dev, dtype=torch.float32),
+                      cur=torch.empty(n, device=dev, dtype=torch.float32),
+                      ctx=torch.empty((2 * b, 77, self.neg.shape[-1]), device=dev, dtype=self.unet.dt),
+                      ctx_kv=None, graph=None, eps=None, launches_per_eval=0)
+            self._graphs[key] = st
+        return st
 
     @torch.no_grad()
     def denoise(self, prompt_embeds: torch.Tensor, latents_nchw: torch.Tensor, guidance_scale: float = 7.5,
-                num_inference_steps: int = 50, trace: Optional[list] = None) -> torch.Tensor:
-        """gill/custom_sd.py:606-651. Returns the final latents, NHWC fp32 [b,h,w,4]."""
-        b = prompt_embeds.shape[0]
+                num_inference_steps: int = 50, trace: Optional[list] = None, use_graph: Optional[bool] = None):
+        """gill/custom_sd.py:606-651. Returns the final latents, NHWC fp32 [b,h,w,4] (a static buffer)."""
+        b, _, h, w = latents_nchw.shape
+        use_graph = self.use_graph if use_graph is None else use_graph
         table = plms_table(num_inference_steps)
         self.unet.prepare_timesteps([t for t, _, _, _ in table])
-        ctx = torch.cat([self.neg.expand(b, -1, -1), prompt_embeds.to(self.unet.dt)], 0)      # custom_sd.py:371
-        ctx_kv = self.unet.precompute_ctx(ctx)
-        lat = latents_nchw.float().permute(0, 2, 3, 1).contiguous()                             # NHWC fp32
-        n = lat.numel()
-        ets = torch.empty((4, n), device=lat.device, dtype=torch.float32)
-        cur = torch.empty(n, device=lat.device, dtype=torch.float32)
-        pair = torch.cat([lat, lat], 0).to(self.unet.dt)                                        # custom_sd.py:630
+        st = self._state(b, h, w)
+        st["ctx"][:b].copy_(self.neg.expand(b, -1, -1))                                         # custom_sd.py:371
+        st["ctx"][b:].copy_(prompt_embeds.to(self.unet.dt))
+        st["ctx_kv"] = self.unet.precompute_ctx(st["ctx"], st["ctx_kv"])
+        lat, pair, ets, cur = st["lat"], st["pair"], st["ets"], st["cur"]
+        lat.copy_(latents_nchw.float().permute(0, 2, 3, 1))                                     # NHWC fp32
+        pair[:b].copy_(lat)                                                                     # custom_sd.py:630
+        pair[b:].copy_(lat)
+        if use_graph and st["graph"] is None:
+            from ._lib import lib
+            self.unet.set_step(0)
+            st["eps"] = self.unet.forward(pair, None, st["ctx_kv"])                             # eager warm-up
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = lib().gillb200_launch_count()
+            with torch.cuda.graph(g):
+                st["eps"] = self.unet.forward(pair, None, st["ctx_kv"])
+            st["launches_per_eval"] = lib().gillb200_launch_count() - n0
+            st["graph"] = g
         head = 0
         for i, (t, cs, ce, mode) in enumerate(table):                                           # custom_sd.py:628
-            eps = self.unet.forward(pair, i, ctx_kv)                                            # :633-638
+            if use_graph:
+                self.unet.set_step(i)
+                st["graph"].replay()                                                            # :633-638
+                self.graph_replays += 1
+                eps = st["eps"]
+            else:
+                eps = self.unet.forward(pair, i, st["ctx_kv"])
             ops.plms_step(eps, guidance_scale, ets, head, mode, cs, ce, lat, cur, pair)         # :641-646
             if mode != 1:
                 head = (head + 1) & 3
@@ -493,7 +543,7 @@ class StableDiffusionB200:
         shape = (b, 4, height // 8, width // 8)
         if latents is None:                                                                      # custom_sd.py:466-470
             latents = torch.randn(shape, generator=generator, device=self.device, dtype=torch.float16)
-        elif tuple(latents.shape) != shape:
+        elif tuple(latents.shape[:2]) != shape[:2] or latents.dim() != 4:
             raise ValueError(f"Unexpected latents shape, got {tuple(latents.shape)}, expected {shape}")
         lat = self.denoise(prompt_embeds.to(self.device), latents.to(self.device), guidance_scale, num_inference_steps)
         u8 = self.vae.decode_u8(lat)                                                            # custom_sd.py:654

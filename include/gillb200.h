@@ -30,6 +30,8 @@ enum { GILLB200_ACT_NONE = 0, GILLB200_ACT_RELU = 1, GILLB200_ACT_GELU = 2, GILL
 int gillb200_version(void);
 const char* gillb200_last_error(void);
 int gillb200_num_sms(void);
+/* number of kernel launches this library has issued so far in this process */
+long long gillb200_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Tensor-core GEMM / implicit-GEMM convolution (tcgen05.mma + TMEM accumulators, TMA-fed).
