@@ -33,7 +33,7 @@ def run():
     out = gill.emit_images_batch(embs, latents=lat.to(dev), num_inference_steps=6, top_k=0)
     torch.cuda.synchronize()
     imgs = out["images"]
-    assert imgs.shape == (B, 256, 256, 3) and imgs.dtype == torch.uint8, imgs.shape
+    assert imgs.shape == (B, 64, 64, 3) and imgs.dtype == torch.uint8, imgs.shape  # tiny VAE: one 2x upsample
 
     # --- GILLMapper vs oracle on the same [IMG] hidden states
     img_ids = torch.tensor(m.retrieval_token_idx, device=dev)

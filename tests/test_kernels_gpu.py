@@ -1,0 +1,267 @@
+"""GPU parity tests of the primitive kernels, called through the C ABI (gill_b200.ops -> libgillb200.so)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float().cpu().double(), b.float().cpu().double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from gill_b200 import ops as o
+
+    return o
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("bn", [0, 32, 64, 128, 160, 256])
+def test_gemm_block_n_variants(ops, dt, bn):
+    torch.manual_seed(0)
+    a = torch.randn(300, 328, device=dev).to(dt)
+    b = torch.randn(520, 328, device=dev).to(dt)
+    got = ops.gemm(a, b, block_n=bn, out_dtype=torch.float32)
+    assert rel(got, a.float() @ b.float().T) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 8, 64), (77, 768, 512), (8, 512, 4096), (1000, 328, 72), (4096, 4096, 1024)])
+def test_gemm_ragged_shapes(ops, shape):
+    M, N, K = shape
+    torch.manual_seed(1)
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = torch.randn(N, K, device=dev).bfloat16()
+    assert rel(ops.gemm(a, b, out_dtype=torch.float32), a.float() @ b.float().T) < 1e-5
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(2)
+    M, N, K = 384, 640, 320
+    a = torch.randn(M, K, device=dev).bfloat16()
+    b = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev)
+    base = a.float() @ b.float().T
+    got = ops.gemm(a, b, bias=bias, residual=res, act="relu", alpha=0.5, out_dtype=torch.float32)
+    assert rel(got, torch.relu(0.5 * base + bias) + res) < 1e-5
+    assert rel(ops.gemm(a, b, bias=bias, act="gelu", out_dtype=torch.float32), F.gelu(base + bias)) < 1e-5
+    assert rel(ops.gemm(a, b, bias=bias, act="silu", out_dtype=torch.float32), F.silu(base + bias)) < 1e-5
+    # GEGLU with interleaved (value, gate) rows
+    val, gate = b[: N // 2], b[N // 2:]
+    bi = torch.stack([val, gate], 1).reshape(N, K).contiguous()
+    bias_i = torch.stack([bias[: N // 2], bias[N // 2:]], 1).reshape(N).contiguous()
+    ref = (a.float() @ val.float().T + bias[: N // 2]) * F.gelu(a.float() @ gate.float().T + bias[N // 2:])
+    assert rel(ops.gemm(a, bi, bias=bias_i, act="geglu", out_dtype=torch.float32), ref) < 1e-5
+    # bias along M, per-row-group bias
+    bm = torch.randn(M, device=dev)
+    rb = torch.randn(M // 128, N, device=dev)
+    got = ops.gemm(a, b, bias=bm, bias_along_m=True, rowbias=rb, rows_per_group=128, out_dtype=torch.float32)
+    assert rel(got, base + bm[:, None] + rb.repeat_interleave(128, 0)) < 1e-5
+    # 16-bit output with residual
+    got = ops.gemm(a, b, bias=bias, residual=res.bfloat16())
+    assert got.dtype == torch.bfloat16 and rel(got, base + bias + res.bfloat16().float()) < 5e-3
+
+
+def test_gemm_second_a_source(ops):
+    torch.manual_seed(3)
+    M, N, K = 256, 192, 320
+    a = torch.randn(M, K, device=dev).bfloat16()
+    a2 = torch.randn(M, 128, device=dev).bfloat16()
+    b = torch.randn(N, K + 128, device=dev).bfloat16()
+    assert rel(ops.gemm(a, b, a2=a2, a2_mode=1, out_dtype=torch.float32), torch.cat([a, a2], 1).float() @ b.float().T) < 1e-5
+    x = torch.randn(M, K, device=dev)
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    w = torch.randn(N, K, device=dev).bfloat16()
+    got = ops.gemm(hi, w, a2=lo, a2_mode=2, out_dtype=torch.float32)
+    assert rel(got, x.double() @ w.double().T) < 2e-5          # split precision: ~16 mantissa bits of the activations
+    assert rel(ops.gemm(hi, w, out_dtype=torch.float32), x.double() @ w.double().T) > 5e-4   # plain bf16 is much worse
+    o_hi = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    o_lo = torch.empty_like(o_hi)
+    ops.gemm(hi, w, out=o_hi, out_lo=o_lo)
+    assert rel(o_hi.float() + o_lo.float(), hi.float() @ w.float().T) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 64), (2, 32, 32, 128, 320), (2, 16, 16, 64, 96), (4, 8, 8, 128, 64),
+                                  (3, 8, 8, 64, 64), (1, 128, 128, 64, 32), (1, 256, 256, 64, 16)])
+def test_conv3x3_implicit_gemm(ops, case):
+    B, H, W, C, Co = case
+    torch.manual_seed(4)
+    x = torch.randn(B, H, W, C, device=dev).half()
+    w = (torch.randn(Co, C, 3, 3, device=dev) / (3 * C ** 0.5)).half()
+    bias = torch.randn(Co, device=dev)
+    rb = torch.randn(B, Co, device=dev)
+    res = torch.randn(B, H, W, Co, device=dev).half()
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    got = ops.conv3x3(x, wk, bias=bias, rowbias=rb, residual=res, out_dtype=torch.float32)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1) + res.float()
+    assert rel(got, ref) < 1e-4
+
+
+def test_conv_helpers(ops):
+    torch.manual_seed(5)
+    x = torch.randn(2, 16, 16, 64, device=dev).half()
+    w = (torch.randn(96, 64, 3, 3, device=dev) * 0.05).half()
+    cols = ops.im2col3x3(x, 2)
+    got = ops.gemm(cols, w.permute(0, 2, 3, 1).reshape(96, -1).contiguous(), out_dtype=torch.float32).view(2, 8, 8, 96)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), stride=2, padding=1).permute(0, 2, 3, 1)
+    assert rel(got, ref) < 1e-5
+    x4 = torch.randn(2, 8, 8, 4, device=dev).half()
+    cols = ops.im2col3x3(x4, 1, ld_out=64)
+    assert cols.shape == (128, 64) and (cols[:, 36:] == 0).all()
+    up = ops.upsample2x(x)
+    assert torch.equal(up, F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("C,dt", [(320, torch.float16), (512, torch.float32), (1280, torch.float16), (4096, torch.float32)])
+def test_layernorm(ops, C, dt):
+    torch.manual_seed(6)
+    x = torch.randn(301, C, device=dev).to(dt)
+    w, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    assert rel(ops.layernorm(x, w, b, 1e-5, out_dtype=torch.float32), F.layer_norm(x.float(), (C,), w, b, 1e-5)) < 1e-5
+    if dt == torch.float32:
+        hi = torch.empty(301, C, device=dev, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi)
+        ops.layernorm(x, w, b, 1e-5, out=hi, out_lo=lo)
+        assert rel(hi.float() + lo.float(), F.layer_norm(x, (C,), w, b, 1e-5)) < 2e-5
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 320, 0, True), (2, 32, 32, 640, 320, True), (2, 8, 8, 1280, 1280, False),
+                                  (1, 128, 128, 256, 0, True), (2, 16, 16, 1280, 640, True)])
+def test_groupnorm_nhwc_with_concat(ops, case):
+    B, H, W, C0, C1, silu = case
+    torch.manual_seed(7)
+    x0 = torch.randn(B, H, W, C0, device=dev).half() * 2 + 0.5
+    x1 = torch.randn(B, H, W, C1, device=dev).half() if C1 else None
+    C = C0 + C1
+    w, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    got = ops.groupnorm(x0, w, b, 32, 1e-5, silu=silu, x2=x1, out_dtype=torch.float32)
+    xx = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(xx.float().permute(0, 3, 1, 2), 32, w, b, 1e-5)
+    ref = F.silu(ref) if silu else ref
+    assert rel(got, ref.permute(0, 2, 3, 1)) < 2e-5
+
+
+def test_small_kernels(ops):
+    torch.manual_seed(8)
+    s = torch.randn(200, 4096, device=dev)
+    assert rel(ops.softmax_rows(s, 0.3, torch.float32), torch.softmax(s * 0.3, -1)) < 1e-5
+    tab = torch.randn(100, 256, device=dev).bfloat16()
+    idx = torch.randint(0, 90, (37,), device=dev)
+    xx = torch.randn(37, 256, device=dev).bfloat16()
+    assert torch.equal(ops.gather_add_rows(tab, idx, x=xx, idx_offset=2), (xx.float() + tab[idx + 2].float()).bfloat16())
+    assert torch.equal(ops.gather_add_rows(tab, idx), tab[idx])
+    x = torch.randn(9, 256, device=dev)
+    assert rel(ops.l2norm_rows(x, torch.float32), x / x.norm(dim=-1, keepdim=True)) < 1e-6
+    img = torch.randn(2, 16, 16, 8, device=dev).half()
+    ref = ((img[..., :3].float() / 2 + 0.5).clamp(0, 1) * 255).round().to(torch.uint8)
+    assert torch.equal(ops.image_to_u8(img, 3), ref)
+    y = torch.randn(8, 64, device=dev)
+    xb = torch.randn(5, 8, 64, device=dev)
+    lo = torch.empty(5, 8, 64, device=dev, dtype=torch.bfloat16)
+    hi = ops.cast_add(xb, y, torch.bfloat16, y_period=y.numel(), out_lo=lo)
+    assert rel(hi.float() + lo.float(), xb + y) < 2e-5
+
+
+def test_plms_step_matches_oracle_scheduler(ops):
+    from gill_b200 import sd as psd
+    from oracle import sd15 as osd
+
+    torch.manual_seed(9)
+    table = psd.plms_table(50)
+    sched = osd.PNDM()
+    sched.set_timesteps(50)
+    n = 4 * 8 * 8 * 4
+    lat = torch.randn(n, device=dev)
+    lat_ref = lat.clone().cpu()
+    ets, cur = torch.zeros(4, n, device=dev), torch.zeros(n, device=dev)
+    pair = torch.zeros(2, n, device=dev, dtype=torch.float16)
+    head = 0
+    for i, (t, cs, ce, mode) in enumerate(table):
+        eps = torch.randn(2, n, device=dev)
+        ops.plms_step(eps, 7.5, ets, head, mode, cs, ce, lat, cur, pair)
+        if mode != 1:
+            head = (head + 1) & 3
+        e = eps.cpu()
+        lat_ref = sched.step(e[0] + 7.5 * (e[1] - e[0]), t, lat_ref)
+        assert rel(lat, lat_ref) < 1e-5, i
+    assert rel(pair[0], lat) < 1e-3 and torch.equal(pair[0], pair[1])
+
+
+CASES = [  # B, H, Lq, Lk, hd, hd_pad, dtype, causal
+    (2, 2, 128, 128, 40, 64, torch.float16, False), (2, 8, 1024, 1024, 40, 64, torch.float16, False),
+    (2, 8, 1024, 77, 40, 64, torch.float16, False), (2, 8, 256, 256, 80, 128, torch.float16, False),
+    (2, 8, 64, 64, 160, 192, torch.float16, False), (2, 8, 256, 77, 160, 192, torch.float16, False),
+    (3, 32, 81, 81, 128, 128, torch.bfloat16, True), (2, 4, 300, 300, 128, 128, torch.bfloat16, True),
+]
+
+
+def attn_ref(q, k, v, H, hp, scale, causal=False, kv_lens=None):
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    qh, kh, vh = (t.float().view(B, -1, H, hp).transpose(1, 2) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2) * scale
+    if causal:
+        i, j = torch.arange(Lq, device=dev)[:, None], torch.arange(Lk, device=dev)[None]
+        s = s.masked_fill(j > i, float("-inf"))
+    if kv_lens is not None:
+        j = torch.arange(Lk, device=dev)[None, None, None]
+        s = s.masked_fill(j >= kv_lens.view(B, 1, 1, 1), float("-inf"))
+    return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, H * hp)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_attention(ops, case):
+    B, H, Lq, Lk, hd, hp, dt, causal = case
+    torch.manual_seed(10)
+
+    def mk(L):
+        t = torch.zeros(B, L, H, hp, device=dev)
+        t[..., :hd] = torch.randn(B, L, H, hd, device=dev)
+        return t.view(B, L, H * hp).to(dt)
+
+    q, k, v = mk(Lq), mk(Lk), mk(Lk)
+    got = ops.attention(q, k, v, H, hp, hd ** -0.5, causal=causal)
+    tol = 1e-2 if dt == torch.bfloat16 else 3e-3   # P is rounded to the operand dtype before P.V
+    assert torch.isfinite(got.float()).all() and rel(got, attn_ref(q, k, v, H, hp, hd ** -0.5, causal)) < tol
+
+
+def test_fused_attention_kv_lens_and_views(ops):
+    torch.manual_seed(11)
+    B, H, L, hp = 3, 4, 200, 128
+    qkv = torch.randn(B, L, 3 * H * hp, device=dev).bfloat16()
+    q, k, v = qkv[:, :, : H * hp], qkv[:, :, H * hp: 2 * H * hp], qkv[:, :, 2 * H * hp:]
+    kvl = torch.tensor([200, 77, 130], device=dev, dtype=torch.int32)
+    got = ops.attention(q, k, v, H, hp, hp ** -0.5, kv_lens=kvl)
+    assert rel(got, attn_ref(q, k, v, H, hp, hp ** -0.5, kv_lens=kvl)) < 1e-2
+
+
+def test_attn_small_f32(ops):
+    torch.manual_seed(12)
+    B = 3
+    for Lq, Lk in ((77, 8), (77, 77), (8, 8)):
+        q = torch.randn(B, Lq, 512, device=dev)
+        kv = torch.randn(B, Lk, 1024, device=dev)
+        out = torch.empty(B, Lq, 512, device=dev)
+        ops.attn_small_f32(q, kv[:, :, :512], kv[:, :, 512:], 4, 128 ** -0.5, out=out)
+        qh = q.view(B, Lq, 4, 128).transpose(1, 2)
+        kh = kv[:, :, :512].reshape(B, Lk, 4, 128).transpose(1, 2)
+        vh = kv[:, :, 512:].reshape(B, Lk, 4, 128).transpose(1, 2)
+        ref = (torch.softmax(qh @ kh.transpose(-1, -2) * 128 ** -0.5, -1) @ vh).transpose(1, 2).reshape(B, Lq, 512)
+        assert rel(out, ref) < 1e-5
+
+
+def test_bad_arguments_raise(ops):
+    from gill_b200._lib import GillB200Error
+
+    a = torch.randn(16, 30, device=dev).bfloat16()      # K stride not a multiple of 8 elements
+    b = torch.randn(16, 30, device=dev).bfloat16()
+    with pytest.raises(GillB200Error):
+        ops.gemm(a, b)
+    with pytest.raises(GillB200Error):
+        ops.topk_scores(torch.randn(64, 64, device=dev).bfloat16(), torch.randn(2, 64, device=dev).bfloat16(), 17)
