@@ -74,9 +74,11 @@ class ShardedBank:
         q_all = torch.empty((W * Ql, q_local.shape[1]), dtype=q_local.dtype, device=q_local.device)
         dist.all_gather_into_tensor(q_all, q_local.contiguous(), group=self.group)           # (1) queries
         v, i = self._local_topk(self.bank, q_all, k, exclude_idx, self.lo)                   # (2) shard top-k
-        cv = torch.empty((W,) + tuple(v.shape), dtype=v.dtype, device=v.device)
-        ci = torch.empty((W,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+        Qa, Kc = v.shape
+        cv = torch.empty((W * Qa, Kc), dtype=v.dtype, device=v.device)                       # rank-major concat
+        ci = torch.empty((W * Qa, Kc), dtype=i.dtype, device=i.device)
         dist.all_gather_into_tensor(cv, v.contiguous(), group=self.group)                    # (3) candidates
         dist.all_gather_into_tensor(ci, i.contiguous(), group=self.group)
+        cv, ci = cv.view(W, Qa, Kc), ci.view(W, Qa, Kc)
         mine = slice(self.rank * Ql, (self.rank + 1) * Ql)
         return self._merge(cv[:, mine].contiguous(), ci[:, mine].contiguous(), k)            # (4) owner merges

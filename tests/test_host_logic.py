@@ -1,0 +1,98 @@
+"""CPU tests of the host-side logic: tokenizer stand-in, caption truncation, shard arithmetic and the 2-rank candidate
+exchange of ShardedBank over gloo (the CUDA kernels are replaced by oracle stand-ins: this tests the plumbing only)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+
+def test_truncate_caption_behaviour():
+    from gill_b200.models import truncate_caption
+
+    assert truncate_caption("a dog. a cat.") == "a dog."
+    assert truncate_caption("\nfirst line\nsecond") == "first line\n"
+    assert truncate_caption("no terminator") == "no terminator"
+    assert truncate_caption("") == ""
+
+
+def test_synthetic_tokenizer_contract():
+    from gill_b200.synthetic import IMG_IDS, SyntheticTokenizer
+
+    t = SyntheticTokenizer()
+    assert len(t) == 50274 and t.cls_token_id == 50265
+    pre = "".join(f"[IMG{i}]" for i in range(8))
+    assert t(pre, add_special_tokens=False).input_ids == IMG_IDS          # model_args.json:18-37
+    ids = t("a dog", add_special_tokens=True, return_tensors="pt").input_ids
+    assert ids.shape == (1, 3) and ids[0, 0] == 2
+    assert t("\n", add_special_tokens=False).input_ids == [50118]
+    assert "[IMG0]" in t.batch_decode(torch.tensor([[2, 50266]]))[0]
+
+
+def test_shard_rows_cover_the_bank():
+    from gill_b200.retrieval import shard_rows
+
+    for n, w in ((3_000_000, 8), (10, 3), (7, 8), (1, 1)):
+        spans = [shard_rows(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_plms_table_is_the_51_step_schedule():
+    from gill_b200.sd import plms_table
+
+    tab = plms_table(50)
+    assert len(tab) == 51 and [t for t, *_ in tab[:4]] == [981, 961, 961, 941] and tab[-1][0] == 1
+    assert [m for *_, m in tab[:6]] == [0, 1, 2, 3, 4, 4]
+    assert all(cs > 1.0 for _, cs, _, _ in tab)        # sqrt(a_prev / a_t) > 1 while denoising
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from gill_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.GillB200Error):
+        _lib.lib()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q_out):
+    import torch.distributed as dist
+
+    from gill_b200.retrieval import ShardedBank, shard_rows
+    from oracle import retrieval as orc
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N, D, K, Ql = 1001, 64, 5, 3
+    bank = orc.synthetic_bank_chunk(0, N, D, exact=True)
+    lo, hi = shard_rows(N, world, rank)
+    q_all = orc.synthetic_queries(world * Ql, D, exact=True)
+    sb = ShardedBank(bank[lo:hi], N, local_topk=lambda b, q, k, ex, base: orc.retrieval_topk(b, q, k, ex, base),
+                     merge=orc.merge_topk)
+    v, i = sb.search(q_all[rank * Ql:(rank + 1) * Ql], K, exclude_idx=[0, 500, 1000])
+    rv, ri = orc.retrieval_topk(bank, q_all[rank * Ql:(rank + 1) * Ql], K, exclude_idx=[0, 500, 1000])
+    q_out.put((rank, bool(torch.equal(v, rv) and torch.equal(i, ri))))
+    dist.destroy_process_group()
+
+
+def test_sharded_bank_exchange_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == {0: True, 1: True}
