@@ -35,19 +35,28 @@ struct alignas(64) AttnParams {
 
 template <int HD_PAD, int BLOCK_KV>
 struct AttnCfg {
+  // HD_PAD == 64 (UNet 64x64 / 32x32 levels, the hot shape): single S and V buffers so that TMEM (256 columns) and
+  // shared memory (< 113 KB) allow TWO CTAs per SM -- the second CTA's MMAs fill the first one's softmax bubbles and
+  // every SM sub-partition has two softmax warps to switch between. Wider heads keep the double-buffered 1-CTA form.
+  static constexpr int SBUF = HD_PAD == 64 ? 1 : 2;
+  static constexpr int VBUF = HD_PAD == 64 ? 1 : 2;
+  static constexpr int KBUF = 2;
+  static constexpr int CTAS_PER_SM = HD_PAD == 64 ? 2 : 1;
   static constexpr int KCH = HD_PAD / 64;           // 64-column chunks per head
   static constexpr int Q_BYTES = 128 * HD_PAD * 2;  // chunk-major: KCH x [128 rows x 128 B]
   static constexpr int KV_BYTES = BLOCK_KV * HD_PAD * 2;
   static constexpr int P_BYTES = 128 * BLOCK_KV * 2;  // (BLOCK_KV/64) x [128 rows x 128 B]
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = Q_BYTES;
-  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + 2 * KV_BYTES;
+  static constexpr int OFF_V = OFF_K + KBUF * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + VBUF * KV_BYTES;
   static constexpr int OFF_BAR = OFF_P + P_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-  static constexpr int TMEM_S0 = 0;            // S buffers at columns [0, BLOCK_KV) and [BLOCK_KV, 2*BLOCK_KV)
-  static constexpr int TMEM_O = 2 * BLOCK_KV;  // O accumulator
-  static constexpr int TMEM_COLS = (2 * BLOCK_KV + HD_PAD) <= 256 ? 256 : 512;
+  static constexpr int TMEM_S0 = 0;               // S buffers at columns [i*BLOCK_KV, (i+1)*BLOCK_KV)
+  static constexpr int TMEM_O = SBUF * BLOCK_KV;  // O accumulator
+  static constexpr int TMEM_COLS = (SBUF * BLOCK_KV + HD_PAD) <= 256 ? 256 : 512;
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "smem for the intended occupancy");
+  static_assert(CTAS_PER_SM * TMEM_COLS <= 512, "TMEM for the intended occupancy");
   static_assert(HD_PAD % 64 == 0 && HD_PAD <= 192, "head pad");
   static_assert(BLOCK_KV == 64 || BLOCK_KV == 128, "kv tile");
   static_assert(SMEM_BYTES <= SMEM_BUDGET, "smem");
@@ -69,7 +78,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 template <int HD_PAD, int BLOCK_KV>
-__global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) attn_kernel(const __grid_constant__ AttnParams p) {
   using C = AttnCfg<HD_PAD, BLOCK_KV>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,19 +131,19 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
       for (int c = 0; c < C::KCH; ++c)
         tma_load_3d(smem + C::OFF_Q + c * (128 * 128), &p.tma_q, &bars->q_full, col0 + c * 64, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bars->k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->k_full[s], C::KV_BYTES);
+        const int ks = j % C::KBUF, vs = j % C::VBUF;
+        const uint32_t kph = (j / C::KBUF) & 1, vph = (j / C::VBUF) & 1;
+        mbar_wait(&bars->k_empty[ks], kph ^ 1);
+        mbar_arrive_expect_tx(&bars->k_full[ks], C::KV_BYTES);
 #pragma unroll
         for (int c = 0; c < C::KCH; ++c)
-          tma_load_3d(smem + C::OFF_K + s * C::KV_BYTES + c * (BLOCK_KV * 128), &p.tma_k, &bars->k_full[s],
+          tma_load_3d(smem + C::OFF_K + ks * C::KV_BYTES + c * (BLOCK_KV * 128), &p.tma_k, &bars->k_full[ks],
                       col0 + c * 64, j * BLOCK_KV, b);
-        mbar_wait(&bars->v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&bars->v_full[s], C::KV_BYTES);
+        mbar_wait(&bars->v_empty[vs], vph ^ 1);
+        mbar_arrive_expect_tx(&bars->v_full[vs], C::KV_BYTES);
 #pragma unroll
         for (int c = 0; c < C::KCH; ++c)
-          tma_load_3d(smem + C::OFF_V + s * C::KV_BYTES + c * (BLOCK_KV * 128), &p.tma_v, &bars->v_full[s],
+          tma_load_3d(smem + C::OFF_V + vs * C::KV_BYTES + c * (BLOCK_KV * 128), &p.tma_v, &bars->v_full[vs],
                       col0 + c * 64, j * BLOCK_KV, b);
       }
     }
@@ -147,12 +156,12 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
       const uint32_t sq = smem_u32(smem + C::OFF_Q);
       const uint32_t sp = smem_u32(smem + C::OFF_P);
       auto issue_s = [&](int j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bars->k_full[s], ph);
-        mbar_wait(&bars->s_empty[s], ph ^ 1);
+        const int ks = j % C::KBUF, s = j % C::SBUF;
+        const uint32_t kph = (j / C::KBUF) & 1, sph = (j / C::SBUF) & 1;
+        mbar_wait(&bars->k_full[ks], kph);
+        mbar_wait(&bars->s_empty[s], sph ^ 1);
         tc_fence_after();
-        const uint32_t sk = smem_u32(smem + C::OFF_K + s * C::KV_BYTES);
+        const uint32_t sk = smem_u32(smem + C::OFF_K + ks * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < HD_PAD / 16; ++k) {
           const int c = k >> 2, kk = k & 3;
@@ -161,18 +170,20 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
           umma_f16(tmem_base + C::TMEM_S0 + s * BLOCK_KV, da, db, idesc_s, k != 0 ? 1u : 0u);
         }
         umma_commit(&bars->s_full[s]);
-        umma_commit(&bars->k_empty[s]);
+        umma_commit(&bars->k_empty[ks]);
       };
       mbar_wait(&bars->q_full, 0);
       issue_s(0);
       for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_s(j + 1);
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&bars->v_full[s], ph);
+        // S_{j+1} overlaps the softmax of tile j when S is double buffered; with a single S buffer it is issued as
+        // soon as the softmax has drained S_j (s_empty), i.e. concurrently with P_j.V_j below.
+        if (C::SBUF == 2 && j + 1 < n_tiles) issue_s(j + 1);
+        const int vs = j % C::VBUF;
+        const uint32_t vph = (j / C::VBUF) & 1;
+        mbar_wait(&bars->v_full[vs], vph);
         mbar_wait(&bars->p_full, j & 1);
         tc_fence_after();
-        const uint32_t sv = smem_u32(smem + C::OFF_V + s * C::KV_BYTES);
+        const uint32_t sv = smem_u32(smem + C::OFF_V + vs * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < BLOCK_KV / 16; ++k) {
           // A = P: K-major, 64-kv chunks of [128 x 128 B]; B = V: MN-major, rows = kv, LBO = 64-column chunk stride
@@ -180,9 +191,10 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
           const uint64_t db = make_smem_desc_sw128(sv + k * (16 * 128), BLOCK_KV * 128, 1024);
           umma_f16(tmem_base + C::TMEM_O, da, db, idesc_o, (j | k) != 0 ? 1u : 0u);
         }
-        umma_commit(&bars->v_empty[s]);
+        umma_commit(&bars->v_empty[vs]);
         umma_commit(&bars->p_empty);
         if (j == n_tiles - 1) umma_commit(&bars->o_done);
+        if (C::SBUF == 1 && j + 1 < n_tiles) issue_s(j + 1);
       }
     }
   } else if (warp >= 4) {
@@ -196,13 +208,15 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
     float m_used = -INFINITY, l = 0.f;
     const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
     for (int j = 0; j < n_tiles; ++j) {
-      const int s = j & 1;
-      const uint32_t ph = (j >> 1) & 1;
+      const int s = j % C::SBUF;
+      const uint32_t ph = (j / C::SBUF) & 1;
       mbar_wait(&bars->s_full[s], ph);
       tc_fence_after();
       const uint32_t ts = tmem_base + C::TMEM_S0 + s * BLOCK_KV + lane_off;
       const int kv0 = j * BLOCK_KV;
       const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
+      // interior tiles (every column visible to every row of this warp) skip all masking work
+      const bool no_mask = __all_sync(0xffffffffu, lim >= BLOCK_KV - 1);
       // pass 1: row max
       float mx = -INFINITY;
 #pragma unroll 1
@@ -210,9 +224,14 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
         uint32_t v[32];
         tmem_ld_32x32b_x32(ts + c, v);
         tmem_wait_ld();
+        if (no_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       mx *= p.scale_log2;
       // lazy rescale decision (warp-uniform because tcgen05.ld/st are .sync.aligned)
@@ -251,15 +270,22 @@ __global__ void __launch_bounds__(256, 1) attn_kernel(const __grid_constant__ At
         tmem_ld_32x32b_x32(ts + c, v);
         tmem_wait_ld();
         uint32_t pk[16];
+        if (no_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c + i <= lim) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used) : 0.f;
-          float p1 = (c + i + 1 <= lim) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used) : 0.f;
-          // accumulate the row sum from the ROUNDED probabilities so that numerator and denominator agree
-          uint32_t u = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-          const float2 f = bf16 ? unpack_bf16x2(u) : unpack_f16x2(u);
-          l += f.x + f.y;
-          pk[i >> 1] = u;
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used);
+            const float p1 = fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used);
+            l += p0 + p1;
+            pk[i >> 1] = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (c + i <= lim) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used) : 0.f;
+            const float p1 = (c + i + 1 <= lim) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used) : 0.f;
+            l += p0 + p1;
+            pk[i >> 1] = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+          }
         }
         uint8_t* chunk = sp + (c >> 6) * (128 * 128) + r * 128;
         const int u0 = (c & 63) >> 3;  // first 16-B unit of this 32-column group within the 64-column chunk

@@ -6,7 +6,8 @@
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16 per instruction)
 //   warp 2        : TMEM allocator
-//   warps 4..7    : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/residual -> vectorised global stores)
+//   warps 4..11   : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/residual -> vectorised global stores);
+//                   warps w and w+4 share a TMEM lane quadrant and split the tile's columns in halves
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // The A operand has two addressing modes:
@@ -23,7 +24,7 @@ namespace gb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // warps 0-3: producer / MMA / TMEM alloc / spare; warps 4-11: epilogue
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 enum { A_PLAIN = 0, A_CONV3X3 = 1 };
@@ -67,7 +68,7 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
   static constexpr int ACC_STRIDE = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "invalid UMMA N / epilogue split");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-B alignment");
 };
 
@@ -216,13 +217,25 @@ __device__ __forceinline__ void store_elem(void* base, long long idx, float v, i
 __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, int row, int n, float* v) {
   const bool geglu = p.act == ACT_GEGLU;
   const int n_out_total = geglu ? p.N / 2 : p.N;
+  if (p.alpha != 1.f) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
+    for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
+  }
   if (p.bias) {
     if (p.bias_along_m) {
       const float b = p.bias[row];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += b;
+    } else if (n + 16 <= p.N && (reinterpret_cast<uintptr_t>(p.bias + n) & 15) == 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldg(b4 + i);
+        v[4 * i] += t.x;
+        v[4 * i + 1] += t.y;
+        v[4 * i + 2] += t.z;
+        v[4 * i + 3] += t.w;
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j)
@@ -231,9 +244,21 @@ __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, int row, i
   }
   if (p.rowbias) {
     const float* rb = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ld_rowbias;
+    if (n + 16 <= p.N && (reinterpret_cast<uintptr_t>(rb + n) & 15) == 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(rb + n);
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (n + j < p.N) v[j] += __ldg(rb + n + j);
+      for (int i = 0; i < 4; ++i) {
+        const float4 t = __ldg(b4 + i);
+        v[4 * i] += t.x;
+        v[4 * i + 1] += t.y;
+        v[4 * i + 2] += t.z;
+        v[4 * i + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (n + j < p.N) v[j] += __ldg(rb + n + j);
+    }
   }
   int cnt = 16, no = n;
   if (geglu) {
@@ -312,7 +337,9 @@ template <int BLOCK_N>
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint32_t tmem_base, int num_m, int num_tiles) {
   using C = GemmCfg<BLOCK_N>;
-  const int ewarp = (threadIdx.x >> 5) & 3;  // TMEM lane quadrant this warp may access
+  const int ewarp = (threadIdx.x >> 5) & 3;        // TMEM lane quadrant this warp may access
+  const int half = ((threadIdx.x >> 5) - 4) >> 2;  // column half handled by this warp
+  constexpr int HALF_N = BLOCK_N / 2;              // multiple of 16 for every instantiated BLOCK_N
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -323,7 +350,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tme
     tc_fence_after();
     const uint32_t taddr = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(ewarp * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
+    for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += 16) {
       uint32_t r[16];
       tmem_ld_32x32b_x16(taddr + c, r);
       tmem_wait_ld();
@@ -377,7 +404,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 4);
+      mbar_init(&bars->tmem_empty[i], 8);
     }
     fence_barrier_init();
   }

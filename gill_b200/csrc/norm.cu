@@ -151,22 +151,35 @@ __device__ __forceinline__ Vec8 gn_load(const GnSrc& s, long long pix, int v, in
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int HW, int G, int chunks,
                                                        float* __restrict__ partial /* [B, chunks, G, 2] */) {
-  extern __shared__ float sm[];  // [C] sums, [C] sumsq
+  // Thread t owns channel vector v and pixel subgroup sg: 256 consecutive threads read 256 consecutive 16-byte
+  // vectors (NHWC is pixel-major, so the next pixel's channels follow). Per-thread register sums -> smem
+  // [sg][sum|sumsq][C] -> per-group totals summed in a fixed order: no atomics, bit-reproducible.
+  extern __shared__ float sm[];
   const int C = src.C0 + src.C1;
   const int nvec = C >> 3;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int pix_per_chunk = (HW + chunks - 1) / chunks;
   const int p0 = chunk * pix_per_chunk, p1 = min(HW, p0 + pix_per_chunk);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  for (int vb = 0; vb < nvec; vb += 32) {
-    const int v = vb + lane;
-    float s[8], q[8];
+  const bool wide = nvec >= 256;
+  const int sgs = wide ? 1 : 256 / nvec;
+  const int vper = wide ? (nvec + 255) / 256 : 1;
+  for (int vi = 0; vi < vper; ++vi) {
+    int v, sg;
+    bool active;
+    if (wide) {
+      v = vi * 256 + threadIdx.x;
+      sg = 0;
+      active = v < nvec;
+    } else {
+      v = threadIdx.x % nvec;
+      sg = threadIdx.x / nvec;
+      active = sg < sgs;
+    }
+    if (active) {
+      float s[8], q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    if (v < nvec) {
-      for (int pix = p0 + warp; pix < p1; pix += nwarps) {
+      for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+      for (int pix = p0 + sg; pix < p1; pix += sgs) {
         const Vec8 x = gn_load(src, static_cast<long long>(b) * HW + pix, v, dtype);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -174,10 +187,12 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
           q[j] += x.v[j] * x.v[j];
         }
       }
+      float* ps = sm + (sg * 2) * C + v * 8;
+      float* pq = sm + (sg * 2 + 1) * C + v * 8;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sm[v * 8 + j], s[j]);
-        atomicAdd(&sm[C + v * 8 + j], q[j]);
+        ps[j] = s[j];
+        pq[j] = q[j];
       }
     }
   }
@@ -185,9 +200,13 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float s = 0.f, q = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      s += sm[c];
-      q += sm[C + c];
+    for (int sg = 0; sg < sgs; ++sg) {
+      const float* ps = sm + (sg * 2) * C;
+      const float* pq = sm + (sg * 2 + 1) * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        s += ps[c];
+        q += pq[c];
+      }
     }
     float* o = partial + ((static_cast<long long>(b) * chunks + chunk) * G + g) * 2;
     o[0] = s;
@@ -331,8 +350,10 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   // fill the machine: B * chunks CTAs
   while (chunks > 1 && B * chunks > 4 * num_sms()) chunks >>= 1;
   const size_t smem = 2 * C * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, B), 256, smem, stream>>>(src, dtype, HW, G, chunks,
-                                                         reinterpret_cast<float*>(workspace));
+  const int nvec = C / 8;
+  const size_t smem_stats = static_cast<size_t>(nvec >= 256 ? 1 : 256 / nvec) * 2 * C * sizeof(float);
+  gn_stats_kernel<<<dim3(chunks, B), 256, smem_stats, stream>>>(src, dtype, HW, G, chunks,
+                                                               reinterpret_cast<float*>(workspace));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   int pix_per_block = (32768 + C - 1) / C;  // ~32K elements per CTA
