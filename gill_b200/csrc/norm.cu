@@ -179,7 +179,21 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
       float s[8], q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-      for (int pix = p0 + sg; pix < p1; pix += sgs) {
+      int pix = p0 + sg;
+      for (; pix + 3 * sgs < p1; pix += 4 * sgs) {  // 4 independent 16-byte loads in flight per thread
+        Vec8 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = gn_load(src, static_cast<long long>(b) * HW + pix + u * sgs, v, dtype);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s[j] += x[u].v[j];
+            q[j] += x[u].v[j] * x[u].v[j];
+          }
+        }
+      }
+      for (; pix < p1; pix += sgs) {
         const Vec8 x = gn_load(src, static_cast<long long>(b) * HW + pix, v, dtype);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -214,21 +228,17 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int HW, int G, int chunks,
-                                                       const float* __restrict__ partial, const float* __restrict__ w,
-                                                       const float* __restrict__ bias, float eps, int silu,
-                                                       void* __restrict__ out, int out_dtype, int pix_per_block) {
-  extern __shared__ float sm[];  // [C] scale, [C] shift
-  const int C = src.C0 + src.C1;
-  const int nvec = C >> 3;
-  const int b = blockIdx.y;
-  const int cpg = C / G;
-  float* sc = sm;
-  float* sh = sm + C;
+// Per-(sample, channel) affine of the normalisation: y = x * scale + shift. One tiny launch per GroupNorm so that the
+// elementwise pass below needs no shared memory and no per-CTA recomputation.
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, int C, int HW,
+                                   const float* __restrict__ w, const float* __restrict__ bias, float eps,
+                                   float* __restrict__ scale_shift /* [B, 2, C] */) {
   __shared__ float gmean[64], grstd[64];
+  const int b = blockIdx.x;
+  const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float s = 0.f, q = 0.f;
-    for (int ch = 0; ch < chunks; ++ch) {
+    for (int ch = 0; ch < chunks; ++ch) {  // fixed order: deterministic
       const float* pp = partial + ((static_cast<long long>(b) * chunks + ch) * G + g) * 2;
       s += pp[0];
       q += pp[1];
@@ -240,27 +250,75 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int
     grstd[g] = rsqrtf(var + eps);
   }
   __syncthreads();
+  float* sc = scale_shift + static_cast<long long>(b) * 2 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const float a = grstd[g] * w[c];
     sc[c] = a;
-    sh[c] = bias[c] - gmean[g] * a;
+    sc[C + c] = bias[c] - gmean[g] * a;
   }
-  __syncthreads();
+}
+
+// Elementwise normalise (+SiLU). Thread t owns channel vector v = t % nvec (scale/shift live in 16 registers) and
+// walks pixels with stride (256 / nvec): 256 consecutive threads touch 256 consecutive 16-byte vectors.
+__global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int HW, const float* __restrict__ scale_shift,
+                                                       int silu, void* __restrict__ out, int out_dtype,
+                                                       int pix_per_block) {
+  const int C = src.C0 + src.C1;
+  const int nvec = C >> 3;
+  const int b = blockIdx.y;
+  const bool wide = nvec >= 256;
+  const int sgs = wide ? 1 : 256 / nvec;
+  const int vper = wide ? (nvec + 255) / 256 : 1;
   const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
-  const long long total = static_cast<long long>(p1 - p0) * nvec;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int pix = p0 + static_cast<int>(i / nvec);
-    const int v = static_cast<int>(i % nvec);
-    const long long gp = static_cast<long long>(b) * HW + pix;
-    Vec8 x = gn_load(src, gp, v, dtype);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = x.v[j] * sc[v * 8 + j] + sh[v * 8 + j];
-      if (silu) y = y / (1.f + __expf(-y));
-      x.v[j] = y;
+  const float* sc = scale_shift + static_cast<long long>(b) * 2 * C;
+  for (int vi = 0; vi < vper; ++vi) {
+    int v, sg;
+    bool active;
+    if (wide) {
+      v = vi * 256 + threadIdx.x;
+      sg = 0;
+      active = v < nvec;
+    } else {
+      v = threadIdx.x % nvec;
+      sg = threadIdx.x / nvec;
+      active = sg < sgs;
     }
-    store8(out, gp * C + v * 8, x, out_dtype);
+    if (!active) continue;
+    float a[8], d[8];
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(sc + v * 8), a1 = *reinterpret_cast<const float4*>(sc + v * 8 + 4);
+      const float4 d0 = *reinterpret_cast<const float4*>(sc + C + v * 8), d1 = *reinterpret_cast<const float4*>(sc + C + v * 8 + 4);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+    }
+    int pix = p0 + sg;
+    // 4 independent 16-byte loads in flight per thread
+    for (; pix + 3 * sgs < p1; pix += 4 * sgs) {
+      Vec8 x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = gn_load(src, static_cast<long long>(b) * HW + pix + u * sgs, v, dtype);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = fmaf(x[u].v[j], a[j], d[j]);
+          if (silu) y = __fdividef(y, 1.f + __expf(-y));
+          x[u].v[j] = y;
+        }
+        store8(out, (static_cast<long long>(b) * HW + pix + u * sgs) * C + v * 8, x[u], out_dtype);
+      }
+    }
+    for (; pix < p1; pix += sgs) {
+      Vec8 x = gn_load(src, static_cast<long long>(b) * HW + pix, v, dtype);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float y = fmaf(x.v[j], a[j], d[j]);
+        if (silu) y = __fdividef(y, 1.f + __expf(-y));
+        x.v[j] = y;
+      }
+      store8(out, (static_cast<long long>(b) * HW + pix) * C + v * 8, x, out_dtype);
+    }
   }
 }
 
@@ -332,7 +390,10 @@ extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, co
   return 0;
 }
 
-extern "C" long long gillb200_groupnorm_workspace_bytes(int B, int G) { return 64LL * B * G * 2 * sizeof(float); }
+extern "C" long long gillb200_groupnorm_workspace_bytes(int B, int G) {
+  // [B, 64 chunks, G, 2] partial sums + [B, 2, C<=4096] scale/shift
+  return (64LL * B * G * 2 + 2LL * B * 4096) * sizeof(float);
+}
 
 extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1, int dtype, int B, int HW, int G,
                                   const float* w, const float* b, float eps, int silu, void* out, int out_dtype,
@@ -340,28 +401,30 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x0 && w && b && out && workspace, "null pointer");
   const int C = C0 + C1;
-  GB_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % G == 0 && G <= 64, "groupnorm: C0=%d C1=%d G=%d", C0, C1, G);
+  GB_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % G == 0 && G <= 64 && C <= 4096, "groupnorm: C0=%d C1=%d G=%d", C0, C1, G);
   GB_CHECK_ARG(C1 == 0 || x1 != nullptr, "groupnorm: second source missing");
   GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16 || dtype == DT_F32, "bad dtype");
   GnSrc src{x0, x1, C0, C1};
   int chunks = HW / 64;
   if (chunks > 64) chunks = 64;
   if (chunks < 1) chunks = 1;
-  // fill the machine: B * chunks CTAs
-  while (chunks > 1 && B * chunks > 4 * num_sms()) chunks >>= 1;
-  const size_t smem = 2 * C * sizeof(float);
+  while (chunks > 1 && B * chunks > 8 * num_sms()) chunks >>= 1;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* scale_shift = partial + 64LL * B * G * 2;
   const int nvec = C / 8;
   const size_t smem_stats = static_cast<size_t>(nvec >= 256 ? 1 : 256 / nvec) * 2 * C * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, B), 256, smem_stats, stream>>>(src, dtype, HW, G, chunks,
-                                                               reinterpret_cast<float*>(workspace));
+  gn_stats_kernel<<<dim3(chunks, B), 256, smem_stats, stream>>>(src, dtype, HW, G, chunks, partial);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
-  int pix_per_block = (32768 + C - 1) / C;  // ~32K elements per CTA
-  if (pix_per_block < 1) pix_per_block = 1;
+  gn_finalize_kernel<<<B, 256, 0, stream>>>(partial, chunks, G, C, HW, w, b, eps, scale_shift);
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  // ~64K elements per CTA, at least 2 waves of CTAs when the tensor is large enough
+  int pix_per_block = (65536 + C - 1) / C;
+  const int sgs = nvec >= 256 ? 1 : 256 / nvec;
+  pix_per_block = ((pix_per_block + 4 * sgs - 1) / (4 * sgs)) * (4 * sgs);
   const int blocks = (HW + pix_per_block - 1) / pix_per_block;
-  gn_apply_kernel<<<dim3(blocks, B), 256, smem, stream>>>(src, dtype, HW, G, chunks,
-                                                         reinterpret_cast<const float*>(workspace), w, b, eps, silu,
-                                                         out, out_dtype, pix_per_block);
+  gn_apply_kernel<<<dim3(blocks, B), 256, 0, stream>>>(src, dtype, HW, scale_shift, silu, out, out_dtype, pix_per_block);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;

@@ -21,10 +21,10 @@ PROFILE = None
 
 
 class _P:
-    __slots__ = ("name", "flops", "bytes", "e0")
+    __slots__ = ("name", "flops", "bytes", "e0", "sig")
 
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.name, self.flops, self.bytes = name, flops, nbytes
+    def __init__(self, name, flops=0.0, nbytes=0.0, sig=""):
+        self.name, self.flops, self.bytes, self.sig = name, flops, nbytes, sig
 
     def __enter__(self):
         if PROFILE is not None:
@@ -36,15 +36,16 @@ class _P:
         if PROFILE is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1))
+            PROFILE.append((self.name, self.flops, self.bytes, self.e0, e1, self.sig))
         return False
 
 
-def profile_summary(records):
-    """Aggregate PROFILE records per kernel family -> {name: dict(ms, launches, flops, bytes)} (call after a sync)."""
+def profile_summary(records, by_shape=False):
+    """Aggregate PROFILE records per kernel family (or per family+shape) -> {name: dict(ms, launches, flops, bytes)}.
+    Call after a synchronize."""
     out = {}
-    for name, fl, by, e0, e1 in records:
-        d = out.setdefault(name, dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
+    for name, fl, by, e0, e1, sig in records:
+        d = out.setdefault(name + (" " + sig if by_shape and sig else ""), dict(ms=0.0, launches=0, flops=0.0, bytes=0.0))
         d["ms"] += e0.elapsed_time(e1)
         d["launches"] += 1
         d["flops"] += fl
@@ -117,7 +118,7 @@ def gemm(
     g.act, g.alpha, g.block_n = _ACT[act], alpha, block_n
     ktot = K + (g.k2 if a2_mode == 1 else 0)
     with _P("gemm" if a2_mode != 2 else "gemm_split", 2.0 * M * N * ktot * (2 if a2_mode == 2 else 1),
-            2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out):
+            2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out, f"M{M} N{N} K{ktot} {act or ''}"):
         check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm")
     return out
 
@@ -170,7 +171,8 @@ def conv3x3(
         r2 = residual.view(B * H * W, N)
         g.residual, g.ldr, g.res_dtype = r2.data_ptr(), r2.stride(0), _DT[residual.dtype]
     g.act, g.alpha, g.block_n = _ACT[act], 1.0, block_n
-    with _P("conv3x3", 2.0 * B * H * W * N * (9 * C + (g.k2 or 0)), 2.0 * (B * H * W * C + N * 9 * C + B * H * W * N)):
+    with _P("conv3x3", 2.0 * B * H * W * N * (9 * C + (g.k2 or 0)), 2.0 * (B * H * W * C + N * 9 * C + B * H * W * N),
+            f"B{B} {H}x{W} C{C}->{N}"):
         check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")
     return out
 
@@ -231,7 +233,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
     a.B, a.H, a.Lq, a.Lk, a.hd_pad = B, heads, Lq, Lk, hd_pad
     a.causal, a.causal_offset = int(causal), causal_offset
     a.dtype, a.scale = _DT[q.dtype], scale
-    with _P("attention", 4.0 * B * heads * Lq * Lk * hd_pad, 2.0 * B * heads * hd_pad * (2 * Lq + 2 * Lk)):
+    with _P("attention", 4.0 * B * heads * Lq * Lk * hd_pad, 2.0 * B * heads * hd_pad * (2 * Lq + 2 * Lk),
+            f"B{B} H{heads} Lq{Lq} Lk{Lk} hp{hd_pad}"):
         check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")
     return out
 
@@ -248,7 +251,7 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e
     assert w.dtype == torch.float32 and b.dtype == torch.float32
     if out is None:
         out = torch.empty((rows, C), device=x.device, dtype=out_dtype or x.dtype)
-    with _P("layernorm"):
+    with _P("layernorm", 0.0, (x.element_size() + out.element_size()) * rows * C, f"rows{rows} C{C}"):
         check(lib().gillb200_layernorm(x.data_ptr(), x.stride(0), _DT[x.dtype], w.data_ptr(), b.data_ptr(), eps, rows, C,
                                        out.data_ptr(), out.stride(0), _DT[out.dtype], _ptr(out_lo), _stream()), "gillb200_layernorm")
     return out
@@ -271,7 +274,7 @@ def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, ep
     if ws is None:
         ws = torch.empty(lib().gillb200_groupnorm_workspace_bytes(B, groups), device=x.device, dtype=torch.uint8)
         _gn_ws[key] = ws
-    with _P("groupnorm"):
+    with _P("groupnorm", 0.0, (2 * x.element_size() + out.element_size()) * B * H * W * (C0 + C1), f"B{B} {H}x{W} C{C0 + C1}"):
         check(lib().gillb200_groupnorm(x.data_ptr(), C0, _ptr(x2), C1, _DT[x.dtype], B, H * W, groups, w.data_ptr(),
                                        b.data_ptr(), eps, int(silu), out.data_ptr(), _DT[out.dtype], ws.data_ptr(),
                                        _stream()), "gillb200_groupnorm")

@@ -216,6 +216,8 @@ class UNetB200:
         self._put("temb_proj_all.weight", torch.cat(ws, 0), torch.float16)
         self._put("temb_proj_all.bias", torch.cat(bs, 0), f32)
         self.temb_total = off
+        # fixed-address buffer holding the current step's time projections (captured graphs read it)
+        self._temb_cur = torch.zeros((1, off), device=self.dev, dtype=torch.float32)
 
     # ------------------------------------------------------------------------------------------------ hoisted work
     def prepare_timesteps(self, timesteps: List[int]):
@@ -249,7 +251,6 @@ class UNetB200:
         ah, al = split(act)
         self._temb_table = ops.gemm(ah, self.w["temb_proj_all.weight"], a2=al, a2_mode=2,
                                     bias=self.w["temb_proj_all.bias"], out_dtype=torch.float32)  # [n, sum_c]
-        self._temb_cur = torch.empty((1, self.temb_total), device=self.dev, dtype=torch.float32)
         self._temb_steps = key
 
     def set_step(self, step: int):
