@@ -98,4 +98,5 @@ class AttnArgs(ctypes.Structure):
         ("causal", _c_int), ("causal_offset", _c_int),
         ("dtype", _c_int),
         ("scale", _c_float),
+        ("ones_col", _c_int),
     ]

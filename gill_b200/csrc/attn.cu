@@ -30,6 +30,8 @@ struct alignas(64) AttnParams {
   int causal, causal_offset;  // key j visible to query i iff j <= i + causal_offset
   int out_dtype;
   int in_dtype;
+  int ones_col;      // >= 0: column (inside the head padding) where V holds 1.0, so O[:, ones_col] IS the softmax
+                     // denominator (computed by the tensor core from the same rounded P as the numerator); -1: none
   float scale_log2;  // softmax scale * log2(e)
 };
 
@@ -74,6 +76,12 @@ struct AttnBars {
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two exponentials per MUFU operation; the result is already the packed fp16 pair the P tile stores
+__device__ __forceinline__ uint32_t exp2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
     const bool bf16 = p.in_dtype == DT_BF16;
     uint8_t* sp = smem + C::OFF_P;
     float m_used = -INFINITY, l = 0.f;
+    const bool packed = !bf16 && p.ones_col >= 0;  // fp16 P with the denominator taken from V's ones column
     const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j % C::SBUF;
@@ -270,7 +279,18 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
         tmem_ld_32x32b_x32(ts + c, v);
         tmem_wait_ld();
         uint32_t pk[16];
-        if (no_mask) {
+        if (packed) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float x0 = fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used);
+            float x1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used);
+            if (!no_mask) {
+              x0 = (c + i <= lim) ? x0 : -60000.f;
+              x1 = (c + i + 1 <= lim) ? x1 : -60000.f;
+            }
+            pk[i >> 1] = exp2_f16x2(pack_f16x2(x0, x1));
+          }
+        } else if (no_mask) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const float p0 = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used);
@@ -306,8 +326,12 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
     // epilogue: O / l
     mbar_wait(&bars->o_done, 0);
     tc_fence_after();
-    const float inv = 1.f / l;
     const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+    if (packed) {
+      l = __uint_as_float(tmem_ld_32x32b_x1(to + p.ones_col));
+      tmem_wait_ld();
+    }
+    const float inv = 1.f / l;
     uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
                      static_cast<long long>(qrow) * p.ldo + col0;
 #pragma unroll 1
@@ -393,6 +417,7 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   p.out_dtype = a->dtype;
   p.in_dtype = a->dtype;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.ones_col = (a->ones_col > 0 && a->ones_col < a->hd_pad) ? a->ones_col : -1;
   if (a->hd_pad == 64) return launch_attn<64, 128>(p, stream);
   if (a->hd_pad == 128) return launch_attn<128, 128>(p, stream);
   return launch_attn<192, 64>(p, stream);

@@ -405,10 +405,12 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   GB_CHECK_ARG(C1 == 0 || x1 != nullptr, "groupnorm: second source missing");
   GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16 || dtype == DT_F32, "bad dtype");
   GnSrc src{x0, x1, C0, C1};
-  int chunks = HW / 64;
+  // ~2 CTAs per SM in flight, each thread streaming >= 4 independent 16-byte loads
+  int chunks = (2 * num_sms() + B - 1) / B;
   if (chunks > 64) chunks = 64;
+  if (chunks > HW) chunks = HW;
   if (chunks < 1) chunks = 1;
-  while (chunks > 1 && B * chunks > 8 * num_sms()) chunks >>= 1;
+  chunks = (HW + (HW + chunks - 1) / chunks - 1) / ((HW + chunks - 1) / chunks);  // drop empty chunks
   float* partial = reinterpret_cast<float*>(workspace);
   float* scale_shift = partial + 64LL * B * G * 2;
   const int nvec = C / 8;
@@ -419,9 +421,11 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   gn_finalize_kernel<<<B, 256, 0, stream>>>(partial, chunks, G, C, HW, w, b, eps, scale_shift);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
-  // ~64K elements per CTA, at least 2 waves of CTAs when the tensor is large enough
+  // ~64K elements per CTA, but never fewer than ~4 CTAs per SM worth of blocks when the tensor is small
   int pix_per_block = (65536 + C - 1) / C;
   const int sgs = nvec >= 256 ? 1 : 256 / nvec;
+  const int want_blocks = (4 * num_sms() + B - 1) / B;
+  if (pix_per_block * want_blocks > HW) pix_per_block = (HW + want_blocks - 1) / want_blocks;
   pix_per_block = ((pix_per_block + 4 * sgs - 1) / (4 * sgs)) * (4 * sgs);
   const int blocks = (HW + pix_per_block - 1) / pix_per_block;
   gn_apply_kernel<<<dim3(blocks, B), 256, 0, stream>>>(src, dtype, HW, scale_shift, silu, out, out_dtype, pix_per_block);

@@ -216,9 +216,10 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_pad: int, scale: float, *,
               out: Optional[torch.Tensor] = None, causal: bool = False, causal_offset: int = 0,
-              kv_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+              kv_lens: Optional[torch.Tensor] = None, ones_col: int = 0) -> torch.Tensor:
     """q [B,Lq,>=H*hd_pad], k/v [B,Lk,>=H*hd_pad] (views into fused QKV buffers allowed; last dim contiguous).
-    Returns out [B,Lq,H*hd_pad]. Pad columns of each head must be zero in q, k, v."""
+    Returns out [B,Lq,H*hd_pad]. Pad columns of each head must be zero in q, k, v -- except that v may carry 1.0 in
+    pad column `ones_col` (> 0) of every head, which moves the softmax row sum onto the tensor core (fp16 only)."""
     B, Lq, _ = q.shape
     Lk = k.shape[1]
     for t in (q, k, v):
@@ -232,7 +233,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
     a.kv_lens = _ptr(kv_lens)
     a.B, a.H, a.Lq, a.Lk, a.hd_pad = B, heads, Lq, Lk, hd_pad
     a.causal, a.causal_offset = int(causal), causal_offset
-    a.dtype, a.scale = _DT[q.dtype], scale
+    a.dtype, a.scale, a.ones_col = _DT[q.dtype], scale, ones_col
     with _P("attention", 4.0 * B * heads * Lq * Lk * hd_pad, 2.0 * B * heads * hd_pad * (2 * Lq + 2 * Lk),
             f"B{B} H{heads} Lq{Lq} Lk{Lk} hp{hd_pad}"):
         check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")

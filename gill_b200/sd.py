@@ -145,6 +145,13 @@ class UNetB200:
             self._put(f"{t}.{n}.bias", sd[f"{t}.{n}.bias"], f32)
         q, k, v = (sd[f"{t}.attn1.to_{x}.weight"].float() for x in "qkv")
         self._put(f"{t}.attn1.qkv", torch.cat([_pad_heads_rows(x, H, hd, hp) for x in (q, k, v)], 0))
+        # V carries 1.0 in the first padding column of every head (a bias on zero weight rows): the attention kernel
+        # then reads the softmax denominator out of the P.V accumulator instead of summing P on the CUDA cores
+        ones = torch.zeros(H, hp)
+        if hp > hd:
+            ones[:, hd] = 1.0
+        self._put(f"{t}.attn1.qkv_bias", torch.cat([torch.zeros(2 * H * hp), ones.reshape(-1)]), f32)
+        self._put(f"{t}.attn2.kv_bias", torch.cat([torch.zeros(H * hp), ones.reshape(-1)]), f32)
         self._put(f"{t}.attn1.out.weight", _pad_heads_cols(sd[f"{t}.attn1.to_out.0.weight"].float(), H, hd, hp))
         self._put(f"{t}.attn1.out.bias", sd[f"{t}.attn1.to_out.0.bias"], f32)
         self._put(f"{t}.attn2.q", _pad_heads_rows(sd[f"{t}.attn2.to_q.weight"].float(), H, hd, hp))
@@ -266,10 +273,11 @@ class UNetB200:
         res = {} if out is None else out
         for p in self.tf_layers:
             w = self.w[f"{p}.transformer_blocks.0.attn2.kv"]
+            bias = self.w[f"{p}.transformer_blocks.0.attn2.kv_bias"]
             if out is None:
-                res[p] = ops.gemm(c2, w).view(B2, L, -1)
+                res[p] = ops.gemm(c2, w, bias=bias).view(B2, L, -1)
             else:
-                ops.gemm(c2, w, out=out[p].view(B2 * L, -1))
+                ops.gemm(c2, w, bias=bias, out=out[p].view(B2 * L, -1))
         return res
 
     # ------------------------------------------------------------------------------------------------ blocks
@@ -304,15 +312,16 @@ class UNetB200:
         h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"])
         # self attention
         n1 = ops.layernorm(h, w[t + ".norm1.weight"], w[t + ".norm1.bias"], 1e-5)
-        qkv = ops.gemm(n1, w[t + ".attn1.qkv"]).view(B, L, 3 * Hh * hp)
+        oc = hd if hp > hd else 0
+        qkv = ops.gemm(n1, w[t + ".attn1.qkv"], bias=w[t + ".attn1.qkv_bias"]).view(B, L, 3 * Hh * hp)
         a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
-                          hd ** -0.5)
+                          hd ** -0.5, ones_col=oc)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h)
         # cross attention against the precomputed K/V of the conditioning
         n2 = ops.layernorm(h, w[t + ".norm2.weight"], w[t + ".norm2.bias"], 1e-5)
         q = ops.gemm(n2, w[t + ".attn2.q"]).view(B, L, Hh * hp)
         kv = ctx_kv[p]
-        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5)
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h)
         # GEGLU feed-forward
         n3 = ops.layernorm(h, w[t + ".norm3.weight"], w[t + ".norm3.bias"], 1e-5)

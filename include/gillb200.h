@@ -105,7 +105,7 @@ int gillb200_topk_merge(const float* cand_val, const long long* cand_idx, int R,
  * Replaces diffusers' Attention (UNet self/cross attention, gill/custom_sd.py:633-638) and OPTAttention
  * (gill/models.py:465). q: [B, Lq, *], k/v: [B, Lk, *], out: [B, Lq, *]; head h occupies columns
  * [h*hd_pad, (h+1)*hd_pad) of each row, hd_pad in {64, 128, 192}; columns beyond the true head dim must be zero in
- * q, k and v (the projection weights are zero-padded at load time). Strides are in elements.
+ * q, k and v (except v's optional ones column, see ones_col) (the projection weights are zero-padded at load time). Strides are in elements.
  * causal: key j is visible to query i iff j <= i + causal_offset. kv_lens: optional per-batch key count (device).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct gillb200_attn_args {
@@ -120,6 +120,8 @@ typedef struct gillb200_attn_args {
   int causal, causal_offset;
   int dtype;
   float scale;
+  int ones_col; /* 0 = unused. > 0: v[..., h*hd_pad + ones_col] == 1.0 for every key (a spare padding column), which
+                 * lets the kernel take the softmax denominator from the P.V product (fp16 only) */
 } gillb200_attn_args;
 
 int gillb200_attention(const gillb200_attn_args* args, void* stream);

@@ -229,6 +229,15 @@ def test_fused_attention(ops, case):
     got = ops.attention(q, k, v, H, hp, hd ** -0.5, causal=causal)
     tol = 1e-2 if dt == torch.bfloat16 else 3e-3   # P is rounded to the operand dtype before P.V
     assert torch.isfinite(got.float()).all() and rel(got, attn_ref(q, k, v, H, hp, hd ** -0.5, causal)) < tol
+    if dt == torch.float16 and hp > hd:
+        # ones-column mode: V[..., hd] = 1 moves the softmax denominator onto the tensor core (packed f16x2 exp2)
+        v1 = v.view(B, Lk, H, hp).clone()
+        v1[..., hd] = 1.0
+        v1 = v1.view(B, Lk, H * hp)
+        got1 = ops.attention(q, k, v1, H, hp, hd ** -0.5, causal=causal, ones_col=hd)
+        ref1 = attn_ref(q, k, v1, H, hp, hd ** -0.5, causal)
+        assert torch.isfinite(got1.float()).all() and rel(got1, ref1) < tol
+        assert (got1.view(B, Lq, H, hp)[..., hd].float() - 1).abs().max() < 2e-3
 
 
 def test_fused_attention_kv_lens_and_views(ops):

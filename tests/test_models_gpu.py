@@ -245,7 +245,7 @@ def test_generate_for_images_and_texts_structure_and_errors(gill_small):
     assert set(out[1].keys()) == {"gen", "ret", "decision"}
     assert out[1]["decision"] == ["gen", [0, 1]]                    # no bank loaded (gill/models.py:704)
     img, score = out[1]["gen"][0]
-    assert img.size == (64, 64) and score == 0
+    assert img.size == (128, 128) and score == 0                   # default 512x512 request -> 64x64 latents -> tiny VAE x2
     with pytest.raises(NotImplementedError):
         gill.generate_for_images_and_texts(["x"], num_words=0)      # gill/models.py:629
     with pytest.raises(ValueError):

@@ -69,10 +69,30 @@ def check_attn():
     got = ops.attention(q, k, v, H, hp, hd ** -0.5, kv_lens=kvl); torch.cuda.synchronize()
     r = rel(got, attn_ref(q, k, v, H, hd, hp, hd ** -0.5, kv_lens=kvl))
     print(f"[{'OK ' if r < 1e-2 else 'BAD'}] attn kv_lens: rel={r:.3e}", flush=True); ok &= r < 1e-2
+    # ones-column (packed exp2) mode
+    for (B, H, Lq, Lk, hd, hp) in [(2, 8, 1024, 1024, 40, 64), (2, 8, 1024, 77, 40, 64), (2, 8, 256, 256, 80, 128), (2, 8, 64, 64, 160, 192)]:
+        def mk(L, ones=False):
+            t = torch.zeros(B, L, H, hp, device=dev); t[..., :hd] = torch.randn(B, L, H, hd, device=dev)
+            if ones: t[..., hd] = 1.0
+            return t.view(B, L, H * hp).half()
+        q, k, v = mk(Lq), mk(Lk), mk(Lk, True)
+        got = ops.attention(q, k, v, H, hp, hd ** -0.5, ones_col=hd); torch.cuda.synchronize()
+        r = rel(got, attn_ref(q, k, v, H, hd, hp, hd ** -0.5))
+        good = r < 3e-3; ok &= good
+        print(f"[{'OK ' if good else 'BAD'}] attn ones_col Lq{Lq} Lk{Lk} hd{hd}/{hp}: rel={r:.3e}", flush=True)
     # perf
     B, H, L, hd, hp = 16, 8, 4096, 40, 64
     q = torch.randn(B, L, H * hp, device=dev).half(); k = torch.randn_like(q); v = torch.randn_like(q)
     out = torch.empty_like(q)
+    vv = v.view(B, L, H, hp); vv[..., hd] = 1.0
+    for _ in range(3): ops.attention(q, k, v, H, hp, hd ** -0.5, out=out, ones_col=hd)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): ops.attention(q, k, v, H, hp, hd ** -0.5, out=out, ones_col=hd)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"perf attn (ones_col/packed) B16 H8 L4096 hd40: {ms:.3f} ms, {4 * B * H * L * L * hd / ms / 1e9:.1f} TFLOP/s (algorithmic)", flush=True)
     for _ in range(3): ops.attention(q, k, v, H, hp, hd ** -0.5, out=out)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
