@@ -226,20 +226,36 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
       const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
       // interior tiles (every column visible to every row of this warp) skip all masking work
       const bool no_mask = __all_sync(0xffffffffu, lim >= BLOCK_KV - 1);
-      // pass 1: row max
+      // pass 1: row max. The tcgen05.ld of the next 32 columns is in flight while the current 32 are reduced.
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_KV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ts + c, v);
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(ts, va);
         tmem_wait_ld();
-        if (no_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int c = 0; c < BLOCK_KV; c += 64) {
+          if (c + 32 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 32, vb);
+          if (no_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(va[i]));
+          }
+          if (c + 32 < BLOCK_KV) {
+            tmem_wait_ld();
+            if (c + 64 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 64, va);
+            if (no_mask) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c + 32 + i <= lim) mx = fmaxf(mx, __uint_as_float(vb[i]));
+            }
+            if (c + 64 < BLOCK_KV) tmem_wait_ld();
+          }
         }
       }
       mx *= p.scale_log2;
@@ -272,12 +288,9 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
         }
         tmem_wait_st();
       }
-      // pass 2: p = exp2(s*scale - m), row sum, P -> smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7))
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_KV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ts + c, v);
-        tmem_wait_ld();
+      // pass 2: p = exp2(s*scale - m), row sum, P -> smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7)).
+      // Same software pipelining of the TMEM loads as pass 1.
+      auto emit = [&](const uint32_t (&v)[32], int c) {
         uint32_t pk[16];
         if (packed) {
 #pragma unroll
@@ -293,16 +306,16 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
         } else if (no_mask) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used);
-            const float p1 = fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used);
+            const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used));
             l += p0 + p1;
             pk[i >> 1] = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c + i <= lim) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - m_used) : 0.f;
-            const float p1 = (c + i + 1 <= lim) ? fast_exp2(__uint_as_float(v[i + 1]) * p.scale_log2 - m_used) : 0.f;
+            const float p0 = (c + i <= lim) ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used)) : 0.f;
+            const float p1 = (c + i + 1 <= lim) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used)) : 0.f;
             l += p0 + p1;
             pk[i >> 1] = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
           }
@@ -313,6 +326,22 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
         for (int u = 0; u < 4; ++u) {
           const int phys = (u0 + u) ^ (r & 7);
           *reinterpret_cast<uint4*>(chunk + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      };
+      {
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32b_x32(ts, va);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < BLOCK_KV; c += 64) {
+          if (c + 32 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 32, vb);
+          emit(va, c);
+          if (c + 32 < BLOCK_KV) {
+            tmem_wait_ld();
+            if (c + 64 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 64, va);
+            emit(vb, c + 32);
+            if (c + 64 < BLOCK_KV) tmem_wait_ld();
+          }
         }
       }
       fence_proxy_async_smem();

@@ -150,7 +150,10 @@ __device__ __forceinline__ Vec8 gn_load(const GnSrc& s, long long pix, int v, in
 }
 
 __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int HW, int G, int chunks,
-                                                       float* __restrict__ partial /* [B, chunks, G, 2] */) {
+                                                       float* __restrict__ partial /* [B, chunks, G, 2] */,
+                                                       int* __restrict__ counters /* [B], zero between launches */,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       float eps, float* __restrict__ scale_shift /* [B, 2, C] */) {
   // Thread t owns channel vector v and pixel subgroup sg: 256 consecutive threads read 256 consecutive 16-byte
   // vectors (NHWC is pixel-major, so the next pixel's channels follow). Per-thread register sums -> smem
   // [sg][sum|sumsq][C] -> per-group totals summed in a fixed order: no atomics, bit-reproducible.
@@ -226,9 +229,41 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
     o[0] = s;
     o[1] = q;
   }
+  // The last CTA of each sample to finish turns the partials into the per-channel affine y = x * scale + shift
+  // (summing chunks in a fixed order: deterministic), so no separate finalize launch is needed.
+  __shared__ int is_last;
+  __shared__ float gmean[64], grstd[64];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&counters[b], 1) == chunks - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const volatile float* pp = partial + ((static_cast<long long>(b) * chunks + ch) * G + g) * 2;
+      s += pp[0];
+      q += pp[1];
+    }
+    const float n = static_cast<float>(cpg) * HW;
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    gmean[g] = mean;
+    grstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  float* sc = scale_shift + static_cast<long long>(b) * 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float a = grstd[g] * w[c];
+    sc[c] = a;
+    sc[C + c] = bias[c] - gmean[g] * a;
+  }
+  if (threadIdx.x == 0) counters[b] = 0;
 }
 
-// Per-(sample, channel) affine of the normalisation: y = x * scale + shift. One tiny launch per GroupNorm so that the
+// (kept for reference / debugging) Per-(sample, channel) affine of the normalisation: y = x * scale + shift. One tiny launch per GroupNorm so that the
 // elementwise pass below needs no shared memory and no per-CTA recomputation.
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, int C, int HW,
                                    const float* __restrict__ w, const float* __restrict__ bias, float eps,
@@ -391,8 +426,9 @@ extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, co
 }
 
 extern "C" long long gillb200_groupnorm_workspace_bytes(int B, int G) {
-  // [B, 64 chunks, G, 2] partial sums + [B, 2, C<=4096] scale/shift
-  return (64LL * B * G * 2 + 2LL * B * 4096) * sizeof(float);
+  // [B] counters (zero-initialised by the caller, self-resetting) + [B, 128 chunks, G, 2] partial sums
+  // + [B, 2, C<=4096] scale/shift
+  return (1024 + 128LL * B * G * 2 + 2LL * B * 4096) * sizeof(float);
 }
 
 extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1, int dtype, int B, int HW, int G,
@@ -405,26 +441,26 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   GB_CHECK_ARG(C1 == 0 || x1 != nullptr, "groupnorm: second source missing");
   GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16 || dtype == DT_F32, "bad dtype");
   GnSrc src{x0, x1, C0, C1};
-  // ~2 CTAs per SM in flight, each thread streaming >= 4 independent 16-byte loads
-  int chunks = (2 * num_sms() + B - 1) / B;
-  if (chunks > 64) chunks = 64;
+  GB_CHECK_ARG(B <= 1024, "groupnorm: batch %d > 1024", B);
+  // ~4 CTAs per SM in flight, each thread streaming >= 4 independent 16-byte loads
+  int chunks = (4 * num_sms() + B - 1) / B;
+  if (chunks > 128) chunks = 128;
   if (chunks > HW) chunks = HW;
   if (chunks < 1) chunks = 1;
   chunks = (HW + (HW + chunks - 1) / chunks - 1) / ((HW + chunks - 1) / chunks);  // drop empty chunks
-  float* partial = reinterpret_cast<float*>(workspace);
-  float* scale_shift = partial + 64LL * B * G * 2;
+  int* counters = reinterpret_cast<int*>(workspace);
+  float* partial = reinterpret_cast<float*>(workspace) + 1024;
+  float* scale_shift = partial + 128LL * B * G * 2;
   const int nvec = C / 8;
   const size_t smem_stats = static_cast<size_t>(nvec >= 256 ? 1 : 256 / nvec) * 2 * C * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, B), 256, smem_stats, stream>>>(src, dtype, HW, G, chunks, partial);
-  GB_COUNT_LAUNCH(1);
-  GB_CUDA(cudaGetLastError());
-  gn_finalize_kernel<<<B, 256, 0, stream>>>(partial, chunks, G, C, HW, w, b, eps, scale_shift);
+  gn_stats_kernel<<<dim3(chunks, B), 256, smem_stats, stream>>>(src, dtype, HW, G, chunks, partial, counters, w, b, eps,
+                                                               scale_shift);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   // ~64K elements per CTA, but never fewer than ~4 CTAs per SM worth of blocks when the tensor is small
   int pix_per_block = (65536 + C - 1) / C;
   const int sgs = nvec >= 256 ? 1 : 256 / nvec;
-  const int want_blocks = (4 * num_sms() + B - 1) / B;
+  const int want_blocks = (8 * num_sms() + B - 1) / B;
   if (pix_per_block * want_blocks > HW) pix_per_block = (HW + want_blocks - 1) / want_blocks;
   pix_per_block = ((pix_per_block + 4 * sgs - 1) / (4 * sgs)) * (4 * sgs);
   const int blocks = (HW + pix_per_block - 1) / pix_per_block;

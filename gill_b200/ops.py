@@ -273,7 +273,8 @@ def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, ep
     key = (x.device.index, B, groups)
     ws = _gn_ws.get(key)
     if ws is None:
-        ws = torch.empty(lib().gillb200_groupnorm_workspace_bytes(B, groups), device=x.device, dtype=torch.uint8)
+        # zero-initialised once: the kernel's per-sample arrival counters reset themselves after every launch
+        ws = torch.zeros(lib().gillb200_groupnorm_workspace_bytes(B, groups), device=x.device, dtype=torch.uint8)
         _gn_ws[key] = ws
     with _P("groupnorm", 0.0, (2 * x.element_size() + out.element_size()) * B * H * W * (C0 + C1), f"B{B} {H}x{W} C{C0 + C1}"):
         check(lib().gillb200_groupnorm(x.data_ptr(), C0, _ptr(x2), C1, _DT[x.dtype], B, H * W, groups, w.data_ptr(),

@@ -130,7 +130,9 @@ int gillb200_attention(const gillb200_attn_args* args, void* stream);
  * Normalisation / softmax (fp32 statistics, 16-byte vectorised).
  *   layernorm : F.layer_norm over the last dim; optional bf16 residue output (split-precision GEMM operand).
  *   groupnorm : nn.GroupNorm (+ optional SiLU) over an NHWC tensor that may be the channel concatenation of two
- *               tensors (UNet up blocks, cat([h, skip])); writes the normalised concatenation.
+ *               tensors (UNet up blocks, cat([h, skip])); writes the normalised concatenation. `workspace` holds
+ *               gillb200_groupnorm_workspace_bytes(B, G) bytes and must be ZERO before its first use (the kernel's
+ *               arrival counters reset themselves afterwards).
  * Replace the norms inside nn.Transformer (gill/layers.py:20-22), OPT (gill/models.py:465) and the UNet / VAE
  * (gill/custom_sd.py:633-638, :388).
  * ------------------------------------------------------------------------------------------------------------- */

@@ -1,0 +1,28 @@
+"""Small driver for ncu captures: a few launches of the hot kernels at their UNet shapes."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gill_b200 import ops
+dev = "cuda"
+which = sys.argv[1]
+torch.manual_seed(0)
+if which == "attn":
+    B, H, L, hd, hp = 16, 8, 4096, 40, 64
+    q = torch.randn(B, L, H * hp, device=dev).half(); k = torch.randn_like(q); v = torch.randn_like(q)
+    for _ in range(2): ops.attention(q, k, v, H, hp, hd ** -0.5)
+    v.view(B, L, H, hp)[..., hd] = 1.0
+    for _ in range(2): ops.attention(q, k, v, H, hp, hd ** -0.5, ones_col=hd)
+elif which == "geglu":
+    a = torch.randn(65536, 320, device=dev).half(); b = torch.randn(2560, 320, device=dev).half(); bias = torch.randn(2560, device=dev)
+    for _ in range(3): ops.gemm(a, b, bias=bias, act="geglu")
+elif which == "gemm320":
+    a = torch.randn(65536, 320, device=dev).half(); b = torch.randn(320, 320, device=dev).half(); bias = torch.randn(320, device=dev)
+    r = torch.randn(65536, 320, device=dev).half()
+    for _ in range(3): ops.gemm(a, b, bias=bias, residual=r)
+elif which == "conv":
+    x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, 2880, device=dev).half() * 0.02; bias = torch.randn(320, device=dev)
+    for _ in range(3): ops.conv3x3(x, w, bias=bias)
+elif which == "gn":
+    x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, device=dev); b = torch.randn(320, device=dev)
+    for _ in range(3): ops.groupnorm(x, w, b, 32, 1e-5, silu=True)
+torch.cuda.synchronize()
