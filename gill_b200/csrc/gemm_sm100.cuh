@@ -361,25 +361,27 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tme
     uint32_t ra[16], rb[16];
     tmem_ld_32x32b_x16(taddr + cbase, ra);
     tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < NCH; i += 2) {
-      if (i + 1 < NCH) tmem_ld_32x32b_x16(taddr + cbase + (i + 1) * 16, rb);
+#pragma unroll 1
+    for (int i = 0; i < NCH; i += 2) {  // rolled: two copies of the epilogue body, not NCH of them
+      const bool has_b = i + 1 < NCH;
+      if (has_b) tmem_ld_32x32b_x16(taddr + cbase + (i + 1) * 16, rb);
       if (row_ok && n0 + cbase + i * 16 < p.N) {
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ra[j]);
         epilogue_chunk16(p, row, n0 + cbase + i * 16, v);
       }
-      if (i + 1 < NCH) {
+      if (has_b) {
         tmem_wait_ld();
-        if (i + 2 < NCH) tmem_ld_32x32b_x16(taddr + cbase + (i + 2) * 16, ra);
+        const bool has_a = i + 2 < NCH;
+        if (has_a) tmem_ld_32x32b_x16(taddr + cbase + (i + 2) * 16, ra);
         if (row_ok && n0 + cbase + (i + 1) * 16 < p.N) {
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rb[j]);
           epilogue_chunk16(p, row, n0 + cbase + (i + 1) * 16, v);
         }
-        if (i + 2 < NCH) tmem_wait_ld();
+        if (has_a) tmem_wait_ld();
       }
     }
     tc_fence_before();
