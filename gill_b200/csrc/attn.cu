@@ -37,13 +37,14 @@ struct alignas(64) AttnParams {
 
 template <int HD_PAD, int BLOCK_KV>
 struct AttnCfg {
-  // HD_PAD == 64 (UNet 64x64 / 32x32 levels, the hot shape): single S and V buffers so that TMEM (256 columns) and
-  // shared memory (< 113 KB) allow TWO CTAs per SM -- the second CTA's MMAs fill the first one's softmax bubbles and
-  // every SM sub-partition has two softmax warps to switch between. Wider heads keep the double-buffered 1-CTA form.
+  // HD_PAD == 64 (UNet 64x64 level, the hot shape; ncu: no pipe above 45%, latency-bound with <= 2 softmax warps per
+  // scheduler): 64-wide KV tiles and single S/K/V buffers bring a CTA down to 128 TMEM columns and ~49 KB of shared
+  // memory, so FOUR CTAs share an SM -- 16 softmax warps per SM hide the TMEM / MUFU / mbarrier latencies and the
+  // other CTAs' MMAs fill each CTA's serial S -> softmax -> P.V chain. Wider heads keep the double-buffered 1-CTA form.
   static constexpr int SBUF = HD_PAD == 64 ? 1 : 2;
   static constexpr int VBUF = HD_PAD == 64 ? 1 : 2;
-  static constexpr int KBUF = 2;
-  static constexpr int CTAS_PER_SM = HD_PAD == 64 ? 2 : 1;
+  static constexpr int KBUF = HD_PAD == 64 ? 1 : 2;
+  static constexpr int CTAS_PER_SM = HD_PAD == 64 ? 4 : 1;
   static constexpr int KCH = HD_PAD / 64;           // 64-column chunks per head
   static constexpr int Q_BYTES = 128 * HD_PAD * 2;  // chunk-major: KCH x [128 rows x 128 B]
   static constexpr int KV_BYTES = BLOCK_KV * HD_PAD * 2;
@@ -56,7 +57,7 @@ struct AttnCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_S0 = 0;               // S buffers at columns [i*BLOCK_KV, (i+1)*BLOCK_KV)
   static constexpr int TMEM_O = SBUF * BLOCK_KV;  // O accumulator
-  static constexpr int TMEM_COLS = (SBUF * BLOCK_KV + HD_PAD) <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = (SBUF * BLOCK_KV + HD_PAD) <= 128 ? 128 : (SBUF * BLOCK_KV + HD_PAD) <= 256 ? 256 : 512;
   static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "smem for the intended occupancy");
   static_assert(CTAS_PER_SM * TMEM_COLS <= 512, "TMEM for the intended occupancy");
   static_assert(HD_PAD % 64 == 0 && HD_PAD <= 192, "head pad");
@@ -226,36 +227,20 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
       const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
       // interior tiles (every column visible to every row of this warp) skip all masking work
       const bool no_mask = __all_sync(0xffffffffu, lim >= BLOCK_KV - 1);
-      // pass 1: row max. The tcgen05.ld of the next 32 columns is in flight while the current 32 are reduced.
+      // pass 1: row max
       float mx = -INFINITY;
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32b_x32(ts, va);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_KV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ts + c, v);
         tmem_wait_ld();
+        if (no_mask) {
 #pragma unroll
-        for (int c = 0; c < BLOCK_KV; c += 64) {
-          if (c + 32 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 32, vb);
-          if (no_mask) {
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(va[i]));
-          }
-          if (c + 32 < BLOCK_KV) {
-            tmem_wait_ld();
-            if (c + 64 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 64, va);
-            if (no_mask) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(vb[i]));
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c + 32 + i <= lim) mx = fmaxf(mx, __uint_as_float(vb[i]));
-            }
-            if (c + 64 < BLOCK_KV) tmem_wait_ld();
-          }
+          for (int i = 0; i < 32; ++i)
+            if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
       }
       mx *= p.scale_log2;
@@ -289,7 +274,6 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
         tmem_wait_st();
       }
       // pass 2: p = exp2(s*scale - m), row sum, P -> smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7)).
-      // Same software pipelining of the TMEM loads as pass 1.
       auto emit = [&](const uint32_t (&v)[32], int c) {
         uint32_t pk[16];
         if (packed) {
@@ -328,21 +312,12 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
           *reinterpret_cast<uint4*>(chunk + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
         }
       };
-      {
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32b_x32(ts, va);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_KV; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(ts + c, v);
         tmem_wait_ld();
-#pragma unroll
-        for (int c = 0; c < BLOCK_KV; c += 64) {
-          if (c + 32 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 32, vb);
-          emit(va, c);
-          if (c + 32 < BLOCK_KV) {
-            tmem_wait_ld();
-            if (c + 64 < BLOCK_KV) tmem_ld_32x32b_x32(ts + c + 64, va);
-            emit(vb, c + 32);
-            if (c + 64 < BLOCK_KV) tmem_wait_ld();
-          }
-        }
+        emit(v, c);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -412,7 +387,7 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   GB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "row strides %% 8");
   GB_CHECK_ARG(a->q_bstride % 8 == 0 && a->k_bstride % 8 == 0 && a->v_bstride % 8 == 0, "batch strides %% 8");
   const bool bf16 = a->dtype == DT_BF16;
-  const int bkv = a->hd_pad == 192 ? 64 : 128;
+  const int bkv = a->hd_pad == 128 ? 128 : 64;
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const uint64_t cols = (uint64_t)a->H * a->hd_pad;
@@ -447,7 +422,7 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   p.in_dtype = a->dtype;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ones_col = (a->ones_col > 0 && a->ones_col < a->hd_pad) ? a->ones_col : -1;
-  if (a->hd_pad == 64) return launch_attn<64, 128>(p, stream);
+  if (a->hd_pad == 64) return launch_attn<64, 64>(p, stream);
   if (a->hd_pad == 128) return launch_attn<128, 128>(p, stream);
   return launch_attn<192, 64>(p, stream);
 }

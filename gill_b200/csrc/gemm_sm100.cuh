@@ -6,8 +6,8 @@
 //   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16 per instruction)
 //   warp 2        : TMEM allocator
-//   warps 4..11   : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/residual -> vectorised global stores);
-//                   warps w and w+4 share a TMEM lane quadrant and split the tile's columns in halves
+//   warps 4..19   : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/residual -> vectorised global stores);
+//                   warps w, w+4, w+8, w+12 share a TMEM lane quadrant and split the tile's 16-column chunks
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // The A operand has two addressing modes:
@@ -24,7 +24,8 @@ namespace gb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;  // warps 0-3: producer / MMA / TMEM alloc / spare; warps 4-11: epilogue
+constexpr int GEMM_EPI_WARPS = 16;  // 4 per SM sub-partition: the CUDA-core epilogue needs the latency hiding
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warps 0-3: producer / MMA / TMEM alloc / spare
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 enum { A_PLAIN = 0, A_CONV3X3 = 1 };
@@ -68,7 +69,7 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
   static constexpr int ACC_STRIDE = BLOCK_N <= 32 ? 32 : BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "invalid UMMA N / epilogue split");
+  static_assert(BLOCK_N % 16 == 0 && BLOCK_N >= 16 && BLOCK_N <= 256, "invalid UMMA N");
   static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-B alignment");
 };
 
@@ -341,9 +342,12 @@ template <int BLOCK_N>
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tmem_full, uint64_t* tmem_empty,
                                               uint32_t tmem_base, int num_m, int num_tiles) {
   using C = GemmCfg<BLOCK_N>;
-  const int ewarp = (threadIdx.x >> 5) & 3;        // TMEM lane quadrant this warp may access
-  const int half = ((threadIdx.x >> 5) - 4) >> 2;  // column half handled by this warp
-  constexpr int HALF_N = BLOCK_N / 2;              // multiple of 16 for every instantiated BLOCK_N
+  const int ewarp = (threadIdx.x >> 5) & 3;         // TMEM lane quadrant this warp may access
+  const int cgrp = ((threadIdx.x >> 5) - 4) >> 2;   // which share of the tile's columns this warp drains
+  constexpr int NGRP = GEMM_EPI_WARPS / 4;
+  constexpr int NCH = BLOCK_N / 16;                 // 16-column chunks per tile, dealt out as evenly as possible
+  const int ch_begin = cgrp * (NCH / NGRP) + min(cgrp, NCH % NGRP);
+  const int ch_end = ch_begin + NCH / NGRP + (cgrp < NCH % NGRP ? 1 : 0);
   int acc = 0;
   uint32_t acc_phase = 0;
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -353,35 +357,17 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tme
     mbar_wait(&tmem_full[acc], acc_phase);
     tc_fence_after();
     const uint32_t taddr = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(ewarp * 32) << 16);
-    // Software-pipelined drain: the tcgen05.ld of chunk i+1 is in flight while chunk i is processed (tcgen05.ld is
-    // asynchronous until tcgen05.wait::ld), so the TMEM latency is paid once per tile instead of once per chunk.
-    constexpr int NCH = HALF_N / 16;
-    const int cbase = half * HALF_N;
-    const bool row_ok = row < p.M;
-    uint32_t ra[16], rb[16];
-    tmem_ld_32x32b_x16(taddr + cbase, ra);
-    tmem_wait_ld();
 #pragma unroll 1
-    for (int i = 0; i < NCH; i += 2) {  // rolled: two copies of the epilogue body, not NCH of them
-      const bool has_b = i + 1 < NCH;
-      if (has_b) tmem_ld_32x32b_x16(taddr + cbase + (i + 1) * 16, rb);
-      if (row_ok && n0 + cbase + i * 16 < p.N) {
+    for (int ch = ch_begin; ch < ch_end; ++ch) {
+      const int c = ch * 16;
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(taddr + c, r);
+      tmem_wait_ld();
+      if (row < p.M && n0 + c < p.N) {
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(ra[j]);
-        epilogue_chunk16(p, row, n0 + cbase + i * 16, v);
-      }
-      if (has_b) {
-        tmem_wait_ld();
-        const bool has_a = i + 2 < NCH;
-        if (has_a) tmem_ld_32x32b_x16(taddr + cbase + (i + 2) * 16, ra);
-        if (row_ok && n0 + cbase + (i + 1) * 16 < p.N) {
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rb[j]);
-          epilogue_chunk16(p, row, n0 + cbase + (i + 1) * 16, v);
-        }
-        if (has_a) tmem_wait_ld();
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        epilogue_chunk16(p, row, n0 + c, v);
       }
     }
     tc_fence_before();
@@ -427,7 +413,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 8);
+      mbar_init(&bars->tmem_empty[i], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
