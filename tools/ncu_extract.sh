@@ -15,7 +15,8 @@ keep = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor"]
+        "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_op_read.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__memory_throughput.avg.pct_of_peak_sustained_elapsed", "gpu__compute_memory_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex.sum", "smsp__cycles_elapsed.avg.per_second", "lts__cycles_elapsed.avg.per_second"]
 with open(f"gpurun_out/ncu_{t}_summary.txt", "w") as f:
     names = [h for h in hdr]
     for d in data:

@@ -22,6 +22,15 @@ elif which == "gemm320":
 elif which == "conv":
     x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, 2880, device=dev).half() * 0.02; bias = torch.randn(320, device=dev)
     for _ in range(3): ops.conv3x3(x, w, bias=bias)
+elif which == "qkv":
+    a = torch.randn(65536, 320, device=dev).half(); b = torch.randn(1536, 320, device=dev).half()
+    for _ in range(3): ops.gemm(a, b)
+elif which == "conv8":
+    x = torch.randn(16, 8, 8, 1280, device=dev).half(); w = torch.randn(1280, 11520, device=dev).half() * 0.01; bias = torch.randn(1280, device=dev)
+    for _ in range(3): ops.conv3x3(x, w, bias=bias)
+elif which == "big":
+    a = torch.randn(8192, 8192, device=dev).bfloat16(); b = torch.randn(8192, 8192, device=dev).bfloat16()
+    for _ in range(3): ops.gemm(a, b, block_n=256)
 elif which == "gn":
     x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, device=dev); b = torch.randn(320, device=dev)
     for _ in range(3): ops.groupnorm(x, w, b, 32, 1e-5, silu=True)
