@@ -1,5 +1,6 @@
 // Host side of the tcgen05 GEMM: tensor-map construction, tile-shape selection, launch, C ABI.
 #include "../../include/gillb200.h"
+#include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "host_common.h"
 
@@ -83,6 +84,24 @@ static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int BN>
+static int launch_gemm2(const GemmParams& p, cudaStream_t stream) {
+  using C = Gemm2Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_n = (p.N + BN - 1) / BN;
+  const int tiles = num_m2 * num_n;
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  gemm2_kernel<BN><<<2 * pairs, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);  // __cluster_dims__(2,1,1)
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -198,10 +217,20 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
 
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N);
   if (a->act == ACT_GEGLU) GB_CHECK_ARG(a->N % 2 == 0, "GEGLU needs even N");
+  // CTA-pair (cta_group::2) kernel: 256 x bn tiles, each CTA loads half of the B tile. Used when there are enough
+  // 256-row tiles to keep every SM pair busy; small problems keep the 1-CTA kernel (more, smaller tiles).
+  bool pair = false;
+  if (a->cta_pair == 2) {
+    pair = true;
+  } else if (a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
+    const long long tiles2 = 1LL * ((a->M + 255) / 256) * ((a->N + bn - 1) / bn);
+    pair = tiles2 >= (num_sms() / 2) * 3 / 4;
+  }
+  if (pair) GB_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "cta_pair needs block_n in {64,128,160,256}");
   {
     const uint64_t dims[2] = {(uint64_t)kb_total_cols, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-    const uint32_t box[2] = {BLOCK_K, (uint32_t)bn};
+    const uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};
     int r = encode_tmap_16bit(&p.tma_b, a->b, 2, dims, strides, box, bf16);
     if (r) return r;
   }
@@ -222,6 +251,14 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   p.alpha = a->alpha;
   if (a->out_lo) GB_CHECK_ARG(a->out_dtype == DT_BF16, "out_lo requires a bf16 primary output");
 
+  if (pair) {
+    switch (bn) {
+      case 64: return launch_gemm2<64>(p, stream);
+      case 128: return launch_gemm2<128>(p, stream);
+      case 160: return launch_gemm2<160>(p, stream);
+      default: return launch_gemm2<256>(p, stream);
+    }
+  }
   switch (bn) {
     case 32: return launch_gemm<32>(p, stream);
     case 64: return launch_gemm<64>(p, stream);

@@ -1,0 +1,193 @@
+// CTA-pair (cta_group::2) variant of the tcgen05 GEMM / implicit conv: one 256 x BLOCK_N tile per pair of SMs.
+//
+// Why: measured on B200 (profiles/r01_ncu_*), TMA can fill one SM's shared memory at ~64 B per SM clock, while a
+// 1-CTA 128 x BN tile consumes 64 + 8192/BN B per MMA clock -- it can never be MMA-bound (tensor pipe 45 % at BN=160,
+// 75 % at BN=256). A CTA pair shares the B tile: each CTA loads its own 128 A rows and HALF of the B rows, the single
+// tcgen05.mma.cta_group::2 issued by the leader reads both halves, so a CTA consumes 32 + 8192/BN B per MMA clock.
+//
+// Protocol (per pair; barriers live at identical smem offsets in both CTAs):
+//   full[s]       leader only. Both producers' TMA loads complete_tx on the LEADER's barrier; the leader's producer
+//                 arms it with the byte count of both CTAs.
+//   empty[s]      one per CTA. The leader's tcgen05.commit multicasts the arrival to both CTAs, each producer waits on
+//                 its own copy before refilling its own smem slot.
+//   tmem_full[a]  one per CTA (multicast commit); each CTA's epilogue drains its own 128 accumulator rows.
+//   tmem_empty[a] leader only, count = 2 x epilogue warps: the peer's epilogue warps arrive remotely (mapa).
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace gb {
+
+template <int BLOCK_N>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - BAR_BYTES - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int ACC_STRIDE = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "invalid 2-CTA UMMA N");
+  static_assert(B_BYTES % 1024 == 0, "B half stage must keep 1024-B alignment");
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ GemmParams p) {
+  using C = Gemm2Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_tiles = smem;
+  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + C::STAGES * C::STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m2 * num_n;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tma_a);
+    tma_prefetch_desc(&p.tma_b);
+    if (p.kb_split < p.num_k_blocks) tma_prefetch_desc(&p.tma_a2);
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&bars->full[i], 1);
+      mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars->tmem_full[i], 1);
+      mbar_init(&bars->tmem_empty[i], 2 * GEMM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(&bars->tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+
+  if (warp == 0) {
+    if (lane_id() == 0) {
+      // ---------------- TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int n0 = (tile / num_m2) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        int cb0 = 0, cy0 = 0, cx0 = 0;
+        if (p.a_mode == A_CONV3X3) {
+          const int per_img = p.conv_W * p.conv_H;
+          cb0 = m0 / per_img;
+          cy0 = (m0 % per_img) / p.conv_W;
+          cx0 = m0 % p.conv_W;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem_tiles + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * C::STAGE_BYTES);
+          if (kb >= p.kb_split) {
+            tma2_load_2d(sa, &p.tma_a2, full_leader, (kb - p.kb_split) * BLOCK_K, m0);
+          } else if (p.a_mode == A_CONV3X3) {
+            const int tap = kb / p.conv_cblocks;
+            const int cb = kb - tap * p.conv_cblocks;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma2_load_4d(sa, &p.tma_a, full_leader, cb * BLOCK_K, cx0 + dx, cy0 + dy, cb0);
+          } else {
+            tma2_load_2d(sa, &p.tma_a, full_leader, kb * BLOCK_K, m0);
+          }
+          tma2_load_2d(sb, &p.tma_b, full_leader, (kb % p.b_kb_wrap) * BLOCK_K, n0);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane_id() == 0 && leader) {
+      // ---------------- MMA issuer (leader CTA only; one thread drives both SMs' tensor cores)
+      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_tiles + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_mcast(&bars->tmem_full[acc], 0b11);  // accumulators ready in both CTAs
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue (both CTAs, own 128 accumulator rows)
+    const int ewarp = warp & 3;
+    const int cgrp = (warp - 4) >> 2;
+    constexpr int NGRP = GEMM_EPI_WARPS / 4;
+    constexpr int NCH = BLOCK_N / 16;
+    const int ch_begin = cgrp * (NCH / NGRP) + min(cgrp, NCH % NGRP);
+    const int ch_end = ch_begin + NCH / NGRP + (cgrp < NCH % NGRP ? 1 : 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int row = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + ewarp * 32 + lane_id();
+      const int n0 = (tile / num_m2) * BLOCK_N;
+      mbar_wait(&bars->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(ewarp * 32) << 16);
+#pragma unroll 1
+      for (int ch = ch_begin; ch < ch_end; ++ch) {
+        const int c = ch * 16;
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(taddr + c, r);
+        tmem_wait_ld();
+        if (row < p.M && n0 + c < p.N) {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          epilogue_chunk16(p, row, n0 + c, v);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer may still be reading our smem / signalling our barriers until here
+  if (warp == 2) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+}
+
+}  // namespace gb
