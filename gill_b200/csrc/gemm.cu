@@ -4,6 +4,7 @@
 #include "gemm_sm100.cuh"
 #include "host_common.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -249,6 +250,10 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   p.act = a->act;
   p.in_dtype = a->in_dtype;
   p.alpha = a->alpha;
+  {
+    const char* dbg = getenv("GILLB200_GEMM_DEBUG");  // measurement aid only (see GemmParams::debug_mode)
+    p.debug_mode = dbg ? atoi(dbg) : 0;
+  }
   if (a->out_lo) GB_CHECK_ARG(a->out_dtype == DT_BF16, "out_lo requires a bf16 primary output");
 
   if (pair) {

@@ -56,6 +56,7 @@ struct alignas(64) GemmParams {
   int act;
   int in_dtype;  // DT_BF16 or DT_F16
   float alpha;
+  int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
 template <int BLOCK_N>
@@ -112,6 +113,14 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
       mbar_wait(&empty[stage], phase ^ 1);
       uint8_t* sa = smem_tiles + stage * C::STAGE_BYTES;
       uint8_t* sb = sa + C::A_BYTES;
+      if (p.debug_mode == 1 && (phase != 0 || tile != tile_begin)) {  // measurement only: reuse stale smem
+        mbar_arrive(&full[stage]);
+        if (++stage == C::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        continue;
+      }
       mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
       if (kb >= p.kb_split) {
         tma_load_2d(sa, &p.tma_a2, &full[stage], (kb - p.kb_split) * BLOCK_K, m0);
@@ -153,10 +162,12 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
       const uint32_t sb = sa + C::A_BYTES;
       const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
       const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+      if (p.debug_mode != 2) {
 #pragma unroll
-      for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-        // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-        umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+          umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
       }
       umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
       if (++stage == C::STAGES) {
