@@ -73,8 +73,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   const uint32_t tmem_base = bars->tmem_ptr;
 
   if (warp == 0) {
-    if (lane_id() == 0) {
-      // ---------------- TMA producer (both CTAs)
+    {
+      // ---------------- TMA producer (both CTAs); warp-uniform loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -92,18 +92,21 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           uint8_t* sa = smem_tiles + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
-          if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * C::STAGE_BYTES);
-          if (kb >= p.kb_split) {
-            tma2_load_2d(sa, &p.tma_a2, full_leader, (kb - p.kb_split) * BLOCK_K, m0);
-          } else if (p.a_mode == A_CONV3X3) {
-            const int tap = kb / p.conv_cblocks;
-            const int cb = kb - tap * p.conv_cblocks;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma2_load_4d(sa, &p.tma_a, full_leader, cb * BLOCK_K, cx0 + dx, cy0 + dy, cb0);
-          } else {
-            tma2_load_2d(sa, &p.tma_a, full_leader, kb * BLOCK_K, m0);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * C::STAGE_BYTES);
+            if (kb >= p.kb_split) {
+              tma2_load_2d(sa, &p.tma_a2, full_leader, (kb - p.kb_split) * BLOCK_K, m0);
+            } else if (p.a_mode == A_CONV3X3) {
+              const int tap = kb / p.conv_cblocks;
+              const int cb = kb - tap * p.conv_cblocks;
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              tma2_load_4d(sa, &p.tma_a, full_leader, cb * BLOCK_K, cx0 + dx, cy0 + dy, cb0);
+            } else {
+              tma2_load_2d(sa, &p.tma_a, full_leader, kb * BLOCK_K, m0);
+            }
+            tma2_load_2d(sb, &p.tma_b, full_leader, (kb % p.b_kb_wrap) * BLOCK_K, n0);
           }
-          tma2_load_2d(sb, &p.tma_b, full_leader, (kb % p.b_kb_wrap) * BLOCK_K, n0);
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -112,7 +115,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane_id() == 0 && leader) {
+    if (leader) {
       // ---------------- MMA issuer (leader CTA only; one thread drives both SMs' tensor cores)
       const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
       int stage = 0;
@@ -130,16 +133,20 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           const uint32_t sb = sa + C::A_BYTES;
           const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
+          }
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma2_commit_mcast(&bars->tmem_full[acc], 0b11);  // accumulators ready in both CTAs
+        if (elect_one()) umma2_commit_mcast(&bars->tmem_full[acc], 0b11);  // accumulators ready in both CTAs
+        __syncwarp();
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

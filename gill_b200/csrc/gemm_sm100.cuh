@@ -90,7 +90,14 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 struct TileCoord {
   int m_blk, n_blk;
 };
-__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m) { return {tile % num_m, tile / num_m}; }
+// num_m > 0: m-fastest (CTAs running side by side share a B tile). num_m < 0 encodes "n-inner" order with |num_m| = num_n:
+// a CTA walks all N tiles of one M block back to back, so the big streaming A operand is fetched from HBM once
+// (used when there are only a few N tiles, e.g. N = 320 with BLOCK_N = 160).
+__device__ __forceinline__ TileCoord tile_coord(int tile, int num_m) {
+  if (num_m > 0) return {tile % num_m, tile / num_m};
+  const int num_n = -num_m;
+  return {tile / num_n, tile % num_n};
+}
 
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
@@ -110,29 +117,36 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
       cx0 = m0 % p.conv_W;  // non-zero only when W > 128 (a tile is then a 128-pixel row segment)
     }
     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      // The whole warp runs this loop (warp-uniform control flow) and one elected lane issues: with a single
+      // divergent lane the compiler has to wrap every UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop and shuttle
+      // operands through R2UR, which made the issue loop ~430 cycles per k-block (measured, profiles/).
       mbar_wait(&empty[stage], phase ^ 1);
       uint8_t* sa = smem_tiles + stage * C::STAGE_BYTES;
       uint8_t* sb = sa + C::A_BYTES;
       if (p.debug_mode == 1 && (phase != 0 || tile != tile_begin)) {  // measurement only: reuse stale smem
-        mbar_arrive(&full[stage]);
+        if (elect_one()) mbar_arrive(&full[stage]);
+        __syncwarp();
         if (++stage == C::STAGES) {
           stage = 0;
           phase ^= 1;
         }
         continue;
       }
-      mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-      if (kb >= p.kb_split) {
-        tma_load_2d(sa, &p.tma_a2, &full[stage], (kb - p.kb_split) * BLOCK_K, m0);
-      } else if (p.a_mode == A_CONV3X3) {
-        const int tap = kb / p.conv_cblocks;
-        const int cb = kb - tap * p.conv_cblocks;
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-        tma_load_4d(sa, &p.tma_a, &full[stage], cb * BLOCK_K, cx0 + dx, cy0 + dy, cb0);
-      } else {
-        tma_load_2d(sa, &p.tma_a, &full[stage], kb * BLOCK_K, m0);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+        if (kb >= p.kb_split) {
+          tma_load_2d(sa, &p.tma_a2, &full[stage], (kb - p.kb_split) * BLOCK_K, m0);
+        } else if (p.a_mode == A_CONV3X3) {
+          const int tap = kb / p.conv_cblocks;
+          const int cb = kb - tap * p.conv_cblocks;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          tma_load_4d(sa, &p.tma_a, &full[stage], cb * BLOCK_K, cx0 + dx, cy0 + dy, cb0);
+        } else {
+          tma_load_2d(sa, &p.tma_a, &full[stage], kb * BLOCK_K, m0);
+        }
+        tma_load_2d(sb, &p.tma_b, &full[stage], (kb % p.b_kb_wrap) * BLOCK_K, n0);
       }
-      tma_load_2d(sb, &p.tma_b, &full[stage], (kb % p.b_kb_wrap) * BLOCK_K, n0);
+      __syncwarp();
       if (++stage == C::STAGES) {
         stage = 0;
         phase ^= 1;
@@ -162,20 +176,24 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
       const uint32_t sb = sa + C::A_BYTES;
       const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
       const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
-      if (p.debug_mode != 2) {
+      if (elect_one()) {
+        if (p.debug_mode != 2) {
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-          umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
         }
+        umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
       }
-      umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
+      __syncwarp();
       if (++stage == C::STAGES) {
         stage = 0;
         phase ^= 1;
       }
     }
-    umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+    if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+    __syncwarp();
     if (++acc == 2) {
       acc = 0;
       acc_phase ^= 1;
@@ -437,15 +455,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
 
+  const int order = (num_n <= 4 && num_m >= 2 * static_cast<int>(gridDim.x)) ? -num_n : num_m;  // see tile_coord()
   if (warp == 0) {
-    if (lane_id() == 0)
-      gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, num_m, blockIdx.x, num_tiles, gridDim.x);
+    gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, order, blockIdx.x, num_tiles, gridDim.x);
   } else if (warp == 1) {
-    if (lane_id() == 0)
-      gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
-                        blockIdx.x, num_tiles, gridDim.x);
+    gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
+                      blockIdx.x, num_tiles, gridDim.x);
   } else if (warp >= 4) {
-    gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, num_m, num_tiles);
+    gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, order, num_tiles);
   }
 
   tc_fence_before();
