@@ -36,6 +36,7 @@ class GemmArgs(ctypes.Structure):
         ("residual", _c_void_p), ("ldr", _c_ll), ("res_dtype", _c_int),
         ("act", _c_int), ("alpha", _c_float),
         ("block_n", _c_int),
+        ("tile_order", _c_int),
         ("cta_pair", _c_int),
     ]
 

@@ -250,6 +250,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   p.act = a->act;
   p.in_dtype = a->in_dtype;
   p.alpha = a->alpha;
+  p.tile_order = a->tile_order;
   {
     const char* dbg = getenv("GILLB200_GEMM_DEBUG");  // measurement aid only (see GemmParams::debug_mode)
     p.debug_mode = dbg ? atoi(dbg) : 0;

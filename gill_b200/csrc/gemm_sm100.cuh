@@ -56,6 +56,7 @@ struct alignas(64) GemmParams {
   int act;
   int in_dtype;  // DT_BF16 or DT_F16
   float alpha;
+  int tile_order;  // 0 auto, 1 m-fastest, 2 n-inner (see tile_coord)
   int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
@@ -455,7 +456,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
 
-  const int order = (num_n <= 4 && num_m >= 2 * static_cast<int>(gridDim.x)) ? -num_n : num_m;  // see tile_coord()
+  const bool n_inner = p.tile_order == 2 || (p.tile_order == 0 && num_n <= 4 && num_m >= 2 * static_cast<int>(gridDim.x));
+  const int order = n_inner ? -num_n : num_m;  // see tile_coord()
   if (warp == 0) {
     gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, order, blockIdx.x, num_tiles, gridDim.x);
   } else if (warp == 1) {

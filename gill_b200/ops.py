@@ -82,6 +82,7 @@ def gemm(
     out_lo: Optional[torch.Tensor] = None,
     block_n: int = 0,
     cta_pair: int = 0,
+    tile_order: int = 0,
 ) -> torch.Tensor:
     """out = act(alpha * a @ b.T + bias + rowbias) + residual     (a: [M,K], b: [N,K], 16-bit; fp32 accumulate).
 
@@ -116,7 +117,7 @@ def gemm(
     if residual is not None:
         _chk2d(residual, "residual")
         g.residual, g.ldr, g.res_dtype = residual.data_ptr(), residual.stride(0), _DT[residual.dtype]
-    g.act, g.alpha, g.block_n, g.cta_pair = _ACT[act], alpha, block_n, cta_pair
+    g.act, g.alpha, g.block_n, g.cta_pair, g.tile_order = _ACT[act], alpha, block_n, cta_pair, tile_order
     ktot = K + (g.k2 if a2_mode == 1 else 0)
     with _P("gemm" if a2_mode != 2 else "gemm_split", 2.0 * M * N * ktot * (2 if a2_mode == 2 else 1),
             2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out, f"M{M} N{N} K{ktot} {act or ''}"):
@@ -137,6 +138,7 @@ def conv3x3(
     a2: Optional[torch.Tensor] = None,
     block_n: int = 0,
     cta_pair: int = 0,
+    tile_order: int = 0,
 ) -> torch.Tensor:
     """3x3 / stride 1 / pad 1 convolution as an implicit GEMM.
 
@@ -172,7 +174,7 @@ def conv3x3(
     if residual is not None:
         r2 = residual.view(B * H * W, N)
         g.residual, g.ldr, g.res_dtype = r2.data_ptr(), r2.stride(0), _DT[residual.dtype]
-    g.act, g.alpha, g.block_n, g.cta_pair = _ACT[act], 1.0, block_n, cta_pair
+    g.act, g.alpha, g.block_n, g.cta_pair, g.tile_order = _ACT[act], 1.0, block_n, cta_pair, tile_order
     with _P("conv3x3", 2.0 * B * H * W * N * (9 * C + (g.k2 or 0)), 2.0 * (B * H * W * C + N * 9 * C + B * H * W * N),
             f"B{B} {H}x{W} C{C}->{N}"):
         check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")

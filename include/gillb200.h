@@ -77,6 +77,7 @@ typedef struct gillb200_gemm_args {
   int act;   /* GEGLU: B rows interleaved (value, gate) pairs; N_out = N/2 */
   float alpha;
   int block_n; /* 0 = auto; else one of 32, 64, 128, 160, 256 */
+  int tile_order; /* 0 = auto; 1 = M-fastest tile order; 2 = N-inner (all N tiles of an M block back to back) */
   int cta_pair; /* 0 = auto; 1 = force the 1-CTA kernel; 2 = force the CTA-pair (tcgen05 cta_group::2, 256-row tile) kernel */
 } gillb200_gemm_args;
 
