@@ -108,21 +108,25 @@ static int launch_gemm2(const GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-// Pick the N tile that minimises (waves x per-tile cost), counting padded columns as wasted work.
-static int pick_block_n(int M, int N) {
+// Pick the N tile width from a small cost model fitted to measurements on B200 (tools/gpu_sweep_shapes.py,
+// profiles/r01_shape_sweep.log): time ~ waves x (k_blocks x BN / eff(BN) + epilogue(BN)), where eff() is the measured
+// MMA-issue / smem-fill efficiency of a 128 x BN tile relative to BN = 256 (MMA-only ceilings: 1868 TF/s at BN=256,
+// ~1300 at BN=160/128). Padding waste is implicit in the tile count.
+static int pick_block_n(int M, int N, int k_blocks) {
   const int cands[5] = {256, 160, 128, 64, 32};
+  const double eff[5] = {1.0, 0.70, 0.70, 0.50, 0.30};
   const int sms = num_sms();
   const int num_m = (M + BLOCK_M - 1) / BLOCK_M;
   double best = 1e30;
-  int best_bn = 128;
+  int best_bn = 256;
   for (int i = 0; i < 5; ++i) {
     const int bn = cands[i];
+    if (bn > 64 && bn / 2 >= N) continue;  // more than half of the tile would be padding
     const int num_n = (N + bn - 1) / bn;
     const long long tiles = 1LL * num_m * num_n;
     const long long waves = (tiles + sms - 1) / sms;
-    // per-tile cost ~ MMA cycles (prop. to bn) + fixed per-tile overhead (epilogue/pipeline fill)
-    const double cost = static_cast<double>(waves) * (bn + 24.0);
-    if (cost < best * 0.999) {
+    const double cost = static_cast<double>(waves) * (k_blocks * (bn / eff[i]) + 8.0 * bn + 400.0);
+    if (cost < best * 0.98) {
       best = cost;
       best_bn = bn;
     }
@@ -216,7 +220,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     GB_CHECK_ARG(a->ldb >= kb_total_cols, "ldb=%lld smaller than K=%d", a->ldb, kb_total_cols);
   }
 
-  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N);
+  int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, p.num_k_blocks);
   if (a->act == ACT_GEGLU) GB_CHECK_ARG(a->N % 2 == 0, "GEGLU needs even N");
   // CTA-pair (cta_group::2) kernel: 256 x bn tiles, each CTA loads half of the B tile. Used when there are enough
   // 256-row tiles to keep every SM pair busy; small problems keep the 1-CTA kernel (more, smaller tiles).
@@ -224,8 +228,10 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   if (a->cta_pair == 2) {
     pair = true;
   } else if (a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
+    // measured: the pair kernel wins (+3..17 %) only when the K loop is long enough to amortise the cluster
+    // handshakes, and loses on short-K, epilogue-heavy shapes
     const long long tiles2 = 1LL * ((a->M + 255) / 256) * ((a->N + bn - 1) / bn);
-    pair = tiles2 >= (num_sms() / 2) * 3 / 4;
+    pair = tiles2 >= (num_sms() / 2) * 3 / 4 && p.num_k_blocks >= 32;
   }
   if (pair) GB_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "cta_pair needs block_n in {64,128,160,256}");
   {
