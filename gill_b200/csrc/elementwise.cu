@@ -256,6 +256,21 @@ __global__ void __launch_bounds__(256) attn_small_f32_kernel(const float* __rest
   }
 }
 
+// out[p, :] = W x[p, :] + b for tiny channel counts (<= 8): the VAE's `latents / 0.18215 -> post_quant_conv` 1x1
+// (gill/custom_sd.py:386-388), folded into one 4x4 map. fp32 in, 16-bit out.
+__global__ void channel_mix_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w,
+                                   const float* __restrict__ b, int cout, long long n, void* __restrict__ out,
+                                   int out_dtype) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n * cout;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long pix = i / cout;
+    const int co = static_cast<int>(i % cout);
+    float acc = b[co];
+    for (int ci = 0; ci < cin; ++ci) acc = fmaf(w[co * cin + ci], x[pix * cin + ci], acc);
+    store_elem(out, i, acc, out_dtype);
+  }
+}
+
 static inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -361,6 +376,16 @@ extern "C" int gillb200_attn_small_f32(const float* q, long long ldq, long long 
   }
   attn_small_f32_kernel<128><<<dim3(H, B), 256, smem, stream>>>(q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
                                                                   out, ldo, o_bs, out_dtype, out_lo);
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_channel_mix(const float* x, int cin, const float* w, const float* b, int cout, long long n,
+                                    void* out, int out_dtype, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x && w && b && out && cin >= 1 && cin <= 8 && cout >= 1 && cout <= 8 && n > 0, "channel_mix: bad args");
+  channel_mix_kernel<<<grid_for(n * cout, 256), 256, 0, stream>>>(x, cin, w, b, cout, n, out, out_dtype);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;

@@ -392,3 +392,14 @@ def attn_small_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int
                                             out.data_ptr(), out.stride(1), out.stride(0), _DT[out.dtype], _ptr(out_lo),
                                             _stream()), "gillb200_attn_small_f32")
     return out
+
+
+def channel_mix(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """out[..., :] = w @ x[..., :] + b over the last (tiny, <= 8) channel dim; x fp32 contiguous."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.dtype == torch.float32 and b.dtype == torch.float32
+    cin, cout = x.shape[-1], w.shape[0]
+    out = torch.empty(x.shape[:-1] + (cout,), device=x.device, dtype=out_dtype)
+    with _P("channel_mix"):
+        check(lib().gillb200_channel_mix(x.data_ptr(), cin, w.data_ptr(), b.data_ptr(), cout, x.numel() // cin,
+                                         out.data_ptr(), _DT[out_dtype], _stream()), "gillb200_channel_mix")
+    return out

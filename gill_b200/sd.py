@@ -394,7 +394,7 @@ class VAEDecoderB200:
         # fold latents / scaling_factor and the 1x1 post_quant_conv into one tiny 4x4 map applied before conv_in
         lc = self.cfg["latent_channels"]
         pq = sd["post_quant_conv.weight"].reshape(lc, lc).float() / self.cfg["scaling_factor"]
-        self.pq_w = pq.to(self.dev)
+        self.pq_w = pq.contiguous().to(self.dev)
         self.pq_b = sd["post_quant_conv.bias"].float().to(self.dev)
         w = self.w["decoder.conv_in.weight"]  # [512, 36] -> K padded to 64
         wp = torch.zeros((w.shape[0], 64), dtype=w.dtype, device=self.dev)
@@ -445,8 +445,8 @@ class VAEDecoderB200:
         cfg, w = self.cfg, self.w
         boc = cfg["block_out_channels"]
         B, H, W, lc = latents.shape
-        # latents/0.18215 -> post_quant_conv: a 4x4 channel map on 16 K elements per image (host-side torch glue)
-        z = (latents.float().reshape(-1, lc) @ self.pq_w.T + self.pq_b).to(self.dt).view(B, H, W, lc).contiguous()
+        # latents/0.18215 -> post_quant_conv: one folded 4x4 channel map
+        z = ops.channel_mix(latents.float().contiguous(), self.pq_w, self.pq_b, self.dt)
         cols = ops.im2col3x3(z, 1, ld_out=64)
         h = ops.gemm(cols, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"]).view(B, H, W, boc[-1])
         h = self._resnet(h, "decoder.mid_block.resnets.0")

@@ -170,6 +170,9 @@ int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int n, void* o
                          void* stream);
 int gillb200_cast_add(const void* x, int x_dtype, const void* y, int y_dtype, long long y_period, void* out,
                       int out_dtype, void* out_lo, long long n, void* stream);
+/* out[p,:] = W x[p,:] + b for <= 8 channels (VAE post_quant_conv folded with the 1/0.18215 scale, custom_sd.py:386) */
+int gillb200_channel_mix(const float* x, int cin, const float* w, const float* b, int cout, long long n, void* out,
+                         int out_dtype, void* stream);
 int gillb200_attn_small_f32(const float* q, long long ldq, long long q_bs, const float* k, long long ldk, long long k_bs,
                             const float* v, long long ldv, long long v_bs, int B, int H, int hd, int Lq, int Lk,
                             float scale, void* out, long long ldo, long long o_bs, int out_dtype, void* out_lo,
