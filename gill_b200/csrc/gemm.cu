@@ -38,8 +38,9 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                      const uint32_t* box, bool is_bf16) {
+// dtype: DT_BF16 / DT_F16 / DT_F32. swizzle_bytes: 128, 64 or 32 (the box's inner extent must not exceed it).
+int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(-EIO, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_err(-EINVAL, "tensor base %p not 16-byte aligned", base);
@@ -55,11 +56,21 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
       if (gstr[i - 1] % 16 != 0) return set_err(-EINVAL, "tensor stride %llu B not a multiple of 16", (unsigned long long)gstr[i - 1]);
     }
   }
-  CUresult r = fn(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank,
-                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapDataType dt = dtype == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                 : dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                   : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                      : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUresult r = fn(out, dt, rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(-EINVAL, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return 0;
+}
+
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool is_bf16) {
+  return encode_tmap(out, base, is_bf16 ? DT_BF16 : DT_F16, rank, dims, strides_bytes, box, 128);
 }
 
 int num_sms() {
@@ -72,37 +83,52 @@ int num_sms() {
   return n;
 }
 
+// Shared-memory plan: [num_stages x stage][1 KB barriers][epilogue staging] (+1 KB alignment slack). The smem-staged
+// epilogue trades ring stages for staging buffers.
+static int plan_smem(GemmParams& p, int stage_bytes, int max_stages) {
+  const int epi_bytes = p.epi_tma ? p.epi_warps * p.epi_nbuf * p.epi_buf_bytes : 0;
+  int stages = (SMEM_BUDGET - 2048 - epi_bytes) / stage_bytes;
+  if (stages > max_stages) stages = max_stages;
+  if (stages > 8) stages = 8;
+  p.num_stages = stages;
+  return stages * stage_bytes + 2048 + epi_bytes;
+}
+
 template <int BN>
-static int launch_gemm(const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   using C = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    GB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    GB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     configured = true;
   }
+  const int smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
+  GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (BN=%d)", BN);
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);
+  gemm_kernel<BN><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <int BN>
-static int launch_gemm2(const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   static bool configured = false;
   if (!configured) {
-    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
     configured = true;
   }
+  const int smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
+  GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (pair, BN=%d)", BN);
   const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles = num_m2 * num_n;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  gemm2_kernel<BN><<<2 * pairs, GEMM_THREADS, C::SMEM_BYTES, stream>>>(p);  // __cluster_dims__(2,1,1)
+  gemm2_kernel<BN><<<2 * pairs, GEMM_THREADS, smem_bytes, stream>>>(p);  // __cluster_dims__(2,1,1)
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -221,7 +247,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   }
 
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, p.num_k_blocks);
-  if (a->act == ACT_GEGLU) GB_CHECK_ARG(a->N % 2 == 0, "GEGLU needs even N");
+  if (a->act == ACT_GEGLU) {
+    GB_CHECK_ARG(a->N % 2 == 0, "GEGLU needs even N");
+    // the smem-staged epilogue emits 32-column output panels = 64 accumulator columns under GEGLU
+    if (!a->block_n && bn % 64 != 0) bn = bn > 64 ? 128 : 64;
+  }
   // CTA-pair (cta_group::2) kernel: 256 x bn tiles, each CTA loads half of the B tile. Used when there are enough
   // 256-row tiles to keep every SM pair busy; small problems keep the 1-CTA kernel (more, smaller tiles).
   bool pair = false;
@@ -262,6 +292,74 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     p.debug_mode = dbg ? atoi(dbg) : 0;
   }
   if (a->out_lo) GB_CHECK_ARG(a->out_dtype == DT_BF16, "out_lo requires a bf16 primary output");
+
+  // ---- epilogue selection: smem-staged TMA stores wherever the layout allows, else the direct per-lane epilogue
+  {
+    static int env_epi = -1, env_warps = 0, env_warps_res = 0;
+    if (env_epi < 0) {
+      const char* e = getenv("GILLB200_EPI");  // "0" forces the direct epilogue (A/B measurements)
+      env_epi = e ? atoi(e) : 1;
+      const char* w = getenv("GILLB200_EPI_WARPS");  // tuning aid: epilogue warps of the staged epilogue
+      env_warps = w ? atoi(w) : 0;
+      if (env_warps != 4 && env_warps != 8 && env_warps != 12 && env_warps != 16) env_warps = 0;
+      const char* wr = getenv("GILLB200_EPI_WARPS_RES");  // same, for launches with a residual (3 buffers per warp)
+      env_warps_res = wr ? atoi(wr) : env_warps;
+      if (env_warps_res != 4 && env_warps_res != 8 && env_warps_res != 12 && env_warps_res != 16) env_warps_res = 0;
+    }
+    const int esz = a->out_dtype == DT_F32 ? 4 : 2;
+    const int n_out = a->act == ACT_GEGLU ? a->N / 2 : a->N;
+    bool ok = env_epi != 0 && a->out_lo == nullptr && reinterpret_cast<uintptr_t>(a->out) % 16 == 0 &&
+              (a->ldo * esz) % 16 == 0;
+    if (a->residual)
+      ok = ok && a->res_dtype == a->out_dtype && reinterpret_cast<uintptr_t>(a->residual) % 16 == 0 &&
+           (a->ldr * esz) % 16 == 0;
+    if (a->act == ACT_GEGLU && bn % 64 != 0) ok = false;  // explicitly requested odd tile width
+    if (ok) {
+      const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
+      const uint32_t box[2] = {EPI_PANEL_COLS, 32};
+      const uint64_t so[1] = {(uint64_t)a->ldo * esz};
+      int r = encode_tmap(&p.tma_out, a->out, a->out_dtype, 2, dims, so, box, esz == 4 ? 128 : 64);
+      if (r) return r;
+      if (a->residual) {
+        const uint64_t sr[1] = {(uint64_t)a->ldr * esz};
+        r = encode_tmap(&p.tma_res, a->residual, a->res_dtype, 2, dims, sr, box, esz == 4 ? 128 : 64);
+        if (r) return r;
+      }
+      p.epi_tma = 1;
+      p.epi_variant = EV_GENERIC;
+      const bool plain = a->out_dtype == DT_F16 && a->alpha == 1.f && a->bias && !a->bias_along_m &&
+                         reinterpret_cast<uintptr_t>(a->bias) % 16 == 0;
+      if (plain && a->act == ACT_GEGLU && a->N % 64 == 0 && !a->rowbias && !a->residual) {
+        p.epi_variant = EV_GEGLU;
+      } else if (plain && a->act == ACT_NONE && a->N % 32 == 0) {
+        if (a->rowbias && !a->residual && a->ld_rowbias % 4 == 0 && reinterpret_cast<uintptr_t>(a->rowbias) % 16 == 0)
+          p.epi_variant = EV_BIAS_ROWBIAS;
+        else if (a->residual && !a->rowbias)
+          p.epi_variant = EV_BIAS_RES;
+        else if (!a->residual && !a->rowbias)
+          p.epi_variant = EV_BIAS;
+      }
+      {
+        static int env_var = -2;
+        if (env_var == -2) {
+          const char* e = getenv("GILLB200_EPI_GENERIC");  // "1": always the all-runtime staged epilogue (A/B)
+          env_var = e ? atoi(e) : 0;
+        }
+        if (env_var) p.epi_variant = EV_GENERIC;
+      }
+      p.epi_nbuf = a->residual ? 3 : 2;
+      p.epi_buf_bytes = 32 * EPI_PANEL_COLS * esz;
+      // as many epilogue warps as leave a >= 3-deep operand ring (fp32 panels are twice as large)
+      // measured (tools/gpu_sweep_shapes.py): 8 warps + a deeper operand ring win everywhere except the erf-heavy
+      // GEGLU epilogue, which wants all 16
+      p.epi_warps = a->act == ACT_GEGLU ? 16 : 8;
+      if (a->residual ? env_warps_res : env_warps) p.epi_warps = a->residual ? env_warps_res : env_warps;
+      const int stage_bytes = (BLOCK_M + (pair ? bn / 2 : bn)) * BLOCK_K * 2;
+      while (p.epi_warps > 4 &&
+             (SMEM_BUDGET - 2048 - p.epi_warps * p.epi_nbuf * p.epi_buf_bytes) / stage_bytes < 3)
+        p.epi_warps -= 4;
+    }
+  }
 
   if (pair) {
     switch (bn) {

@@ -39,7 +39,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
-  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + C::STAGES * C::STAGE_BYTES);
+  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + p.num_stages * C::STAGE_BYTES);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const uint32_t rank = cluster_ctarank();
@@ -59,7 +60,13 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], 2 * GEMM_EPI_WARPS);
+      mbar_init(&bars->tmem_empty[i], 2 * (p.epi_tma ? p.epi_warps : GEMM_EPI_WARPS));
+    }
+    if (p.epi_tma) {
+      tma_prefetch_desc(&p.tma_out);
+      if (p.residual) tma_prefetch_desc(&p.tma_res);
+      for (int w = 0; w < GEMM_EPI_WARPS; ++w)
+        for (int i = 0; i < EPI_MAX_NBUF; ++i) mbar_init(&bars->res_full[w][i], 1);
     }
     fence_barrier_init();
   }
@@ -107,7 +114,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             tma2_load_2d(sb, &p.tma_b, full_leader, (kb % p.b_kb_wrap) * BLOCK_K, n0);
           }
           __syncwarp();
-          if (++stage == C::STAGES) {
+          if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -140,7 +147,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
           }
           __syncwarp();
-          if (++stage == C::STAGES) {
+          if (++stage == p.num_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -155,6 +162,21 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp >= 4) {
     // ---------------- epilogue (both CTAs, own 128 accumulator rows)
+    if (p.epi_tma) {
+      if (warp - 4 < p.epi_warps) {
+        epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE>(
+            p, bars, epi_stage, tmem_base, pair, num_tiles, num_pairs,
+            [&](int tile, int* row_base, int* n0) {
+              *row_base = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+              *n0 = (tile / num_m2) * BLOCK_N;
+            },
+            [&](int acc) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane_id() == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+            });
+      }
+    } else {
     const int ewarp = warp & 3;
     const int cgrp = (warp - 4) >> 2;
     constexpr int NGRP = GEMM_EPI_WARPS / 4;
@@ -189,6 +211,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         acc = 0;
         acc_phase ^= 1;
       }
+    }
     }
   }
 

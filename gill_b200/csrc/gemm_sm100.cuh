@@ -57,6 +57,17 @@ struct alignas(64) GemmParams {
   int in_dtype;  // DT_BF16 or DT_F16
   float alpha;
   int tile_order;  // 0 auto, 1 m-fastest, 2 n-inner (see tile_coord)
+  // smem-staged epilogue (epi_tma != 0): each epilogue warp writes 32-row x 32-column output panels into swizzled
+  // shared memory and one lane hands them to TMA (tma_out); the residual panel is TMA-loaded into the same buffer
+  // ahead of time (tma_res). Global memory only ever sees full-line bulk transactions.
+  CUtensorMap tma_out;
+  CUtensorMap tma_res;
+  int epi_tma;
+  int epi_variant;    // EV_* specialisation of the staged epilogue
+  int epi_warps;      // epilogue warps that take part (multiple of 4, <= GEMM_EPI_WARPS)
+  int epi_nbuf;       // staging buffers per warp: 2, or 3 with a residual
+  int epi_buf_bytes;  // 2048 (16-bit output) or 4096 (fp32 output)
+  int num_stages;     // smem ring depth actually used (<= GemmCfg::STAGES)
   int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
@@ -127,7 +138,7 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
       if (p.debug_mode == 1 && (phase != 0 || tile != tile_begin)) {  // measurement only: reuse stale smem
         if (elect_one()) mbar_arrive(&full[stage]);
         __syncwarp();
-        if (++stage == C::STAGES) {
+        if (++stage == p.num_stages) {
           stage = 0;
           phase ^= 1;
         }
@@ -148,7 +159,7 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
         tma_load_2d(sb, &p.tma_b, &full[stage], (kb % p.b_kb_wrap) * BLOCK_K, n0);
       }
       __syncwarp();
-      if (++stage == C::STAGES) {
+      if (++stage == p.num_stages) {
         stage = 0;
         phase ^= 1;
       }
@@ -188,7 +199,7 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
         umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
       }
       __syncwarp();
-      if (++stage == C::STAGES) {
+      if (++stage == p.num_stages) {
         stage = 0;
         phase ^= 1;
       }
@@ -248,10 +259,10 @@ __device__ __forceinline__ void store_elem(void* base, long long idx, float v, i
     reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
 
-// Processes 16 accumulator columns [n, n+16) of one row. `v` holds the raw fp32 accumulators.
-__device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, int row, int n, float* v) {
+// alpha / bias / per-sample row bias / activation on 16 accumulator columns [n, n+16) of one row (in place).
+// Returns the number of output values left in v[0..cnt): 8 for GEGLU (value * gelu(gate) pairs), else 16.
+__device__ __forceinline__ int epi_math16(const GemmParams& p, int row, int n, float* v) {
   const bool geglu = p.act == ACT_GEGLU;
-  const int n_out_total = geglu ? p.N / 2 : p.N;
   if (p.alpha != 1.f) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] *= p.alpha;
@@ -295,19 +306,29 @@ __device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, int row, i
         if (n + j < p.N) v[j] += __ldg(rb + n + j);
     }
   }
-  int cnt = 16, no = n;
   if (geglu) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float a = v[2 * j], g = v[2 * j + 1];
       v[j] = a * gelu_erf(g);
     }
-    cnt = 8;
-    no = n / 2;
-  } else if (p.act != ACT_NONE) {
+    return 8;
+  }
+  if (p.act != ACT_NONE) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
   }
+  return 16;
+}
+
+// Direct epilogue: 16 accumulator columns [n, n+16) of one row -> math -> (+ residual) -> global stores by the
+// owning lane. Handles every layout (odd strides, out_lo, mixed residual dtype); each lane touches its own row, so a
+// warp store instruction spans 32 cache lines -- used only where the smem-staged TMA epilogue cannot be.
+__device__ __forceinline__ void epilogue_chunk16(const GemmParams& p, int row, int n, float* v) {
+  const bool geglu = p.act == ACT_GEGLU;
+  const int n_out_total = geglu ? p.N / 2 : p.N;
+  const int cnt = epi_math16(p, row, n, v);
+  const int no = geglu ? n / 2 : n;
   const bool full = (no + cnt <= n_out_total);
   if (p.residual) {
     const long long roff = static_cast<long long>(row) * p.ldr + no;
@@ -410,15 +431,302 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tme
   }
 }
 
-// Kernel -------------------------------------------------------------------------------------------------------
+// Smem-staged TMA epilogue -----------------------------------------------------------------------------------------
+//
+// Why: with the direct epilogue every lane owns one output row, so each 16-byte store/load instruction of a warp
+// touches 32 different cache lines = 32 L1TEX wavefronts; a 128x256 fp16 tile costs >4000 LSU cycles, more than the
+// 2560 tensor cycles of a K=320 tile (measured: the UNet's short-K linears ran at 250-600 TFLOP/s). Here the warp
+// writes its 32x32 panel into swizzled shared memory (conflict-free 16-byte accesses) and a single lane issues one TMA
+// store; residual panels come in the same way, prefetched one panel ahead, and are overwritten in place.
+constexpr int EPI_PANEL_COLS = 32;
+constexpr int EPI_MAX_NBUF = 3;
+
+// Compile-time specialisations of the staged epilogue for the shapes that dominate the UNet (fp16 output, N % 32 == 0,
+// alpha == 1, column bias present); EV_GENERIC keeps every option a runtime branch (fp32 / bf16 outputs, other
+// activations, bias along M, N tails). ncu on the first, all-runtime version: ~400 warp instructions per 32x32 panel,
+// 44 % issue-slot utilisation and the epilogue warps latency-bound -- the specialised bodies are ~100.
+enum { EV_BIAS = 0, EV_BIAS_RES = 1, EV_BIAS_ROWBIAS = 2, EV_GEGLU = 3, EV_GENERIC = 4 };
+
+// 16-byte unit `u` of row `r` inside a 32-row panel buffer written/read by TMA with SWIZZLE_64B (16-bit elements,
+// 64-byte rows) or SWIZZLE_128B (fp32, 128-byte rows)
+__device__ __forceinline__ uint8_t* epi_unit(uint8_t* buf, int r, int u, bool f32) {
+  return f32 ? buf + r * 128 + ((u ^ (r & 7)) << 4) : buf + r * 64 + ((u ^ ((r >> 1) & 3)) << 4);
+}
+
+// v[0..cnt) -> (+ residual already sitting in the buffer) -> buffer, at output column `oc` of the panel
+__device__ __forceinline__ void epi_to_smem(const GemmParams& p, uint8_t* buf, int r, int oc, const float* v, int cnt,
+                                            bool has_res) {
+  if (p.out_dtype == DT_F32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (i * 4 < cnt) {
+        float4* q = reinterpret_cast<float4*>(epi_unit(buf, r, (oc >> 2) + i, true));
+        float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        if (has_res) {
+          const float4 t = *q;
+          o.x += t.x;
+          o.y += t.y;
+          o.z += t.z;
+          o.w += t.w;
+        }
+        *q = o;
+      }
+    }
+  } else {
+    const bool bf16 = p.out_dtype == DT_BF16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (i * 8 < cnt) {
+        uint4* q = reinterpret_cast<uint4*>(epi_unit(buf, r, (oc >> 3) + i, false));
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = v[8 * i + j];
+        if (has_res) {
+          const uint4 t = *q;
+          const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 g = bf16 ? unpack_bf16x2(w[j]) : unpack_f16x2(w[j]);
+            f[2 * j] += g.x;
+            f[2 * j + 1] += g.y;
+          }
+        }
+        uint4 o;
+        if (bf16) {
+          o.x = pack_bf16x2(f[0], f[1]);
+          o.y = pack_bf16x2(f[2], f[3]);
+          o.z = pack_bf16x2(f[4], f[5]);
+          o.w = pack_bf16x2(f[6], f[7]);
+        } else {
+          o.x = pack_f16x2(f[0], f[1]);
+          o.y = pack_f16x2(f[2], f[3]);
+          o.z = pack_f16x2(f[4], f[5]);
+          o.w = pack_f16x2(f[6], f[7]);
+        }
+        *q = o;
+      }
+    }
+  }
+}
+
+// v[0..8k) fp32 -> fp16 -> 16-byte units [u0, u0 + k) of row `lane` (SWIZZLE_64B panel), adding the fp16 residual that
+// already sits there when RES.
+template <int K8, bool RES>
+__device__ __forceinline__ void epi_f16_units(uint8_t* buf, int lane, int u0, float* f) {
+  uint8_t* rowp = buf + lane * 64;
+  const int x = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < K8; ++i) {
+    uint4* q = reinterpret_cast<uint4*>(rowp + (((u0 + i) ^ x) << 4));
+    if (RES) {
+      const uint4 t = *q;
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 g = unpack_f16x2(w[j]);
+        f[8 * i + 2 * j] += g.x;
+        f[8 * i + 2 * j + 1] += g.y;
+      }
+    }
+    *q = make_uint4(pack_f16x2(f[8 * i], f[8 * i + 1]), pack_f16x2(f[8 * i + 2], f[8 * i + 3]),
+                    pack_f16x2(f[8 * i + 4], f[8 * i + 5]), pack_f16x2(f[8 * i + 6], f[8 * i + 7]));
+  }
+}
 
 struct GemmSmemBars {
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[GEMM_EPI_WARPS][EPI_MAX_NBUF];
   uint32_t tmem_ptr;
 };
+static_assert(sizeof(GemmSmemBars) <= 1024, "barrier block");
+
+// The staged epilogue of one warp over all of its tiles.
+//   tile_fn(tile, &row_base, &n0): first accumulator row of this CTA's 128-row block and first column of the tile.
+//   release_fn(acc): arrive on the tile's tmem_empty barrier (local, or the pair leader's for cta_group::2).
+// Per panel: [lane 0: make sure the staging buffer is free, prefetch the next residual panel] -> bias loads in flight
+// -> tcgen05.ld -> math -> swizzled st.shared -> fence.proxy.async -> [lane 0: TMA store].
+template <int BLOCK_N, int ACC_STRIDE, int VAR, typename TileFn, typename Release>
+__device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemBars* bars, uint8_t* epi_stage,
+                                                  uint32_t tmem_base, int tile_begin, int tile_end, int tile_step,
+                                                  TileFn tile_fn, Release release_fn) {
+  const int warp = threadIdx.x >> 5;
+  const int ew = warp - 4, quad = warp & 3;
+  const int cgrp = ew >> 2, ngrp = p.epi_warps >> 2;
+  const int lane = lane_id();
+  constexpr bool GEGLU = VAR == EV_GEGLU;
+  const bool geglu = VAR == EV_GENERIC ? p.act == ACT_GEGLU : GEGLU;
+  const bool has_res = VAR == EV_GENERIC ? p.residual != nullptr : VAR == EV_BIAS_RES;
+  const int acc_per_panel = geglu ? 2 * EPI_PANEL_COLS : EPI_PANEL_COLS;
+  const int np = (BLOCK_N + acc_per_panel - 1) / acc_per_panel;
+  const int n_out_total = geglu ? p.N / 2 : p.N;
+  const int pb0 = cgrp * (np / ngrp) + min(cgrp, np % ngrp);
+  const int pe0 = pb0 + np / ngrp + (cgrp < np % ngrp ? 1 : 0);
+  const uint32_t nbuf = static_cast<uint32_t>(p.epi_nbuf);
+  const uint32_t panel_bytes = static_cast<uint32_t>(p.epi_buf_bytes);
+  uint8_t* stage = epi_stage + ew * nbuf * panel_bytes;
+  uint64_t* res_bar = bars->res_full[ew];
+  // staging-buffer rotation: `buf` = buffer of the current panel, `par` bit b = parity of res_bar[b]'s next completion
+  uint32_t buf = 0, par = 0;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+
+  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+    int row_base, n0;
+    tile_fn(tile, &row_base, &n0);
+    const int row0 = row_base + quad * 32;
+    const int no0 = geglu ? n0 >> 1 : n0;
+    const uint32_t taddr = tmem_base + acc * ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
+    // panels entirely beyond N (last N tile) or a slab entirely beyond M produce nothing
+    int pe = min(pe0, (n_out_total - no0 + EPI_PANEL_COLS - 1) / EPI_PANEL_COLS);
+    if (row0 >= p.M) pe = pb0;
+    const int row = min(row0 + lane, p.M - 1);  // rows >= M are clipped by the TMA store; clamp only for bias reads
+    const float* rb_row = nullptr;
+    if (VAR == EV_BIAS_ROWBIAS) rb_row = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ld_rowbias;
+
+    auto fetch_res = [&](int pnl, uint32_t b) {  // lane 0 only
+      mbar_arrive_expect_tx(&res_bar[b], panel_bytes);
+      tma_load_2d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, row0);
+    };
+    if (has_res && pb0 < pe && lane == 0) {  // the first residual panel travels while the tile's MMAs finish
+      tma_store_wait_read<1>();
+      fetch_res(pb0, buf);
+    }
+    mbar_wait(&bars->tmem_full[acc], acc_phase);
+    tc_fence_after();
+    if (pb0 >= pe) release_fn(acc);
+
+    for (int pnl = pb0; pnl < pe; ++pnl) {
+      uint8_t* sbuf = stage + buf * panel_bytes;
+      const uint32_t nxt = buf + 1 == nbuf ? 0 : buf + 1;
+      if (lane == 0) {
+        tma_store_wait_read<1>();  // the store issued two panels ago has drained its staging buffer
+        if (has_res && pnl + 1 < pe) fetch_res(pnl + 1, nxt);
+      }
+      __syncwarp();
+      const bool last = pnl == pe - 1;
+      const int nacc = n0 + pnl * acc_per_panel;  // first accumulator column (global) of this panel
+
+      if (VAR == EV_GENERIC) {
+        if (has_res) mbar_wait(&res_bar[buf], (par >> buf) & 1);
+        const int halves = geglu ? 2 : 1;
+#pragma unroll 1
+        for (int h = 0; h < halves; ++h) {
+          const int acol = pnl * acc_per_panel + h * 32;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + acol, r);
+          tmem_wait_ld();
+          if (last && h == halves - 1) release_fn(acc);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[16 * c + j]);
+            const int cnt = epi_math16(p, row, n0 + acol + 16 * c, v);
+            epi_to_smem(p, sbuf, lane, geglu ? h * 16 + 8 * c : 16 * c, v, cnt, has_res);
+          }
+        }
+      } else if (GEGLU) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nacc + h * 32);
+          float4 bv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + pnl * 64 + h * 32, r);
+          tmem_wait_ld();
+          if (last && h == 1) release_fn(acc);
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // (value, gate) pairs are interleaved along N
+            f[2 * i] = (__uint_as_float(r[4 * i]) + bv[i].x) * gelu_erf(__uint_as_float(r[4 * i + 1]) + bv[i].y);
+            f[2 * i + 1] = (__uint_as_float(r[4 * i + 2]) + bv[i].z) * gelu_erf(__uint_as_float(r[4 * i + 3]) + bv[i].w);
+          }
+          epi_f16_units<2, false>(sbuf, lane, 2 * h, f);
+        }
+      } else {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + nacc);
+        float4 bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+        if (VAR == EV_BIAS_ROWBIAS) {
+          const float4* r4 = reinterpret_cast<const float4*>(rb_row + nacc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = __ldg(r4 + i);
+            bv[i].x += t.x;
+            bv[i].y += t.y;
+            bv[i].z += t.z;
+            bv[i].w += t.w;
+          }
+        }
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + pnl * 32, r);
+        tmem_wait_ld();
+        if (last) release_fn(acc);
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          f[4 * i] = __uint_as_float(r[4 * i]) + bv[i].x;
+          f[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bv[i].y;
+          f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv[i].z;
+          f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv[i].w;
+        }
+        if (VAR == EV_BIAS_RES) mbar_wait(&res_bar[buf], (par >> buf) & 1);
+        epi_f16_units<4, VAR == EV_BIAS_RES>(sbuf, lane, 0, f);
+      }
+
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
+        tma_store_commit();
+      }
+      par ^= 1u << buf;
+      buf = nxt;
+    }
+    if (++acc == 2) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
+  }
+  if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk reads
+}
+
+// Runtime -> compile-time variant dispatch (once per warp, outside the tile loop).
+template <int BLOCK_N, int ACC_STRIDE, typename TileFn, typename Release>
+__device__ __forceinline__ void epilogue_warp_tma_dispatch(const GemmParams& p, GemmSmemBars* bars, uint8_t* epi_stage,
+                                                           uint32_t tmem_base, int tile_begin, int tile_end,
+                                                           int tile_step, TileFn tile_fn, Release release_fn) {
+  switch (p.epi_variant) {
+    case EV_BIAS:
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS>(p, bars, epi_stage, tmem_base, tile_begin, tile_end, tile_step,
+                                                       tile_fn, release_fn);
+      break;
+    case EV_BIAS_RES:
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_RES>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
+                                                           tile_step, tile_fn, release_fn);
+      break;
+    case EV_BIAS_ROWBIAS:
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_ROWBIAS>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
+                                                               tile_step, tile_fn, release_fn);
+      break;
+    case EV_GEGLU:
+      if constexpr (BLOCK_N % 64 == 0)
+        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GEGLU>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
+                                                          tile_step, tile_fn, release_fn);
+      break;
+    default:
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GENERIC>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
+                                                          tile_step, tile_fn, release_fn);
+  }
+}
+
+// Kernel -------------------------------------------------------------------------------------------------------
+
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -426,7 +734,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_tiles = smem;
-  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + C::STAGES * C::STAGE_BYTES);
+  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + p.num_stages * C::STAGE_BYTES);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
@@ -443,7 +752,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
-      mbar_init(&bars->tmem_empty[i], GEMM_EPI_WARPS);
+      mbar_init(&bars->tmem_empty[i], p.epi_tma ? p.epi_warps : GEMM_EPI_WARPS);
+    }
+    if (p.epi_tma) {
+      tma_prefetch_desc(&p.tma_out);
+      if (p.residual) tma_prefetch_desc(&p.tma_res);
+      for (int w = 0; w < GEMM_EPI_WARPS; ++w)
+        for (int i = 0; i < EPI_MAX_NBUF; ++i) mbar_init(&bars->res_full[w][i], 1);
     }
     fence_barrier_init();
   }
@@ -464,7 +779,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
                       blockIdx.x, num_tiles, gridDim.x);
   } else if (warp >= 4) {
-    gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, order, num_tiles);
+    if (!p.epi_tma) {
+      gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, order, num_tiles);
+    } else if (warp - 4 < p.epi_warps) {
+      epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE>(
+          p, bars, epi_stage, tmem_base, blockIdx.x, num_tiles, gridDim.x,
+          [&](int tile, int* row_base, int* n0) {
+            const TileCoord tc = tile_coord(tile, order);
+            *row_base = tc.m_blk * BLOCK_M;
+            *n0 = tc.n_blk * BLOCK_N;
+          },
+          [&](int acc) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane_id() == 0) mbar_arrive(&bars->tmem_empty[acc]);
+          });
+    }
   }
 
   tc_fence_before();

@@ -30,6 +30,10 @@ int set_err(int code, const char* fmt, ...);
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool is_bf16);
 
+// general form: dtype 0 = bf16, 1 = fp16, 2 = fp32; swizzle_bytes 128 / 64 / 32
+int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
 int num_sms();
 
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)

@@ -276,6 +276,7 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
     int r = encode_tmap_16bit(&p.tma_b, bank, 2, dims, strides, box, true);
     if (r) return r;
   }
+  p.num_stages = GemmCfg<TOPK_BN>::STAGES;
   TopkEpi e;
   memset(&e, 0, sizeof(e));
   const int num_m = (Q + BLOCK_M - 1) / BLOCK_M;
