@@ -17,6 +17,7 @@
 #include "gemm_sm100.cuh"
 #include "host_common.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace gb {
@@ -79,11 +80,48 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// two exponentials per MUFU operation; the result is already the packed fp16 pair the P tile stores
-__device__ __forceinline__ uint32_t exp2_f16x2(uint32_t x) {
-  uint32_t y;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
-  return y;
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// max of 32 raw scores; unmasked tiles use the 3-input FMNMX3 (17 instructions instead of 31)
+template <bool MASKED>
+__device__ __forceinline__ float attn_max32(const uint32_t (&v)[32], int c, int lim) {
+  if (!MASKED) {
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+      t[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    return fmax3(fmax3(t[0], t[1], t[2]), fmax3(t[3], t[4], t[5]), fmax3(fmax3(t[6], t[7], t[8]), t[9], t[10]));
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+  return mx;
+}
+
+// p = exp2(s * scale - m) for 32 columns -> 16 packed pairs; returns the fp32 row-sum contribution when SUM. Masked
+// columns (> lim) give exactly 0. Compile-time variants keep the interior-tile path free of selects.
+template <bool MASKED, bool SUM, bool BF16>
+__device__ __forceinline__ float attn_exp32(const uint32_t (&v)[32], int c, int lim, float scale_log2, float m,
+                                            uint32_t (&pk)[16]) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), scale_log2, -m));
+    float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m));
+    if (MASKED) {
+      p0 = (c + i <= lim) ? p0 : 0.f;
+      p1 = (c + i + 1 <= lim) ? p1 : 0.f;
+    }
+    if (SUM) sum += p0 + p1;
+    pk[i >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+  }
+  return sum;
 }
 
 template <int HD_PAD, int BLOCK_KV>
@@ -214,8 +252,8 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
     const uint32_t lane_off = static_cast<uint32_t>(ewarp * 32) << 16;
     const bool bf16 = p.in_dtype == DT_BF16;
     uint8_t* sp = smem + C::OFF_P;
-    float m_used = -INFINITY, l = 0.f;
-    const bool packed = !bf16 && p.ones_col >= 0;  // fp16 P with the denominator taken from V's ones column
+    float m_used = 0.f, l = 0.f;
+    const bool use_ones = p.ones_col >= 0;  // softmax denominator comes out of the P.V product (V's ones column)
     const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j % C::SBUF;
@@ -227,40 +265,33 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
       const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
       // interior tiles (every column visible to every row of this warp) skip all masking work
       const bool no_mask = __all_sync(0xffffffffu, lim >= BLOCK_KV - 1);
-      // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_KV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ts + c, v);
-        tmem_wait_ld();
+
+      auto max32 = [&](const uint32_t (&v)[32], int c) -> float {
+        return no_mask ? attn_max32<false>(v, c, lim) : attn_max32<true>(v, c, lim);
+      };
+      // p = exp2(s*scale - m_used) for 32 columns -> packed 16-bit pairs; returns their fp32 sum (0 when use_ones)
+      auto exp32 = [&](const uint32_t (&v)[32], int c, uint32_t (&pk)[16]) -> float {
         if (no_mask) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+          if (use_ones) return bf16 ? attn_exp32<false, false, true>(v, c, lim, p.scale_log2, m_used, pk)
+                                    : attn_exp32<false, false, false>(v, c, lim, p.scale_log2, m_used, pk);
+          return bf16 ? attn_exp32<false, true, true>(v, c, lim, p.scale_log2, m_used, pk)
+                      : attn_exp32<false, true, false>(v, c, lim, p.scale_log2, m_used, pk);
         }
-      }
-      mx *= p.scale_log2;
-      // lazy rescale decision (warp-uniform because tcgen05.ld/st are .sync.aligned)
-      float alpha = 1.f;
-      bool need = false;
-      if (j == 0) {
-        m_used = mx == -INFINITY ? 0.f : mx;
-      } else if (mx > m_used + 8.f) {
-        alpha = fast_exp2(m_used - mx);
-        m_used = mx;
-        need = true;
-      }
-      // P buffer free and O quiescent once P.V of tile j-1 has retired
-      if (j > 0) {
-        mbar_wait(&bars->p_empty, (j - 1) & 1);
-        tc_fence_after();
-      }
-      if (__any_sync(0xffffffffu, need)) {
-        l *= alpha;
+        return bf16 ? attn_exp32<true, true, true>(v, c, lim, p.scale_log2, m_used, pk)
+                    : attn_exp32<true, true, false>(v, c, lim, p.scale_log2, m_used, pk);
+      };
+      // P -> smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7))
+      auto store32 = [&](const uint32_t (&pk)[16], int c) {
+        uint8_t* chunk = sp + (c >> 6) * (128 * 128) + r * 128;
+        const int u0 = (c & 63) >> 3;  // first 16-B unit of this 32-column group within the 64-column chunk
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int phys = (u0 + u) ^ (r & 7);
+          *reinterpret_cast<uint4*>(chunk + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
+      };
+      // O *= alpha (TMEM round trip); only when some row's running max grew by more than 2^8
+      auto rescale_o = [&](float alpha) {
         const uint32_t to = tmem_base + C::TMEM_O + lane_off;
 #pragma unroll 1
         for (int c = 0; c < HD_PAD; c += 16) {
@@ -272,52 +303,66 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
           tmem_st_32x32b_x16(to + c, v);
         }
         tmem_wait_st();
-      }
-      // pass 2: p = exp2(s*scale - m), row sum, P -> smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7)).
-      auto emit = [&](const uint32_t (&v)[32], int c) {
-        uint32_t pk[16];
-        if (packed) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float x0 = fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used);
-            float x1 = fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used);
-            if (!no_mask) {
-              x0 = (c + i <= lim) ? x0 : -60000.f;
-              x1 = (c + i + 1 <= lim) ? x1 : -60000.f;
-            }
-            pk[i >> 1] = exp2_f16x2(pack_f16x2(x0, x1));
-          }
-        } else if (no_mask) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used));
-            l += p0 + p1;
-            pk[i >> 1] = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = (c + i <= lim) ? fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_used)) : 0.f;
-            const float p1 = (c + i + 1 <= lim) ? fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_used)) : 0.f;
-            l += p0 + p1;
-            pk[i >> 1] = bf16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
-          }
-        }
-        uint8_t* chunk = sp + (c >> 6) * (128 * 128) + r * 128;
-        const int u0 = (c & 63) >> 3;  // first 16-B unit of this 32-column group within the 64-column chunk
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int phys = (u0 + u) ^ (r & 7);
-          *reinterpret_cast<uint4*>(chunk + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-        }
       };
+
+      if (j == 0) {
+        // first tile: true row max first (two passes over S)
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_KV; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(ts + c, v);
-        tmem_wait_ld();
-        emit(v, c);
+        for (int c = 0; c < BLOCK_KV; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(ts + c, v);
+          tmem_wait_ld();
+          mx = fmaxf(mx, max32(v, c));
+        }
+        m_used = mx == -INFINITY ? 0.f : mx * p.scale_log2;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_KV; c += 32) {
+          uint32_t v[32], pk[16];
+          tmem_ld_32x32b_x32(ts + c, v);
+          tmem_wait_ld();
+          l += exp32(v, c, pk);
+          store32(pk, c);
+        }
+      } else {
+        // later tiles: ONE pass. Exponentials are taken against the running reference max while the tile max is
+        // tracked on the side (FMNMX3); only if it exceeds the reference by more than 2^8 is the tile redone after
+        // rescaling O. The exp work of the first 32 columns overlaps P.V of the previous tile (p_empty wait below).
+        float mx = -INFINITY, lt = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_KV; c += 32) {
+          uint32_t v[32], pk[16];
+          tmem_ld_32x32b_x32(ts + c, v);
+          tmem_wait_ld();
+          mx = fmaxf(mx, max32(v, c));
+          lt += exp32(v, c, pk);
+          if (c == 0) {  // P buffer free and O quiescent once P.V of tile j-1 has retired
+            mbar_wait(&bars->p_empty, (j - 1) & 1);
+            tc_fence_after();
+          }
+          store32(pk, c);
+        }
+        mx *= p.scale_log2;
+        const bool need = mx > m_used + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          float alpha = 1.f;
+          if (need) {
+            alpha = fast_exp2(m_used - mx);
+            m_used = mx;
+          }
+          l *= alpha;
+          rescale_o(alpha);
+          lt = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < BLOCK_KV; c += 32) {
+            uint32_t v[32], pk[16];
+            tmem_ld_32x32b_x32(ts + c, v);
+            tmem_wait_ld();
+            lt += exp32(v, c, pk);
+            store32(pk, c);
+          }
+        }
+        l += lt;
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -331,7 +376,7 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
     mbar_wait(&bars->o_done, 0);
     tc_fence_after();
     const uint32_t to = tmem_base + C::TMEM_O + lane_off;
-    if (packed) {
+    if (use_ones) {
       l = __uint_as_float(tmem_ld_32x32b_x1(to + p.ones_col));
       tmem_wait_ld();
     }
@@ -355,6 +400,262 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ================================================================================================================
+// attn2: the same math with NO dedicated producer / MMA warps.
+//
+// ncu on attn_kernel<64,64> (profiles/r01_ncu_attn_*): 65 % of issue slots busy, a third of all executed instructions
+// were the mbarrier try_wait / BRA / YIELD loops of the waiting producer and MMA warps, and every KV tile paid two
+// barrier hand-offs (softmax -> MMA warp -> softmax). Here a CTA is just the four softmax warps (128 threads = the 128
+// query rows): after a tile's P is in shared memory the CTA meets at one bar.sync and thread 0 issues P.V for this
+// tile and Q.K^T for the next (8-24 tcgen05.mma + one commit); at the top of a tile, when S has arrived, the same
+// thread issues the TMA loads for the next K and the current V -- their buffers are provably free because the tensor
+// pipe retires MMAs in order. Nobody spins except on the one barrier that is the true dependency (S ready).
+// 128 threads per CTA also lift the register cap to 128, so a whole 64-column score row stays in registers: one TMEM
+// read per tile, exact row max before the exponentials, lazy rescale (> 2^8) as before.
+template <int HD_PAD>
+struct Attn2Cfg {
+  static constexpr int BKV = 64;
+  static constexpr int KCH = HD_PAD / 64;
+  static constexpr int Q_BYTES = 128 * HD_PAD * 2;
+  static constexpr int KV_BYTES = BKV * HD_PAD * 2;
+  static constexpr int P_BYTES = 128 * BKV * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int TMEM_S = 0;
+  static constexpr int TMEM_O = BKV;
+  static constexpr int TMEM_COLS = BKV + HD_PAD <= 128 ? 128 : 256;
+  static constexpr int CTAS_PER_SM = HD_PAD == 64 ? 4 : HD_PAD == 128 ? 2 : 1;
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "smem for the intended occupancy");
+  static_assert(CTAS_PER_SM * TMEM_COLS <= 512, "TMEM for the intended occupancy");
+};
+
+struct Attn2Bars {
+  uint64_t q_full, k_full, v_full, s_full;
+  uint32_t tmem_ptr;
+};
+
+template <int HD_PAD>
+__global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kernel(const __grid_constant__ AttnParams p) {
+  using C = Attn2Cfg<HD_PAD>;
+  constexpr int BKV = C::BKV;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Attn2Bars* bars = reinterpret_cast<Attn2Bars*>(smem + C::OFF_BAR);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int kv_len = p.kv_lens ? p.kv_lens[b] : p.Lk;
+  int n_tiles = (kv_len + BKV - 1) / BKV;
+  if (p.causal) {
+    const int last_visible = min(kv_len - 1, q0 + 127 + p.causal_offset);
+    n_tiles = min(n_tiles, last_visible / BKV + 1);
+  }
+  if (n_tiles < 1) n_tiles = 1;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tma_q);
+    tma_prefetch_desc(&p.tma_k);
+    tma_prefetch_desc(&p.tma_v);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->k_full, 1);
+    mbar_init(&bars->v_full, 1);
+    mbar_init(&bars->s_full, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(&bars->tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+  const int col0 = head * HD_PAD;
+  const bool bf16 = p.in_dtype == DT_BF16;
+  const uint32_t idesc_s = make_idesc_f16(128, BKV, bf16, false);
+  const uint32_t idesc_o = make_idesc_f16(128, HD_PAD, bf16, true);  // B = V, MN-major
+  const uint32_t sq = smem_u32(smem + C::OFF_Q), sk = smem_u32(smem + C::OFF_K), sv = smem_u32(smem + C::OFF_V),
+                 spa = smem_u32(smem + C::OFF_P);
+
+  // ---- issue helpers (thread 0 only)
+  auto load_kv = [&](int j, bool is_v) {
+    uint64_t* bar = is_v ? &bars->v_full : &bars->k_full;
+    mbar_arrive_expect_tx(bar, C::KV_BYTES);
+#pragma unroll
+    for (int c = 0; c < C::KCH; ++c)
+      tma_load_3d(smem + (is_v ? C::OFF_V : C::OFF_K) + c * (BKV * 128), is_v ? &p.tma_v : &p.tma_k, bar, col0 + c * 64,
+                  j * BKV, b);
+  };
+  auto mma_s = [&]() {
+#pragma unroll
+    for (int k = 0; k < HD_PAD / 16; ++k) {
+      const int c = k >> 2, kk = k & 3;
+      umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + c * (128 * 128) + kk * 32, 16, 1024),
+               make_smem_desc_sw128(sk + c * (BKV * 128) + kk * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+    }
+  };
+  auto mma_pv = [&](int j) {
+#pragma unroll
+    for (int k = 0; k < BKV / 16; ++k)
+      umma_f16(tmem_base + C::TMEM_O, make_smem_desc_sw128(spa + k * 32, 16, 1024),
+               make_smem_desc_sw128(sv + k * (16 * 128), BKV * 128, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
+  };
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
+#pragma unroll
+    for (int c = 0; c < C::KCH; ++c)
+      tma_load_3d(smem + C::OFF_Q + c * (128 * 128), &p.tma_q, &bars->q_full, col0 + c * 64, q0, b);
+    load_kv(0, false);
+    load_kv(0, true);
+    mbar_wait(&bars->q_full, 0);
+    mbar_wait(&bars->k_full, 0);
+    tc_fence_after();
+    mma_s();
+    umma_commit(&bars->s_full);
+  }
+  __syncwarp();
+
+  // ---- softmax: thread <-> query row
+  const int r = tid;
+  const int qrow = q0 + r;
+  const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t ts = tmem_base + C::TMEM_S + lane_off;
+  const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+  uint8_t* sp = smem + C::OFF_P;
+  float m_used = 0.f, l = 0.f;
+  const bool use_ones = p.ones_col >= 0;
+  const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
+
+  for (int j = 0; j < n_tiles; ++j) {
+    mbar_wait(&bars->s_full, j & 1);
+    tc_fence_after();
+    if (tid == 0) {
+      if (j + 1 < n_tiles) load_kv(j + 1, false);  // K buffer is free: S_j has retired
+      if (j > 0) load_kv(j, true);                 // V buffer is free: P.V_{j-1} retired before S_j
+    }
+    __syncwarp();
+    const int kv0 = j * BKV;
+    const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
+    const bool no_mask = __all_sync(0xffffffffu, lim >= BKV - 1);
+    uint32_t s0[32], s1[32];
+    tmem_ld_32x32b_x32(ts, s0);
+    tmem_ld_32x32b_x32(ts + 32, s1);
+    tmem_wait_ld();
+    float mx = no_mask ? fmaxf(attn_max32<false>(s0, 0, lim), attn_max32<false>(s1, 32, lim))
+                       : fmaxf(attn_max32<true>(s0, 0, lim), attn_max32<true>(s1, 32, lim));
+    mx *= p.scale_log2;
+    // lazy rescale decision (warp-uniform branch because tcgen05.ld/st are .sync.aligned)
+    float alpha = 1.f;
+    bool need = false;
+    if (j == 0) {
+      m_used = mx == -INFINITY ? 0.f : mx;
+    } else if (mx > m_used + 8.f) {
+      alpha = fast_exp2(m_used - mx);
+      m_used = mx;
+      need = true;
+    }
+    if (__any_sync(0xffffffffu, need)) {  // O is quiescent: P.V_{j-1} retired before S_j
+      l *= alpha;
+#pragma unroll 1
+      for (int c = 0; c < HD_PAD; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(to + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st_32x32b_x16(to + c, v);
+      }
+      tmem_wait_st();
+    }
+    // p = exp2(s*scale - m) -> P tile in smem (K-major SW128: 16-B unit u of row r lands at u ^ (r & 7))
+    uint8_t* prow = sp + r * 128;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t(&sh)[32] = h == 0 ? s0 : s1;
+      uint32_t pk[16];
+      float part;
+      if (no_mask) {
+        if (use_ones) part = bf16 ? attn_exp32<false, false, true>(sh, 32 * h, lim, p.scale_log2, m_used, pk)
+                                  : attn_exp32<false, false, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
+        else part = bf16 ? attn_exp32<false, true, true>(sh, 32 * h, lim, p.scale_log2, m_used, pk)
+                         : attn_exp32<false, true, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
+      } else {
+        part = bf16 ? attn_exp32<true, true, true>(sh, 32 * h, lim, p.scale_log2, m_used, pk)
+                    : attn_exp32<true, true, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
+      }
+      l += part;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int phys = (4 * h + u) ^ (r & 7);
+        *reinterpret_cast<uint4*>(prow + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(&bars->v_full, j & 1);
+      tc_fence_after();
+      mma_pv(j);
+      if (j + 1 < n_tiles) {
+        mbar_wait(&bars->k_full, (j + 1) & 1);
+        tc_fence_after();
+        mma_s();
+      }
+      umma_commit(&bars->s_full);  // completion #(j+1): S_{j+1} ready, or (last tile) O final
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue: O / l
+  mbar_wait(&bars->s_full, n_tiles & 1);
+  tc_fence_after();
+  if (use_ones) {
+    l = __uint_as_float(tmem_ld_32x32b_x1(to + p.ones_col));
+    tmem_wait_ld();
+  }
+  const float inv = 1.f / l;
+  uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
+                   static_cast<long long>(qrow) * p.ldo + col0;
+#pragma unroll 1
+  for (int c = 0; c < HD_PAD; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(to + c, v);
+    tmem_wait_ld();
+    if (qrow < p.Lq) {
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * inv;
+      store16(orow + c, f, 16, p.out_dtype);
+      store16(orow + c + 16, f + 16, 16, p.out_dtype);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int HD_PAD>
+static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
+  using C = Attn2Cfg<HD_PAD>;
+  static bool configured = false;
+  if (!configured) {
+    GB_CUDA(cudaFuncSetAttribute(attn2_kernel<HD_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((p.Lq + 127) / 128, p.H, p.B);
+  attn2_kernel<HD_PAD><<<grid, 128, C::SMEM_BYTES, stream>>>(p);
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int HD_PAD, int BLOCK_KV>
@@ -387,7 +688,13 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   GB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "row strides %% 8");
   GB_CHECK_ARG(a->q_bstride % 8 == 0 && a->k_bstride % 8 == 0 && a->v_bstride % 8 == 0, "batch strides %% 8");
   const bool bf16 = a->dtype == DT_BF16;
-  const int bkv = a->hd_pad == 128 ? 128 : 64;
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("GILLB200_ATTN");  // A/B aid. "1": warp-specialised attn_kernel for every head size;
+    impl = e ? atoi(e) : 0;                   //          "2": 4-warp attn2 for every head size
+  }
+  const bool use_attn2 = impl == 2 || (impl != 1 && a->hd_pad == 64);
+  const int bkv = (!use_attn2 && a->hd_pad == 128) ? 128 : 64;  // K/V TMA box rows = the kernel's KV tile
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const uint64_t cols = (uint64_t)a->H * a->hd_pad;
@@ -422,6 +729,11 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   p.in_dtype = a->dtype;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ones_col = (a->ones_col > 0 && a->ones_col < a->hd_pad) ? a->ones_col : -1;
+  if (use_attn2) {
+    if (a->hd_pad == 64) return launch_attn2<64>(p, stream);
+    if (a->hd_pad == 128) return launch_attn2<128>(p, stream);
+    return launch_attn2<192>(p, stream);
+  }
   if (a->hd_pad == 64) return launch_attn<64, 64>(p, stream);
   if (a->hd_pad == 128) return launch_attn<128, 128>(p, stream);
   return launch_attn<192, 64>(p, stream);

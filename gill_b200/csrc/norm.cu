@@ -133,6 +133,74 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__
   }
 }
 
+// Narrow rows (C <= 1280): LPR lanes per row, 32/LPR rows per warp, every lane keeps its <= MAXV 16-byte vectors in
+// registers, so one warp has 32*MAXV independent loads in flight (the one-warp-per-row form above leaves most lanes
+// idle at C = 320 and reached ~2 TB/s). Sub-warp xor-shuffle reductions, two-pass variance.
+template <int LPR, int MAXV>
+__global__ void __launch_bounds__(128) layernorm_sub_kernel(const void* __restrict__ x, long long ldx, int in_dtype,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            float eps, int rows, int C, void* __restrict__ out,
+                                                            long long ldo, int out_dtype, void* __restrict__ out_lo) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = (blockIdx.x * 4 + warp) * RPW + lane / LPR;
+  const int t = lane % LPR;
+  const int nvec = C >> 3;
+  const bool active = row < rows;
+  Vec8 buf[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = t + i * LPR;
+    if (active && v < nvec) buf[i] = load8(x, static_cast<long long>(row) * ldx + v * 8, in_dtype);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (active && t + i * LPR < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += buf[i].v[j];
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (active && t + i * LPR < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = buf[i].v[j] - mean;
+        q += d * d;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int v = t + i * LPR;
+    if (active && v < nvec) {
+      Vec8 o;
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + v * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + v * 8 + 4));
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = (buf[i].v[j] - mean) * rstd * ww[j] + bb[j];
+      const long long off = static_cast<long long>(row) * ldo + v * 8;
+      store8(out, off, o, out_dtype);
+      if (out_lo) {
+        Vec8 lo;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lo.v[j] = o.v[j] - __bfloat162float(__float2bfloat16_rn(o.v[j]));
+        store8(out_lo, off, lo, DT_BF16);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm
 // NHWC input, optionally the channel-concatenation of two tensors (UNet up blocks: cat([h, skip])).
 // Pass 1: grid (chunks, B): per-channel partial sums over a pixel chunk -> per-group (sum, sumsq) partials.
@@ -413,9 +481,15 @@ extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, co
   GB_CHECK_ARG(C % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "layernorm needs C, ldx, ldo multiples of 8");
   GB_CHECK_ARG(C <= 5120, "layernorm supports C <= 5120 (got %d)", C);
   GB_CHECK_ARG(!out_lo || out_dtype == DT_BF16, "out_lo requires bf16 output");
-  if (C <= 1280) {
-    layernorm_kernel<1, 5><<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
-                                                                out_dtype, out_lo);
+  if (C <= 320) {
+    layernorm_sub_kernel<8, 5><<<(rows + 15) / 16, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                     out_dtype, out_lo);
+  } else if (C <= 640) {
+    layernorm_sub_kernel<16, 5><<<(rows + 7) / 8, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                    out_dtype, out_lo);
+  } else if (C <= 1280) {
+    layernorm_sub_kernel<32, 5><<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                    out_dtype, out_lo);
   } else {
     layernorm_kernel<4, 5><<<rows, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
                                                       out_lo);

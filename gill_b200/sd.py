@@ -312,7 +312,10 @@ class UNetB200:
         h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"])
         # self attention
         n1 = ops.layernorm(h, w[t + ".norm1.weight"], w[t + ".norm1.bias"], 1e-5)
-        oc = 0  # ones-column / packed-exp2 mode measured 12% slower on B200 (f16x2 ex2 runs at half rate): not used
+        # V carries 1.0 in the first padding column of each head, so the P.V accumulator's column `hd` IS the softmax
+        # denominator: the kernel skips the 64 row-sum FADDs per KV tile (fp32 exp2 kept; the packed f16x2 ex2 variant
+        # measured slower on B200)
+        oc = hd if hp > hd else 0
         qkv = ops.gemm(n1, w[t + ".attn1.qkv"], bias=w[t + ".attn1.qkv_bias"]).view(B, L, 3 * Hh * hp)
         a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
                           hd ** -0.5, ones_col=oc)

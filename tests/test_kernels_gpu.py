@@ -118,7 +118,8 @@ def test_conv_helpers(ops):
     assert torch.equal(up, F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1))
 
 
-@pytest.mark.parametrize("C,dt", [(320, torch.float16), (512, torch.float32), (1280, torch.float16), (4096, torch.float32)])
+@pytest.mark.parametrize("C,dt", [(320, torch.float16), (200, torch.float16), (512, torch.float32), (640, torch.float16),
+                                  (1280, torch.float16), (4096, torch.float32)])
 def test_layernorm(ops, C, dt):
     torch.manual_seed(6)
     x = torch.randn(301, C, device=dev).to(dt)
@@ -238,6 +239,32 @@ def test_fused_attention(ops, case):
         ref1 = attn_ref(q, k, v1, H, hp, hd ** -0.5, causal)
         assert torch.isfinite(got1.float()).all() and rel(got1, ref1) < tol
         assert (got1.view(B, Lq, H, hp)[..., hd].float() - 1).abs().max() < 2e-3
+
+
+@pytest.mark.parametrize("hd,hp,dt", [(40, 64, torch.float16), (80, 128, torch.float16), (128, 128, torch.bfloat16)])
+def test_fused_attention_growing_max(ops, hd, hp, dt):
+    """Key norms grow along the sequence, so the running row max rises by far more than the lazy-rescale threshold
+    (2^8) several times: exercises the single-pass softmax's redo + O-rescale path."""
+    torch.manual_seed(13)
+    B, H, L = 2, 4, 1024
+
+    def mk(scale_rows=None):
+        t = torch.zeros(B, L, H, hp, device=dev)
+        x = torch.randn(B, L, H, hd, device=dev)
+        if scale_rows is not None:
+            x = x * scale_rows.view(1, L, 1, 1)
+        t[..., :hd] = x
+        return t
+
+    q, k, v = mk(), mk(torch.linspace(0.05, 12.0, L, device=dev)), mk()
+    oc = 0
+    if hp > hd and dt == torch.float16:
+        v[..., hd] = 1.0
+        oc = hd
+    q, k, v = (t.view(B, L, H * hp).to(dt) for t in (q, k, v))
+    got = ops.attention(q, k, v, H, hp, hd ** -0.5, ones_col=oc)
+    ref = attn_ref(q, k, v, H, hp, hd ** -0.5)
+    assert torch.isfinite(got.float()).all() and rel(got, ref) < (1e-2 if dt == torch.bfloat16 else 3e-3)
 
 
 def test_fused_attention_kv_lens_and_views(ops):
