@@ -38,6 +38,8 @@ class GemmArgs(ctypes.Structure):
         ("block_n", _c_int),
         ("tile_order", _c_int),
         ("cta_pair", _c_int),
+        ("sk_workspace", _c_void_p),
+        ("stream_k", _c_int),
     ]
 
 
@@ -68,6 +70,7 @@ def _declare(L):
     L.gillb200_num_sms.restype = _c_int
     L.gillb200_gemm.argtypes = [ctypes.POINTER(GemmArgs), _c_void_p]
     L.gillb200_gemm.restype = _c_int
+    L.gillb200_gemm_streamk_workspace_bytes.restype = _c_ll
     from . import _lib_decl
 
     _lib_decl.declare(L)

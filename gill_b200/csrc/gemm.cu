@@ -107,7 +107,13 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (p.sk_per > 0) {  // stream-K: every SM gets an equal share of the (tile, k-block) units
+    const long long total = 1LL * tiles * p.num_k_blocks;
+    grid = num_sms();
+    p.sk_per = static_cast<int>((total + grid - 1) / grid);
+    grid = static_cast<int>((total + p.sk_per - 1) / p.sk_per);
+  }
   gemm_kernel<BN><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -168,6 +174,12 @@ extern "C" int gillb200_version(void) { return GILLB200_VERSION; }
 extern "C" const char* gillb200_last_error(void) { return gb::err_buf(); }
 extern "C" int gillb200_num_sms(void) { return gb::num_sms(); }
 extern "C" long long gillb200_launch_count(void) { return gb::g_launch_count; }
+
+// stream-K scratch: [sms x GEMM_EPI_WARPS] arrival flags (padded to 16 KB), then one 128 x 256 fp32 partial tile per SM
+static constexpr long long SK_FLAG_BYTES = 16384;
+extern "C" long long gillb200_gemm_streamk_workspace_bytes(void) {
+  return SK_FLAG_BYTES + 1LL * gb::num_sms() * BLOCK_M * 256 * sizeof(float);
+}
 
 extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -254,10 +266,25 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   }
   // CTA-pair (cta_group::2) kernel: 256 x bn tiles, each CTA loads half of the B tile. Used when there are enough
   // 256-row tiles to keep every SM pair busy; small problems keep the 1-CTA kernel (more, smaller tiles).
+  // Stream-K candidate (decided first, it needs the 1-CTA kernel): implicit-conv shapes whose whole-tile schedule
+  // would leave most of the last wave empty (UNet 16x16 / 8x8 levels: 160 / 40 tiles on 148 SMs). Measured
+  // (tools/gpu_sweep_shapes.py): 16x16 C1280 150 -> 111 us, 8x8 C2560 149 -> 102 us; plain short-K linears lose
+  // (the fix-up costs more than the idle SMs), so auto mode is limited to convolutions.
+  bool want_sk = false;
+  if (a->sk_workspace && a->stream_k != 1 && a->tile_order != 2 && a->cta_pair != 2) {
+    if (a->stream_k == 2) {
+      want_sk = true;
+    } else if (a->conv3x3 && a->out_dtype != DT_F32 && p.num_k_blocks >= 16) {
+      if (!a->block_n && a->N % 256 == 0) bn = 256;  // tile quantisation no longer matters: widest tile
+      const long long tiles = 1LL * ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + bn - 1) / bn);
+      const long long waves = (tiles + num_sms() - 1) / num_sms();
+      want_sk = static_cast<double>(tiles) / static_cast<double>(waves * num_sms()) < 0.8;
+    }
+  }
   bool pair = false;
   if (a->cta_pair == 2) {
     pair = true;
-  } else if (a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
+  } else if (!want_sk && a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
     // measured: the pair kernel wins (+3..17 %) only when the K loop is long enough to amortise the cluster
     // handshakes, and loses on short-K, epilogue-heavy shapes
     const long long tiles2 = 1LL * ((a->M + 255) / 256) * ((a->N + bn - 1) / bn);
@@ -350,14 +377,29 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
       p.epi_nbuf = a->residual ? 3 : 2;
       p.epi_buf_bytes = 32 * EPI_PANEL_COLS * esz;
       // as many epilogue warps as leave a >= 3-deep operand ring (fp32 panels are twice as large)
-      // measured (tools/gpu_sweep_shapes.py): 8 warps + a deeper operand ring win everywhere except the erf-heavy
-      // GEGLU epilogue, which wants all 16
-      p.epi_warps = a->act == ACT_GEGLU ? 16 : 8;
+      // measured (tools/gpu_sweep_shapes.py): 8 warps + a deeper operand ring beat 16 warps on every plain shape
+      p.epi_warps = GEMM_EPI_WARPS;
       if (a->residual ? env_warps_res : env_warps) p.epi_warps = a->residual ? env_warps_res : env_warps;
+      if (p.epi_warps > GEMM_EPI_WARPS) p.epi_warps = GEMM_EPI_WARPS;
       const int stage_bytes = (BLOCK_M + (pair ? bn / 2 : bn)) * BLOCK_K * 2;
       while (p.epi_warps > 4 &&
              (SMEM_BUDGET - 2048 - p.epi_warps * p.epi_nbuf * p.epi_buf_bytes) / stage_bytes < 3)
         p.epi_warps -= 4;
+    }
+  }
+
+  // ---- stream-K (see want_sk above): only the 1-CTA kernel with the staged epilogue
+  if (want_sk && !pair && p.epi_tma) {
+    const long long tiles = 1LL * ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + bn - 1) / bn);
+    const int sms = num_sms();
+    const long long total = tiles * p.num_k_blocks;
+    const bool fits = bn <= 256 && total < (1LL << 30) && (total + sms - 1) / sms >= 4 &&
+                      p.num_k_blocks <= 8 * ((total + sms - 1) / sms);  // <= ~9 partials per tile
+    if (fits) {
+      p.sk_per = 1;  // finalised (units per CTA) by launch_gemm
+      p.sk_flags = reinterpret_cast<int*>(a->sk_workspace);
+      p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->sk_workspace) + SK_FLAG_BYTES);
+      p.tile_order = 1;  // m-fastest: neighbouring CTAs share weight tiles
     }
   }
 

@@ -165,7 +165,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     if (p.epi_tma) {
       if (warp - 4 < p.epi_warps) {
         epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE>(
-            p, bars, epi_stage, tmem_base, pair, num_tiles, num_pairs,
+            p, bars, epi_stage, tmem_base, SegIter{p.num_k_blocks, pair, num_pairs, num_tiles, 0, 0},
             [&](int tile, int* row_base, int* n0) {
               *row_base = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
               *n0 = (tile / num_m2) * BLOCK_N;

@@ -24,7 +24,7 @@ namespace gb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_EPI_WARPS = 16;  // 4 per SM sub-partition: the CUDA-core epilogue needs the latency hiding
+constexpr int GEMM_EPI_WARPS = 8;  // 2 per SM sub-partition; 384 threads leave 168 registers per thread (16 warps capped it at 96: spills)
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warps 0-3: producer / MMA / TMEM alloc / spare
 constexpr int SMEM_BUDGET = 227 * 1024;
 
@@ -68,6 +68,13 @@ struct alignas(64) GemmParams {
   int epi_nbuf;       // staging buffers per warp: 2, or 3 with a residual
   int epi_buf_bytes;  // 2048 (16-bit output) or 4096 (fp32 output)
   int num_stages;     // smem ring depth actually used (<= GemmCfg::STAGES)
+  // stream-K (sk_per > 0, 1-CTA kernel + staged epilogue only): the tiles' k-blocks form one linear range of
+  // num_tiles * num_k_blocks units and CTA c owns units [c * sk_per, (c + 1) * sk_per). A tile cut by a CTA boundary
+  // is finished by the CTA that owns its first k-block; the others park fp32 partial accumulators in sk_ws[cta] and
+  // raise sk_flags[cta][epilogue warp].
+  int sk_per;
+  float* sk_ws;
+  int* sk_flags;
   int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
@@ -111,13 +118,60 @@ __device__ __forceinline__ TileCoord tile_coord(int tile, int num_m) {
   return {tile / num_n, tile % num_n};
 }
 
+// One unit of work for a CTA: k-blocks [kb0, kb1) of `tile`. Plain persistent scheduling hands out whole tiles
+// (tile = first, first + step, ...); stream-K hands out one contiguous range of (tile, k-block) units per CTA.
+struct Seg {
+  int tile, kb0, kb1;
+};
+struct SegIter {
+  int kb_per_tile;
+  int tile, step, end;  // whole-tile mode
+  int u, u1;            // stream-K mode (u1 > 0)
+  __device__ __forceinline__ bool next(Seg& sg) {
+    if (u1 == 0) {
+      if (tile >= end) return false;
+      sg.tile = tile;
+      sg.kb0 = 0;
+      sg.kb1 = kb_per_tile;
+      tile += step;
+      return true;
+    }
+    if (u >= u1) return false;
+    sg.tile = u / kb_per_tile;
+    sg.kb0 = u - sg.tile * kb_per_tile;
+    const int len = min(kb_per_tile - sg.kb0, u1 - u);
+    sg.kb1 = sg.kb0 + len;
+    u += len;
+    return true;
+  }
+};
+__device__ __forceinline__ SegIter make_seg_iter(const GemmParams& p, int num_tiles, int first, int step) {
+  SegIter it;
+  it.kb_per_tile = p.num_k_blocks;
+  it.tile = first;
+  it.step = step;
+  it.end = num_tiles;
+  it.u = 0;
+  it.u1 = 0;
+  if (p.sk_per > 0) {
+    const int total = num_tiles * p.num_k_blocks;
+    it.u = min(total, static_cast<int>(blockIdx.x) * p.sk_per);
+    it.u1 = min(total, it.u + p.sk_per);
+    if (it.u1 == 0) it.u1 = -1, it.u = 0;  // (cannot happen: total > 0) keep stream-K mode distinguishable
+  }
+  return it;
+}
+
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
-                                              int num_m, int tile_begin, int tile_end, int tile_step) {
+                                              int num_m, SegIter it) {
   using C = GemmCfg<BLOCK_N>;
   int stage = 0;
   uint32_t phase = 0;
-  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+  const int tile_begin = it.tile;
+  Seg sg;
+  while (it.next(sg)) {
+    const int tile = sg.tile;
     const TileCoord tc = tile_coord(tile, num_m);
     const int m0 = tc.m_blk * BLOCK_M;
     const int n0 = tc.n_blk * BLOCK_N;
@@ -128,7 +182,7 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
       cy0 = (m0 % per_img) / p.conv_W;
       cx0 = m0 % p.conv_W;  // non-zero only when W > 128 (a tile is then a 128-pixel row segment)
     }
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+    for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
       // The whole warp runs this loop (warp-uniform control flow) and one elected lane issues: with a single
       // divergent lane the compiler has to wrap every UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop and shuttle
       // operands through R2UR, which made the issue loop ~430 cycles per k-block (measured, profiles/).
@@ -170,18 +224,19 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
                                          uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
-                                         int tile_begin, int tile_end, int tile_step) {
+                                         SegIter it) {
   using C = GemmCfg<BLOCK_N>;
   const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+  Seg sg;
+  while (it.next(sg)) {
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+    for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       const uint32_t sa = smem_u32(smem_tiles + stage * C::STAGE_BYTES);
@@ -193,7 +248,7 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - sg.kb0) | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
@@ -550,8 +605,7 @@ static_assert(sizeof(GemmSmemBars) <= 1024, "barrier block");
 // -> tcgen05.ld -> math -> swizzled st.shared -> fence.proxy.async -> [lane 0: TMA store].
 template <int BLOCK_N, int ACC_STRIDE, int VAR, typename TileFn, typename Release>
 __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemBars* bars, uint8_t* epi_stage,
-                                                  uint32_t tmem_base, int tile_begin, int tile_end, int tile_step,
-                                                  TileFn tile_fn, Release release_fn) {
+                                                  uint32_t tmem_base, SegIter it, TileFn tile_fn, Release release_fn) {
   const int warp = threadIdx.x >> 5;
   const int ew = warp - 4, quad = warp & 3;
   const int cgrp = ew >> 2, ngrp = p.epi_warps >> 2;
@@ -573,10 +627,20 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
   int acc = 0;
   uint32_t acc_phase = 0;
 
-  for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+  Seg sg;
+  while (it.next(sg)) {
+    const int tile = sg.tile;
     int row_base, n0;
     tile_fn(tile, &row_base, &n0);
     const int row0 = row_base + quad * 32;
+    // stream-K: a tile cut by a CTA boundary. The owner of k-block 0 finishes it; everyone else parks partials.
+    const bool sk_partial = sg.kb0 > 0;
+    const bool sk_reduce = sg.kb0 == 0 && sg.kb1 < it.kb_per_tile;
+    int sk_first = 0, sk_last = -1;  // CTAs whose partials this (finishing) CTA adds
+    if (sk_reduce) {
+      sk_first = static_cast<int>(blockIdx.x) + 1;
+      sk_last = ((tile + 1) * it.kb_per_tile - 1) / p.sk_per;
+    }
     const int no0 = geglu ? n0 >> 1 : n0;
     const uint32_t taddr = tmem_base + acc * ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
     // panels entirely beyond N (last N tile) or a slab entirely beyond M produce nothing
@@ -590,13 +654,74 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       mbar_arrive_expect_tx(&res_bar[b], panel_bytes);
       tma_load_2d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, row0);
     };
-    if (has_res && pb0 < pe && lane == 0) {  // the first residual panel travels while the tile's MMAs finish
+    if (has_res && pb0 < pe && !sk_partial && lane == 0) {  // first residual panel travels while the MMAs finish
       tma_store_wait_read<1>();
       fetch_res(pb0, buf);
     }
     mbar_wait(&bars->tmem_full[acc], acc_phase);
     tc_fence_after();
     if (pb0 >= pe) release_fn(acc);
+
+    if (sk_partial) {
+      // park this warp's share of the fp32 accumulators: sk_ws[cta][row 0..127][col 0..BLOCK_N), one 128-byte line per
+      // lane and 32-column chunk; then raise this warp's flag (the finisher's warp with the same index consumes it)
+      float* ws = p.sk_ws + (static_cast<size_t>(blockIdx.x) * BLOCK_M + quad * 32 + lane) * BLOCK_N;
+      for (int pnl = pb0; pnl < pe; ++pnl) {
+        const int halves = geglu ? 2 : 1;
+#pragma unroll 1
+        for (int h = 0; h < halves; ++h) {
+          const int acol = pnl * acc_per_panel + h * 32;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + acol, r);
+          tmem_wait_ld();
+          if (pnl == pe - 1 && h == halves - 1) release_fn(acc);
+          float4* dst = reinterpret_cast<float4*>(ws + acol);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                        __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+        }
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        int* flag = p.sk_flags + static_cast<size_t>(blockIdx.x) * GEMM_EPI_WARPS + ew;
+        asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+      continue;
+    }
+    if (sk_reduce && pb0 < pe) {
+      // wait (once per tile) until the same-index warp of every contributing CTA has parked its partials
+      if (lane == 0) {
+        for (int c = sk_first; c <= sk_last; ++c) {
+          const int* flag = p.sk_flags + static_cast<size_t>(c) * GEMM_EPI_WARPS + ew;
+          int v;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          } while (v == 0);
+        }
+      }
+      __syncwarp();
+    }
+    // adds the parked partials of accumulator columns [acol, acol + 32) of this lane's row, in CTA order
+    auto sk_add = [&](uint32_t (&r)[32], int acol) {
+      for (int c = sk_first; c <= sk_last; ++c) {
+        const float4* src = reinterpret_cast<const float4*>(
+            p.sk_ws + (static_cast<size_t>(c) * BLOCK_M + quad * 32 + lane) * BLOCK_N + acol);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldcg(src + i);
+          r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + t.x);
+          r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + t.y);
+          r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + t.z);
+          r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + t.w);
+        }
+      }
+    };
 
     for (int pnl = pb0; pnl < pe; ++pnl) {
       uint8_t* sbuf = stage + buf * panel_bytes;
@@ -619,6 +744,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           tmem_ld_32x32b_x32(taddr + acol, r);
           tmem_wait_ld();
           if (last && h == halves - 1) release_fn(acc);
+          if (sk_reduce) sk_add(r, acol);
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             float v[16];
@@ -639,6 +765,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           tmem_ld_32x32b_x32(taddr + pnl * 64 + h * 32, r);
           tmem_wait_ld();
           if (last && h == 1) release_fn(acc);
+          if (sk_reduce) sk_add(r, pnl * 64 + h * 32);
           float f[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {  // (value, gate) pairs are interleaved along N
@@ -667,6 +794,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         tmem_ld_32x32b_x32(taddr + pnl * 32, r);
         tmem_wait_ld();
         if (last) release_fn(acc);
+        if (sk_reduce) sk_add(r, pnl * 32);
         float f[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -688,6 +816,11 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       par ^= 1u << buf;
       buf = nxt;
     }
+    if (sk_reduce && pb0 < pe) {  // consumed: re-arm the flags for the next launch (this warp is their only reader)
+      __syncwarp();
+      if (lane == 0)
+        for (int c = sk_first; c <= sk_last; ++c) p.sk_flags[static_cast<size_t>(c) * GEMM_EPI_WARPS + ew] = 0;
+    }
     if (++acc == 2) {
       acc = 0;
       acc_phase ^= 1;
@@ -699,29 +832,24 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
 // Runtime -> compile-time variant dispatch (once per warp, outside the tile loop).
 template <int BLOCK_N, int ACC_STRIDE, typename TileFn, typename Release>
 __device__ __forceinline__ void epilogue_warp_tma_dispatch(const GemmParams& p, GemmSmemBars* bars, uint8_t* epi_stage,
-                                                           uint32_t tmem_base, int tile_begin, int tile_end,
-                                                           int tile_step, TileFn tile_fn, Release release_fn) {
+                                                           uint32_t tmem_base, SegIter it, TileFn tile_fn,
+                                                           Release release_fn) {
   switch (p.epi_variant) {
     case EV_BIAS:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS>(p, bars, epi_stage, tmem_base, tile_begin, tile_end, tile_step,
-                                                       tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_BIAS_RES:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_RES>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
-                                                           tile_step, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_RES>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_BIAS_ROWBIAS:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_ROWBIAS>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
-                                                               tile_step, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_ROWBIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_GEGLU:
       if constexpr (BLOCK_N % 64 == 0)
-        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GEGLU>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
-                                                          tile_step, tile_fn, release_fn);
+        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GEGLU>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     default:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GENERIC>(p, bars, epi_stage, tmem_base, tile_begin, tile_end,
-                                                          tile_step, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GENERIC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
   }
 }
 
@@ -773,17 +901,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
 
   const bool n_inner = p.tile_order == 2 || (p.tile_order == 0 && num_n <= 4 && num_m >= 2 * static_cast<int>(gridDim.x));
   const int order = n_inner ? -num_n : num_m;  // see tile_coord()
+  const SegIter seg_it = make_seg_iter(p, num_tiles, blockIdx.x, gridDim.x);
   if (warp == 0) {
-    gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, order, blockIdx.x, num_tiles, gridDim.x);
+    gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, order, seg_it);
   } else if (warp == 1) {
-    gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
-                      blockIdx.x, num_tiles, gridDim.x);
+    gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base, seg_it);
   } else if (warp >= 4) {
     if (!p.epi_tma) {
       gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, order, num_tiles);
     } else if (warp - 4 < p.epi_warps) {
       epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE>(
-          p, bars, epi_stage, tmem_base, blockIdx.x, num_tiles, gridDim.x,
+          p, bars, epi_stage, tmem_base, seg_it,
           [&](int tile, int* row_base, int* n0) {
             const TileCoord tc = tile_coord(tile, order);
             *row_base = tc.m_blk * BLOCK_M;

@@ -91,10 +91,11 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
   const int tile_begin = n_lo * num_m + m_blk, tile_end = n_hi * num_m, tile_step = num_m;
 
   if (warp == 0) {
-    gemm_producer<TOPK_BN>(p, smem_tiles, bars->full, bars->empty, num_m, tile_begin, tile_end, tile_step);
+    gemm_producer<TOPK_BN>(p, smem_tiles, bars->full, bars->empty, num_m,
+                           SegIter{p.num_k_blocks, tile_begin, tile_step, tile_end, 0, 0});
   } else if (warp == 1) {
     gemm_mma<TOPK_BN>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base,
-                      tile_begin, tile_end, tile_step);
+                      SegIter{p.num_k_blocks, tile_begin, tile_step, tile_end, 0, 0});
   } else if (warp >= 4) {
     // 8 epilogue warps: warps 4..7 scan columns [0,128) of each tile, warps 8..11 scan [128,256); both groups cover
     // all 128 TMEM lanes (a warp may only touch lanes 32*(warp%4) .. +31). Each thread keeps its own top-KMAX.

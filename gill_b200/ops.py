@@ -64,6 +64,20 @@ def _chk2d(t: torch.Tensor, name: str):
         raise ValueError(f"{name} must be 2-D with a contiguous last dim, got shape {tuple(t.shape)} stride {t.stride()}")
 
 
+_sk_ws = {}
+
+
+def _streamk_ws(device: torch.device) -> int:
+    """Per-(device, stream) stream-K scratch (zeroed once: the kernel's arrival flags re-arm themselves). One buffer per
+    stream because two GEMMs running concurrently must not share it."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _sk_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(lib().gillb200_gemm_streamk_workspace_bytes(), device=device, dtype=torch.uint8)
+        _sk_ws[key] = ws
+    return ws.data_ptr()
+
+
 def gemm(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -83,6 +97,7 @@ def gemm(
     block_n: int = 0,
     cta_pair: int = 0,
     tile_order: int = 0,
+    stream_k: int = 0,
 ) -> torch.Tensor:
     """out = act(alpha * a @ b.T + bias + rowbias) + residual     (a: [M,K], b: [N,K], 16-bit; fp32 accumulate).
 
@@ -118,6 +133,9 @@ def gemm(
         _chk2d(residual, "residual")
         g.residual, g.ldr, g.res_dtype = residual.data_ptr(), residual.stride(0), _DT[residual.dtype]
     g.act, g.alpha, g.block_n, g.cta_pair, g.tile_order = _ACT[act], alpha, block_n, cta_pair, tile_order
+    g.stream_k = stream_k
+    if stream_k != 1:
+        g.sk_workspace = _streamk_ws(a.device)
     ktot = K + (g.k2 if a2_mode == 1 else 0)
     with _P("gemm" if a2_mode != 2 else "gemm_split", 2.0 * M * N * ktot * (2 if a2_mode == 2 else 1),
             2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out, f"M{M} N{N} K{ktot} {act or ''}"):
@@ -139,6 +157,7 @@ def conv3x3(
     block_n: int = 0,
     cta_pair: int = 0,
     tile_order: int = 0,
+    stream_k: int = 0,
 ) -> torch.Tensor:
     """3x3 / stride 1 / pad 1 convolution as an implicit GEMM.
 
@@ -175,6 +194,9 @@ def conv3x3(
         r2 = residual.view(B * H * W, N)
         g.residual, g.ldr, g.res_dtype = r2.data_ptr(), r2.stride(0), _DT[residual.dtype]
     g.act, g.alpha, g.block_n, g.cta_pair, g.tile_order = _ACT[act], 1.0, block_n, cta_pair, tile_order
+    g.stream_k = stream_k
+    if stream_k != 1:
+        g.sk_workspace = _streamk_ws(x.device)
     with _P("conv3x3", 2.0 * B * H * W * N * (9 * C + (g.k2 or 0)), 2.0 * (B * H * W * C + N * 9 * C + B * H * W * N),
             f"B{B} {H}x{W} C{C}->{N}"):
         check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")

@@ -79,7 +79,14 @@ typedef struct gillb200_gemm_args {
   int block_n; /* 0 = auto; else one of 32, 64, 128, 160, 256 */
   int tile_order; /* 0 = auto; 1 = M-fastest tile order; 2 = N-inner (all N tiles of an M block back to back) */
   int cta_pair; /* 0 = auto; 1 = force the 1-CTA kernel; 2 = force the CTA-pair (tcgen05 cta_group::2, 256-row tile) kernel */
+  /* optional stream-K scratch: gillb200_gemm_streamk_workspace_bytes() bytes of device memory, ZERO before its first
+   * use (the arrival flags re-arm themselves) and not shared between concurrently running GEMMs. When given, shapes
+   * whose tile count fills the SMs badly (the UNet's 8x8 / 16x16 levels) split their K range evenly over all SMs. */
+  void* sk_workspace;
+  int stream_k; /* 0 = auto (when sk_workspace is given); 1 = never; 2 = always (if the kernel variant supports it) */
 } gillb200_gemm_args;
+
+long long gillb200_gemm_streamk_workspace_bytes(void);
 
 int gillb200_gemm(const gillb200_gemm_args* args, void* stream);
 

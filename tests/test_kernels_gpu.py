@@ -103,6 +103,48 @@ def test_conv3x3_implicit_gemm(ops, case):
     assert rel(got, ref) < 1e-4
 
 
+@pytest.mark.parametrize("case", [(1024, 1280, 5120, 0), (4096, 1280, 1536, 0), (520, 384, 2048, 128), (1024, 10240, 1280, 256)])
+def test_gemm_stream_k(ops, case):
+    """stream_k=2 forces the K range of every tile to be shared between CTAs (fp32 partials through the workspace,
+    finished in a fixed CTA order): same result as whole-tile scheduling up to fp32 summation order, bit-stable."""
+    M, N, K, bn = case
+    torch.manual_seed(20)
+    a = torch.randn(M, K, device=dev).half()
+    b = (torch.randn(N, K, device=dev) * 0.05).half()
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev).half()
+    ref = a.float() @ b.float().T + bias + res.float()
+    plain = ops.gemm(a, b, bias=bias, residual=res, stream_k=1, block_n=bn)
+    sk1 = ops.gemm(a, b, bias=bias, residual=res, stream_k=2, block_n=bn)
+    sk2 = ops.gemm(a, b, bias=bias, residual=res, stream_k=2, block_n=bn)
+    assert rel(sk1, ref) < 1e-3 and rel(plain, ref) < 1e-3 and rel(sk1, plain) < 5e-4
+    assert torch.equal(sk1, sk2)
+    # fp32 output goes through the generic staged epilogue
+    o32 = ops.gemm(a, b, bias=bias, stream_k=2, block_n=bn, out_dtype=torch.float32)
+    assert rel(o32, a.float() @ b.float().T + bias) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(16, 8, 1280, 1280), (4, 16, 640, 1280), (2, 8, 2560, 320)])
+def test_conv3x3_stream_k(ops, case):
+    B, HW, C, Co = case
+    torch.manual_seed(21)
+    x = torch.randn(B, HW, HW, C, device=dev).half()
+    w = (torch.randn(Co, C, 3, 3, device=dev) * 0.02).half()
+    wk = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    bias = torch.randn(Co, device=dev)
+    rb = torch.randn(B, Co, device=dev)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1)
+    for sk in (1, 2, 0):
+        got = ops.conv3x3(x, wk, bias=bias, rowbias=rb, stream_k=sk)
+        assert rel(got, ref) < 1e-3, sk
+    res = torch.randn(B, HW, HW, Co, device=dev).half()
+    got = ops.conv3x3(x, wk, bias=bias, residual=res, stream_k=2)
+    ref2 = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    assert rel(got, ref2) < 1e-3
+    assert torch.equal(got, ops.conv3x3(x, wk, bias=bias, residual=res, stream_k=2))
+
+
 def test_conv_helpers(ops):
     torch.manual_seed(5)
     x = torch.randn(2, 16, 16, 64, device=dev).half()
