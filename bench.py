@@ -247,8 +247,11 @@ def run_ours(args):
     if rank == 0:
         mp = m.gen_text_hidden_fcs[0]
         gx = torch.Generator().manual_seed(1234)
-        x256 = torch.randn(256, 8, 4096, generator=gx).to(torch.bfloat16).to(dev)
-        img_embs = m.input_embeddings(torch.tensor([m.retrieval_token_idx], device=dev))
+        # bf16-rounded inputs held in fp32: the mapper's fp32-output mode (bf16 hi+lo operands) is the one
+        # that meets the <= 1e-3 parity bar; a bf16 input tensor would select the bf16-in/bf16-out drop-in mode whose
+        # output rounding alone is 1.7e-3
+        x256 = torch.randn(256, 8, 4096, generator=gx).to(torch.bfloat16).float().to(dev)
+        img_embs = m.input_embeddings(torch.tensor([m.retrieval_token_idx], device=dev)).float()
         for _ in range(2):
             y = mp(x256, img_embs)
         torch.cuda.synchronize()

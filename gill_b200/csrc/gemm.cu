@@ -40,7 +40,7 @@ static EncodeTiledFn get_encode_fn() {
 
 // dtype: DT_BF16 / DT_F16 / DT_F32. swizzle_bytes: 128, 64 or 32 (the box's inner extent must not exceed it).
 int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(-EIO, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return set_err(-EINVAL, "tensor base %p not 16-byte aligned", base);
@@ -50,7 +50,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const u
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) {
       gstr[i - 1] = strides_bytes[i - 1];
       if (gstr[i - 1] % 16 != 0) return set_err(-EINVAL, "tensor stride %llu B not a multiple of 16", (unsigned long long)gstr[i - 1]);
@@ -70,7 +70,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const u
 
 int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool is_bf16) {
-  return encode_tmap(out, base, is_bf16 ? DT_BF16 : DT_F16, rank, dims, strides_bytes, box, 128);
+  return encode_tmap(out, base, is_bf16 ? DT_BF16 : DT_F16, rank, dims, strides_bytes, box, 128, nullptr);
 }
 
 int num_sms() {
@@ -197,9 +197,12 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   int kb_main;
   if (a->conv3x3) {
     GB_CHECK_ARG(a->conv_C % BLOCK_K == 0, "conv3x3 needs C %% 64 == 0 (C=%d)", a->conv_C);
-    GB_CHECK_ARG(a->M == a->conv_B * a->conv_H * a->conv_W, "conv3x3: M != B*H*W");
+    const int cs = a->conv_stride == 2 ? 2 : 1;
+    GB_CHECK_ARG(a->conv_stride == 0 || a->conv_stride == 1 || a->conv_stride == 2, "conv3x3: stride must be 1 or 2");
+    GB_CHECK_ARG(a->conv_H % cs == 0 && a->conv_W % cs == 0, "conv3x3: H, W must be multiples of the stride");
+    const int W = a->conv_W / cs, H = a->conv_H / cs;  // OUTPUT size: an M tile is a box of output pixels
+    GB_CHECK_ARG(a->M == a->conv_B * H * W, "conv3x3: M != B*Ho*Wo");
     GB_CHECK_ARG(a->K == 9 * a->conv_C, "conv3x3: K != 9*C");
-    const int W = a->conv_W, H = a->conv_H;
     int bw, bh, bb;
     if (W >= 128) {
       GB_CHECK_ARG(W % 128 == 0, "conv3x3: W=%d must be a multiple of 128 when >= 128", W);
@@ -212,11 +215,16 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
       GB_CHECK_ARG(H % bh == 0, "conv3x3: H=%d not a multiple of the box height %d", H, bh);
       bb = 128 / (bw * bh);
     }
-    const uint64_t dims[4] = {(uint64_t)a->conv_C, (uint64_t)W, (uint64_t)H, (uint64_t)a->conv_B};
-    const uint64_t strides[3] = {(uint64_t)a->conv_C * 2, (uint64_t)W * a->conv_C * 2, (uint64_t)H * W * a->conv_C * 2};
-    const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
-    int r = encode_tmap_16bit(&p.tma_a, a->a, 4, dims, strides, box, bf16);
+    GB_CHECK_ARG(bw * cs <= 256 && bh * cs <= 256, "conv3x3: strided box exceeds 256");
+    const uint64_t dims[4] = {(uint64_t)a->conv_C, (uint64_t)a->conv_W, (uint64_t)a->conv_H, (uint64_t)a->conv_B};
+    const uint64_t strides[3] = {(uint64_t)a->conv_C * 2, (uint64_t)a->conv_W * a->conv_C * 2,
+                                 (uint64_t)a->conv_H * a->conv_W * a->conv_C * 2};
+    // with element strides the box is given in input elements: N loaded elements need a box of N * stride
+    const uint32_t box[4] = {64, (uint32_t)(bw * cs), (uint32_t)(bh * cs), (uint32_t)bb};
+    const uint32_t es[4] = {1, (uint32_t)cs, (uint32_t)cs, 1};
+    int r = encode_tmap(&p.tma_a, a->a, bf16 ? DT_BF16 : DT_F16, 4, dims, strides, box, 128, cs == 2 ? es : nullptr);
     if (r) return r;
+    p.conv_stride = cs;
     p.a_mode = A_CONV3X3;
     p.conv_cblocks = a->conv_C / BLOCK_K;
     p.conv_W = W;
@@ -345,11 +353,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
       const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
       const uint32_t box[2] = {EPI_PANEL_COLS, 32};
       const uint64_t so[1] = {(uint64_t)a->ldo * esz};
-      int r = encode_tmap(&p.tma_out, a->out, a->out_dtype, 2, dims, so, box, esz == 4 ? 128 : 64);
+      int r = encode_tmap(&p.tma_out, a->out, a->out_dtype, 2, dims, so, box, esz == 4 ? 128 : 64, nullptr);
       if (r) return r;
       if (a->residual) {
         const uint64_t sr[1] = {(uint64_t)a->ldr * esz};
-        r = encode_tmap(&p.tma_res, a->residual, a->res_dtype, 2, dims, sr, box, esz == 4 ? 128 : 64);
+        r = encode_tmap(&p.tma_res, a->residual, a->res_dtype, 2, dims, sr, box, esz == 4 ? 128 : 64, nullptr);
         if (r) return r;
       }
       p.epi_tma = 1;

@@ -107,7 +107,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
               const int tap = kb / p.conv_cblocks;
               const int cb = kb - tap * p.conv_cblocks;
               const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-              tma2_load_4d(sa, &p.tma_a, full_leader, cb * BLOCK_K, cx0 + dx, cy0 + dy, cb0);
+              tma2_load_4d(sa, &p.tma_a, full_leader, cb * BLOCK_K, p.conv_stride * cx0 + dx, p.conv_stride * cy0 + dy,
+                           cb0);
             } else {
               tma2_load_2d(sa, &p.tma_a, full_leader, kb * BLOCK_K, m0);
             }

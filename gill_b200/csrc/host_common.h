@@ -31,8 +31,9 @@ int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64
                       const uint32_t* box, bool is_bf16);
 
 // general form: dtype 0 = bf16, 1 = fp16, 2 = fp32; swizzle_bytes 128 / 64 / 32
+// elem_strides: optional per-dimension traversal strides (nullptr = all 1)
 int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
-                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+                const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides);
 
 int num_sms();
 

@@ -158,10 +158,11 @@ def conv3x3(
     cta_pair: int = 0,
     tile_order: int = 0,
     stream_k: int = 0,
+    stride: int = 1,
 ) -> torch.Tensor:
-    """3x3 / stride 1 / pad 1 convolution as an implicit GEMM.
+    """3x3 / pad 1 convolution (stride 1 or 2) as an implicit GEMM.
 
-    x: NHWC [B,H,W,C] (C % 64 == 0); w: [Cout, 9*C (+k2)] with k = (ky*3+kx)*C + c; returns NHWC [B,H,W,Cout].
+    x: NHWC [B,H,W,C] (C % 64 == 0); w: [Cout, 9*C (+k2)] with k = (ky*3+kx)*C + c; returns NHWC [B,H/s,W/s,Cout].
     rowbias [B, Cout] is added per sample (time embedding); a2 [B*H*W, k2] K-concatenates a 1x1 shortcut input whose
     weights occupy the trailing k2 columns of w.
     """
@@ -169,11 +170,14 @@ def conv3x3(
     assert x.is_contiguous()
     _chk2d(w, "w")
     N = w.shape[0]
+    assert stride in (1, 2) and H % stride == 0 and W % stride == 0
+    Hi, Wi = H, W
+    H, W = H // stride, W // stride
     if out is None:
         out = torch.empty((B, H, W, N), device=x.device, dtype=out_dtype or x.dtype)
     g = GemmArgs()
     g.a, g.lda = x.data_ptr(), C
-    g.conv3x3, g.conv_B, g.conv_H, g.conv_W, g.conv_C = 1, B, H, W, C
+    g.conv3x3, g.conv_B, g.conv_H, g.conv_W, g.conv_C, g.conv_stride = 1, B, Hi, Wi, C, stride
     if a2 is not None:
         _chk2d(a2, "a2")
         g.a2, g.lda2, g.k2, g.a2_mode = a2.data_ptr(), a2.stride(0), a2.shape[1], 1

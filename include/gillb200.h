@@ -44,7 +44,7 @@ long long gillb200_launch_count(void);
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct gillb200_gemm_args {
   /* A operand: [M, K] with row stride lda (elements). With conv3x3 != 0, `a` is an NHWC activation
-   * [conv_B, conv_H, conv_W, conv_C] and the GEMM is the 3x3/stride-1/pad-1 convolution: M = B*H*W, K = 9*C,
+   * [conv_B, conv_H, conv_W, conv_C] and the GEMM is the 3x3/pad-1 convolution (stride conv_stride): M = B*H*W, K = 9*C,
    * B operand laid out [N, 9*C] with k = (ky*3+kx)*C + c. */
   const void* a;
   long long lda;
@@ -84,6 +84,8 @@ typedef struct gillb200_gemm_args {
    * whose tile count fills the SMs badly (the UNet's 8x8 / 16x16 levels) split their K range evenly over all SMs. */
   void* sk_workspace;
   int stream_k; /* 0 = auto (when sk_workspace is given); 1 = never; 2 = always (if the kernel variant supports it) */
+  int conv_stride; /* conv3x3 only: 0/1 = stride 1; 2 = stride 2 (conv_H/conv_W stay the INPUT size, M = B*(H/2)*(W/2));
+                    * the A tensor map then walks the input with TMA element strides, no im2col buffer */
 } gillb200_gemm_args;
 
 long long gillb200_gemm_streamk_workspace_bytes(void);

@@ -145,6 +145,34 @@ def test_conv3x3_stream_k(ops, case):
     assert torch.equal(got, ops.conv3x3(x, wk, bias=bias, residual=res, stream_k=2))
 
 
+@pytest.mark.parametrize("case", [(2, 64, 320, 320), (2, 32, 640, 640), (4, 16, 1280, 1280), (1, 16, 64, 96)])
+def test_conv3x3_stride2_implicit(ops, case):
+    """Stride-2 downsampler through TMA element strides == F.conv2d(stride=2, padding=1)."""
+    B, HW, C, Co = case
+    torch.manual_seed(22)
+    x = torch.randn(B, HW, HW, C, device=dev).half()
+    w = (torch.randn(Co, C, 3, 3, device=dev) * 0.03).half()
+    wk = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    bias = torch.randn(Co, device=dev)
+    got = ops.conv3x3(x, wk, bias=bias, stride=2, out_dtype=torch.float32)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert got.shape == ref.shape and rel(got, ref) < 1e-5
+
+
+def test_geglu_fast_epilogue_fp16(ops):
+    """fp16-output GEGLU takes the specialised staged epilogue with the polynomial GELU (|err| <= 7e-5 abs)."""
+    torch.manual_seed(23)
+    M, N, K = 512, 1280, 320
+    a = torch.randn(M, K, device=dev).half()
+    b = (torch.randn(N, K, device=dev) * 0.08).half()
+    bias = torch.randn(N, device=dev)
+    val, gate = b[0::2], b[1::2]
+    ref = (a.float() @ val.float().T + bias[0::2]) * F.gelu(a.float() @ gate.float().T + bias[1::2])
+    got = ops.gemm(a, b, bias=bias, act="geglu")
+    assert got.dtype == torch.float16 and rel(got, ref) < 1e-3
+    assert (got.float() - ref).abs().max() < 2e-3 * ref.abs().max()
+
+
 def test_conv_helpers(ops):
     torch.manual_seed(5)
     x = torch.randn(2, 16, 16, 64, device=dev).half()
