@@ -127,6 +127,8 @@ __device__ __forceinline__ float attn_exp32(const uint32_t (&v)[32], int c, int 
 template <int HD_PAD, int BLOCK_KV>
 __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) attn_kernel(const __grid_constant__ AttnParams p) {
   using C = AttnCfg<HD_PAD, BLOCK_KV>;
+  pdl_wait();
+  pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   AttnBars* bars = reinterpret_cast<AttnBars*>(smem + C::OFF_BAR);
@@ -444,6 +446,8 @@ template <int HD_PAD>
 __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kernel(const __grid_constant__ AttnParams p) {
   using C = Attn2Cfg<HD_PAD>;
   constexpr int BKV = C::BKV;
+  pdl_wait();
+  pdl_launch();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Attn2Bars* bars = reinterpret_cast<Attn2Bars*>(smem + C::OFF_BAR);
@@ -652,9 +656,8 @@ static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  attn2_kernel<HD_PAD><<<grid, 128, C::SMEM_BYTES, stream>>>(p);
+  GB_CUDA(launch_pdl(attn2_kernel<HD_PAD>, grid, dim3(128), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
-  GB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -668,9 +671,8 @@ static int launch_attn(const AttnParams& p, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  attn_kernel<HD_PAD, BLOCK_KV><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
+  GB_CUDA(launch_pdl(attn_kernel<HD_PAD, BLOCK_KV>, grid, dim3(256), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
-  GB_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -15,6 +15,8 @@ __device__ __forceinline__ uint4 ldg16(const void* p) { return *reinterpret_cast
 __global__ void gather_add_rows_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ table,
                                        const long long* __restrict__ idx, long long idx_offset, long long rows, int D,
                                        int is_bf16, uint16_t* __restrict__ out) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   const int nvec = D >> 3;
   const long long total = rows * nvec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -42,6 +44,8 @@ __global__ void gather_add_rows_kernel(const uint16_t* __restrict__ x, const uin
 // nearest-neighbour 2x upsample, NHWC 16-bit (F.interpolate(scale_factor=2, mode="nearest") in the UNet/VAE up blocks)
 __global__ void upsample2x_kernel(const uint16_t* __restrict__ x, int B, int H, int W, int C,
                                   uint16_t* __restrict__ out) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   const int nvec = C >> 3;
   const long long total = static_cast<long long>(B) * 2 * H * 2 * W * nvec;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -61,6 +65,8 @@ __global__ void upsample2x_kernel(const uint16_t* __restrict__ x, int B, int H, 
 // C = 4). out[m, (ky*3+kx)*C + c] for m = (b, oy, ox); columns [9*C, ld_out) are zero-filled.
 __global__ void im2col3x3_kernel(const uint16_t* __restrict__ x, int B, int H, int W, int C, int stride, int Ho,
                                  int Wo, uint16_t* __restrict__ out, long long ld_out) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   const long long total = static_cast<long long>(B) * Ho * Wo * ld_out;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -90,6 +96,8 @@ __global__ void plms_step_kernel(const void* __restrict__ eps_pair, int eps_dtyp
                                  int head, int mode, float c_sample, float c_eps, float* __restrict__ latents,
                                  float* __restrict__ cur_sample, void* __restrict__ lat16_pair, int lat16_dtype,
                                  long long n) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float eu = load_elem(eps_pair, i, eps_dtype), et = load_elem(eps_pair, n + i, eps_dtype);
@@ -128,6 +136,8 @@ __global__ void plms_step_kernel(const void* __restrict__ eps_pair, int eps_dtyp
 // VAE epilogue (gill/custom_sd.py:389-391 + numpy_to_pil): uint8 NHWC = round(clamp(x/2 + 0.5, 0, 1) * 255)
 __global__ void image_to_u8_kernel(const void* __restrict__ x, int dtype, long long pixels, int ldx, int channels,
                                    uint8_t* __restrict__ out) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   const long long total = pixels * channels;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -142,6 +152,8 @@ __global__ void image_to_u8_kernel(const void* __restrict__ x, int dtype, long l
 // y = x / ||x||_2 per row (gill/models.py:674); one warp per row; fp32 in, 16-bit or fp32 out.
 __global__ void l2norm_rows_kernel(const float* __restrict__ x, long long ldx, int rows, int n, void* __restrict__ out,
                                    long long ldo, int out_dtype) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -160,6 +172,8 @@ __global__ void l2norm_rows_kernel(const float* __restrict__ x, long long ldx, i
 __global__ void cast_add_kernel(const void* __restrict__ x, int x_dtype, const void* __restrict__ y, int y_dtype,
                                 void* __restrict__ out, int out_dtype, void* __restrict__ out_lo, long long n,
                                 long long y_period) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float v = load_elem(x, i, x_dtype);
@@ -178,6 +192,8 @@ __global__ void __launch_bounds__(256) attn_small_f32_kernel(const float* __rest
                                                              int Lq, int Lk, float scale, void* __restrict__ out,
                                                              long long ldo, long long o_bs, int out_dtype,
                                                              void* __restrict__ out_lo) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   extern __shared__ float sm[];
   const int LkP = Lk + 1;
   float* sk = sm;                      // [Lk][HD+1]
@@ -261,6 +277,8 @@ __global__ void __launch_bounds__(256) attn_small_f32_kernel(const float* __rest
 __global__ void channel_mix_kernel(const float* __restrict__ x, int cin, const float* __restrict__ w,
                                    const float* __restrict__ b, int cout, long long n, void* __restrict__ out,
                                    int out_dtype) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n * cout;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long pix = i / cout;
@@ -286,9 +304,9 @@ extern "C" int gillb200_gather_add_rows(const void* x, const void* table, const 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(table && idx && out && D % 8 == 0 && rows > 0, "gather_add_rows: bad args");
   GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16, "gather_add_rows: 16-bit only");
-  gather_add_rows_kernel<<<grid_for(rows * (D / 8), 256), 256, 0, stream>>>(
+  GB_CUDA(launch_pdl(gather_add_rows_kernel, dim3(grid_for(rows * (D / 8), 256)), dim3(256), 0, stream, 
       reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(table), idx, idx_offset, rows, D,
-      dtype == DT_BF16, reinterpret_cast<uint16_t*>(out));
+      dtype == DT_BF16, reinterpret_cast<uint16_t*>(out)));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -297,8 +315,8 @@ extern "C" int gillb200_gather_add_rows(const void* x, const void* table, const 
 extern "C" int gillb200_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && C % 8 == 0, "upsample2x: bad args");
-  upsample2x_kernel<<<grid_for(4LL * B * H * W * (C / 8), 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint16_t*>(x), B, H, W, C, reinterpret_cast<uint16_t*>(out));
+  GB_CUDA(launch_pdl(upsample2x_kernel, dim3(grid_for(4LL * B * H * W * (C / 8), 256)), dim3(256), 0, stream, 
+      reinterpret_cast<const uint16_t*>(x), B, H, W, C, reinterpret_cast<uint16_t*>(out)));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -309,8 +327,8 @@ extern "C" int gillb200_im2col3x3(const void* x, int B, int H, int W, int C, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && (stride == 1 || stride == 2) && ld_out >= 9 * C, "im2col3x3: bad args");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  im2col3x3_kernel<<<grid_for(1LL * B * Ho * Wo * ld_out, 256), 256, 0, stream>>>(
-      reinterpret_cast<const uint16_t*>(x), B, H, W, C, stride, Ho, Wo, reinterpret_cast<uint16_t*>(out), ld_out);
+  GB_CUDA(launch_pdl(im2col3x3_kernel, dim3(grid_for(1LL * B * Ho * Wo * ld_out, 256)), dim3(256), 0, stream, 
+      reinterpret_cast<const uint16_t*>(x), B, H, W, C, stride, Ho, Wo, reinterpret_cast<uint16_t*>(out), ld_out));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -322,8 +340,8 @@ extern "C" int gillb200_plms_step(const void* eps_pair, int eps_dtype, float gui
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(eps_pair && ets && latents && cur_sample && n > 0, "plms_step: null pointer");
   GB_CHECK_ARG(mode >= 0 && mode <= 4 && head >= 0 && head < 4, "plms_step: bad mode/head");
-  plms_step_kernel<<<grid_for(n, 256), 256, 0, stream>>>(eps_pair, eps_dtype, guidance, ets, head, mode, c_sample,
-                                                         c_eps, latents, cur_sample, lat16_pair, lat16_dtype, n);
+  GB_CUDA(launch_pdl(plms_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, eps_pair, eps_dtype, guidance, ets, head, mode, c_sample,
+                                                         c_eps, latents, cur_sample, lat16_pair, lat16_dtype, n));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -333,8 +351,8 @@ extern "C" int gillb200_image_to_u8(const void* x, int dtype, long long pixels, 
                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && pixels > 0 && channels > 0 && ldx >= channels, "image_to_u8: bad args");
-  image_to_u8_kernel<<<grid_for(pixels * channels, 256), 256, 0, stream>>>(x, dtype, pixels, ldx, channels,
-                                                                           reinterpret_cast<uint8_t*>(out));
+  GB_CUDA(launch_pdl(image_to_u8_kernel, dim3(grid_for(pixels * channels, 256)), dim3(256), 0, stream, x, dtype, pixels, ldx, channels,
+                                                                           reinterpret_cast<uint8_t*>(out)));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -344,7 +362,7 @@ extern "C" int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int
                                     int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && rows > 0 && n > 0, "l2norm_rows: bad args");
-  l2norm_rows_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, rows, n, out, ldo, out_dtype);
+  GB_CUDA(launch_pdl(l2norm_rows_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, x, ldx, rows, n, out, ldo, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -354,7 +372,7 @@ extern "C" int gillb200_cast_add(const void* x, int x_dtype, const void* y, int 
                                  int out_dtype, void* out_lo, long long n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && n > 0, "cast_add: bad args");
-  cast_add_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period);
+  GB_CUDA(launch_pdl(cast_add_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -374,8 +392,8 @@ extern "C" int gillb200_attn_small_f32(const float* q, long long ldq, long long 
     GB_CUDA(cudaFuncSetAttribute(attn_small_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
-  attn_small_f32_kernel<128><<<dim3(H, B), 256, smem, stream>>>(q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
-                                                                  out, ldo, o_bs, out_dtype, out_lo);
+  GB_CUDA(launch_pdl(attn_small_f32_kernel<128>, dim3(dim3(H, B)), dim3(256), smem, stream, q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
+                                                                  out, ldo, o_bs, out_dtype, out_lo));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -385,7 +403,7 @@ extern "C" int gillb200_channel_mix(const float* x, int cin, const float* w, con
                                     void* out, int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && w && b && out && cin >= 1 && cin <= 8 && cout >= 1 && cout <= 8 && n > 0, "channel_mix: bad args");
-  channel_mix_kernel<<<grid_for(n * cout, 256), 256, 0, stream>>>(x, cin, w, b, cout, n, out, out_dtype);
+  GB_CUDA(launch_pdl(channel_mix_kernel, dim3(grid_for(n * cout, 256)), dim3(256), 0, stream, x, cin, w, b, cout, n, out, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;

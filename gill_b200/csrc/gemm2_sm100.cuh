@@ -78,6 +78,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     {

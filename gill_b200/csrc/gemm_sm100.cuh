@@ -919,6 +919,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
+  pdl_wait();    // barriers, TMEM and descriptors are set up; operands of the previous kernel are visible from here on
+  pdl_launch();
 
   const bool n_inner = p.tile_order == 2 || (p.tile_order == 0 && num_n <= 4 && num_m >= 2 * static_cast<int>(gridDim.x));
   const int order = n_inner ? -num_n : num_m;  // see tile_coord()

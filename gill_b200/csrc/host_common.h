@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 
 namespace gb {
 
@@ -36,6 +37,25 @@ int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const u
                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes, const uint32_t* elem_strides);
 
 int num_sms();
+
+// Launch, optionally (GILLB200_PDL=1) with the programmatic-dependent-launch attribute: the kernel must call
+// gb::pdl_wait() before its first global-memory access. Captured into CUDA graphs as programmatic dependency edges.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)
 extern long long g_launch_count;

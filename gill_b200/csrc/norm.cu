@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const void* __restrict__
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         float eps, int rows, int C, void* __restrict__ out,
                                                         long long ldo, int out_dtype, void* __restrict__ out_lo) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   __shared__ float red[2][4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rows_per_block = 4 / WARPS;
@@ -141,6 +143,8 @@ __global__ void __launch_bounds__(128) layernorm_sub_kernel(const void* __restri
                                                             const float* __restrict__ w, const float* __restrict__ b,
                                                             float eps, int rows, int C, void* __restrict__ out,
                                                             long long ldo, int out_dtype, void* __restrict__ out_lo) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int row = (blockIdx.x * 4 + warp) * RPW + lane / LPR;
@@ -222,6 +226,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
                                                        int* __restrict__ counters /* [B], zero between launches */,
                                                        const float* __restrict__ w, const float* __restrict__ bias,
                                                        float eps, float* __restrict__ scale_shift /* [B, 2, C] */) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   // Thread t owns channel vector v and pixel subgroup sg: 256 consecutive threads read 256 consecutive 16-byte
   // vectors (NHWC is pixel-major, so the next pixel's channels follow). Per-thread register sums -> smem
   // [sg][sum|sumsq][C] -> per-group totals summed in a fixed order: no atomics, bit-reproducible.
@@ -336,6 +342,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(GnSrc src, int dtype, int
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks, int G, int C, int HW,
                                    const float* __restrict__ w, const float* __restrict__ bias, float eps,
                                    float* __restrict__ scale_shift /* [B, 2, C] */) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   __shared__ float gmean[64], grstd[64];
   const int b = blockIdx.x;
   const int cpg = C / G;
@@ -367,6 +375,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int HW, const float* __restrict__ scale_shift,
                                                        int silu, void* __restrict__ out, int out_dtype,
                                                        int pix_per_block) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   const int C = src.C0 + src.C1;
   const int nvec = C >> 3;
   const int b = blockIdx.y;
@@ -430,6 +440,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const void* __restrict__ x, long long ldx, int in_dtype,
                                                            float scale, int n, void* __restrict__ out, long long ldo,
                                                            int out_dtype) {
+  pdl_wait();  // (programmatic dependent launch: inputs of the previous kernel visible from here)
+  pdl_launch();
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const int nvec = n >> 3;
@@ -482,17 +494,17 @@ extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, co
   GB_CHECK_ARG(C <= 5120, "layernorm supports C <= 5120 (got %d)", C);
   GB_CHECK_ARG(!out_lo || out_dtype == DT_BF16, "out_lo requires bf16 output");
   if (C <= 320) {
-    layernorm_sub_kernel<8, 5><<<(rows + 15) / 16, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
-                                                                     out_dtype, out_lo);
+    GB_CUDA(launch_pdl(layernorm_sub_kernel<8, 5>, dim3((rows + 15) / 16), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                     out_dtype, out_lo));
   } else if (C <= 640) {
-    layernorm_sub_kernel<16, 5><<<(rows + 7) / 8, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
-                                                                    out_dtype, out_lo);
+    GB_CUDA(launch_pdl(layernorm_sub_kernel<16, 5>, dim3((rows + 7) / 8), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                    out_dtype, out_lo));
   } else if (C <= 1280) {
-    layernorm_sub_kernel<32, 5><<<(rows + 3) / 4, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
-                                                                    out_dtype, out_lo);
+    GB_CUDA(launch_pdl(layernorm_sub_kernel<32, 5>, dim3((rows + 3) / 4), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+                                                                    out_dtype, out_lo));
   } else {
-    layernorm_kernel<4, 5><<<rows, 128, 0, stream>>>(x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
-                                                      out_lo);
+    GB_CUDA(launch_pdl(layernorm_kernel<4, 5>, dim3(rows), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
+                                                      out_lo));
   }
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -527,8 +539,8 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   float* scale_shift = partial + 128LL * B * G * 2;
   const int nvec = C / 8;
   const size_t smem_stats = static_cast<size_t>(nvec >= 256 ? 1 : 256 / nvec) * 2 * C * sizeof(float);
-  gn_stats_kernel<<<dim3(chunks, B), 256, smem_stats, stream>>>(src, dtype, HW, G, chunks, partial, counters, w, b, eps,
-                                                               scale_shift);
+  GB_CUDA(launch_pdl(gn_stats_kernel, dim3(dim3(chunks, B)), dim3(256), smem_stats, stream, src, dtype, HW, G, chunks, partial, counters, w, b, eps,
+                                                               scale_shift));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   // ~64K elements per CTA, but never fewer than ~4 CTAs per SM worth of blocks when the tensor is small
@@ -538,7 +550,7 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   if (pix_per_block * want_blocks > HW) pix_per_block = (HW + want_blocks - 1) / want_blocks;
   pix_per_block = ((pix_per_block + 4 * sgs - 1) / (4 * sgs)) * (4 * sgs);
   const int blocks = (HW + pix_per_block - 1) / pix_per_block;
-  gn_apply_kernel<<<dim3(blocks, B), 256, 0, stream>>>(src, dtype, HW, scale_shift, silu, out, out_dtype, pix_per_block);
+  GB_CUDA(launch_pdl(gn_apply_kernel, dim3(dim3(blocks, B)), dim3(256), 0, stream, src, dtype, HW, scale_shift, silu, out, out_dtype, pix_per_block));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -549,7 +561,7 @@ extern "C" int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && n % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "softmax_rows: n, ldx, ldo multiples of 8");
   GB_CHECK_ARG(rows > 0 && rows < (1LL << 31), "softmax_rows: bad row count");
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(x, ldx, in_dtype, scale, n, out, ldo, out_dtype);
+  GB_CUDA(launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, x, ldx, in_dtype, scale, n, out, ldo, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
