@@ -118,6 +118,48 @@ def make_inputs(rank):
     return vis, ids, lat
 
 
+def stage_breakdown(gill, vis, ids, lat, reps=2):
+    """CUDA-event time of each stage of one step (device-resident inputs): OPT prefill / GILLMapper / 51 graph-replayed
+    UNet evaluations + PLMS / VAE decode. Mirrors GILL.emit_images_batch (gill_b200/models.py)."""
+    m = gill.model
+    dev = vis.device
+
+    def ev():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def step():
+        marks = [ev()]
+        txt = m.input_embeddings(ids)
+        embs = torch.cat([vis, txt], dim=1)
+        B, P, D = embs.shape
+        img_ids = torch.tensor(m.retrieval_token_idx, dtype=torch.int64, device=dev)
+        img_embs = m.input_embeddings(img_ids[None, :])
+        full = torch.cat([embs.to(m.lm.dt), img_embs.expand(B, -1, -1).to(m.lm.dt)], dim=1)
+        hs, lg = m.lm.forward(full, logit_positions=[P - 1])
+        raw = hs[:, P:P + m.num_tokens, :].float().contiguous()
+        marks.append(ev())
+        gen = m.gen_text_hidden_fcs[0](raw, img_embs.float())
+        marks.append(ev())
+        latn = gill.sd_pipe.denoise(gen, lat)
+        marks.append(ev())
+        gill.sd_pipe.vae.decode_u8(latn)
+        marks.append(ev())
+        return marks
+
+    step()
+    torch.cuda.synchronize()
+    acc = [0.0] * 4
+    for _ in range(reps):
+        mk = step()
+        torch.cuda.synchronize()
+        for i in range(4):
+            acc[i] += mk[i].elapsed_time(mk[i + 1]) / reps
+    return {"opt_prefill": round(acc[0], 2), "gill_mapper": round(acc[1], 2), "unet_51_evals_plms": round(acc[2], 2),
+            "vae_decode": round(acc[3], 2), "unet_ms_per_eval": round(acc[2] / 51, 3)}
+
+
 def run_ours(args):
     from gill_b200 import ops, synthetic
     from gill_b200._lib import lib
@@ -194,7 +236,7 @@ def run_ours(args):
     e2e_per_s = world * BATCH / (ms_e2e / 1e3)
 
     # ---- roofline of the dominant kernel family, measured live with CUDA events (one eager, un-graphed UNet eval)
-    roof, breakdown = None, None
+    roof, breakdown, stages, rooflines = None, None, None, None
     if rank == 0:
         sdp = gill.sd_pipe
         st = next(iter(sdp._graphs.values()))
@@ -209,12 +251,27 @@ def run_ours(args):
                          "launches_per_eval": d["launches"] // 2,
                          "tflops": round(d["flops"] / d["ms"] / 1e9, 1) if d["flops"] else None}
                      for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+        stages = stage_breakdown(gill, vis_d, ids_d, lat_d)
+        traffic_db = {}
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")  # dram bytes per launch from `ncu --set full` captures
+        if os.path.exists(tp):
+            traffic_db = json.load(open(tp))
+        rooflines = []
+        for k, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+            if d["flops"]:
+                a_ = d["flops"] / d["ms"] / 1e9
+                rooflines.append({"family": k, "bound": "tensor", "achieved": round(a_, 1), "peak": pk["tf_sustained"],
+                                  "unit": "TFLOP/s", "frac": round(a_ / pk["tf_sustained"], 3)})
+            elif d["bytes"]:
+                a_ = d["bytes"] / d["ms"] / 1e6
+                rooflines.append({"family": k, "bound": "hbm", "achieved": round(a_, 1), "peak": pk["hbm"],
+                                  "unit": "GB/s", "frac": round(a_ / pk["hbm"], 3)})
         top = max(prof.items(), key=lambda kv: kv[1]["ms"])
         ach = top[1]["flops"] / top[1]["ms"] / 1e9
         roof = {"kernel": {"conv3x3": "gemm_kernel<BN> (implicit 3x3 conv mode)", "gemm": "gemm_kernel<BN>",
                            "attention": "attn_kernel<HD_PAD,BLOCK_KV>"}.get(top[0], top[0]),
                 "bound": "tensor", "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 3), "traffic": None,
+                "frac": round(ach / pk["tf_sustained"], 3), "traffic": traffic_db.get(top[0]),
                 "peak_source": pk["src"] + " sustained bf16 (kernel timed inside a long step)",
                 "launches_timed": top[1]["launches"], "avg_launch_ms": round(top[1]["ms"] / top[1]["launches"], 4),
                 "share_of_unet_eval": round(top[1]["ms"] / tot, 3)}
@@ -309,7 +366,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "achieved_tflops_whole_step": round(flop_per_batch / (ms_dev / 1e3), 1),
-        "roofline": roof, "unet_eval_breakdown": breakdown, "cpu_baseline": cpu, "retrieval": retrieval_obj,
+        "roofline": roof, "rooflines_by_family": rooflines, "stages_ms": stages, "unet_eval_breakdown": breakdown,
+        "cpu_baseline": cpu, "retrieval": retrieval_obj,
         "mapper": mapper_obj,
     }
     print(json.dumps(line))

@@ -128,21 +128,28 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     if (leader) {
       // ---------------- MMA issuer (leader CTA only; one thread drives both SMs' tensor cores)
       const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
+      // incremental descriptors + look-ahead probe of the next stage's barrier: see gemm_mma()
+      const uint32_t s0 = smem_u32(smem_tiles);
+      const uint64_t da0 = make_smem_desc_sw128(s0, 16, 1024);
+      const uint64_t db0 = make_smem_desc_sw128(s0 + C::A_BYTES, 16, 1024);
+      constexpr uint64_t DESC_STEP = C::STAGE_BYTES >> 4;
+      uint64_t da = da0, db = db0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      bool ready = false;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&bars->full[stage], phase);
+          if (!ready) mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_tiles + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+          const bool wrap = stage + 1 == p.num_stages;
+          const int nstage = wrap ? 0 : stage + 1;
+          const uint32_t nphase = wrap ? phase ^ 1 : phase;
+          ready = mbar_test_wait(&bars->full[nstage], nphase);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
@@ -150,10 +157,10 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
           }
           __syncwarp();
-          if (++stage == p.num_stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+          da = wrap ? da0 : da + DESC_STEP;
+          db = wrap ? db0 : db + DESC_STEP;
+          stage = nstage;
+          phase = nphase;
         }
         if (elect_one()) umma2_commit_mcast(&bars->tmem_full[acc], 0b11);  // accumulators ready in both CTAs
         __syncwarp();

@@ -248,22 +248,33 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
                                          SegIter it) {
   using C = GemmCfg<BLOCK_N>;
   const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
+  // Measured (GILLB200_GEMM_DEBUG=1, no TMA): a k-block took ~300 cycles of issue-side preparation PLUS 3 x N/2
+  // cycles -- tcgen05.mma issue blocks while the previous MMA occupies the pipe, so everything between the last MMA of
+  // one k-block and the first of the next is exposed. Hence: smem descriptors are advanced incrementally (their
+  // start-address field counts 16-byte units, a stage is STAGE_BYTES/16 further), and the NEXT stage's full barrier is
+  // probed (non-blocking test_wait) before this stage's MMAs are issued, so its latency hides under them.
+  const uint32_t s0 = smem_u32(smem_tiles);
+  const uint64_t da0 = make_smem_desc_sw128(s0, 16, 1024);
+  const uint64_t db0 = make_smem_desc_sw128(s0 + C::A_BYTES, 16, 1024);
+  constexpr uint64_t DESC_STEP = C::STAGE_BYTES >> 4;
+  uint64_t da = da0, db = db0;
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
+  bool ready = false;  // full[stage] of the current phase already seen complete by the look-ahead probe
   Seg sg;
   while (it.next(sg)) {
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
     for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
-      mbar_wait(&full[stage], phase);
+      if (!ready) mbar_wait(&full[stage], phase);
       tc_fence_after();
-      const uint32_t sa = smem_u32(smem_tiles + stage * C::STAGE_BYTES);
-      const uint32_t sb = sa + C::A_BYTES;
-      const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-      const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+      const bool wrap = stage + 1 == p.num_stages;
+      const int nstage = wrap ? 0 : stage + 1;
+      const uint32_t nphase = wrap ? phase ^ 1 : phase;
+      ready = mbar_test_wait(&full[nstage], nphase);
       if (elect_one()) {
         if (p.debug_mode != 2) {
 #pragma unroll
@@ -275,10 +286,10 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
         umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
       }
       __syncwarp();
-      if (++stage == p.num_stages) {
-        stage = 0;
-        phase ^= 1;
-      }
+      da = wrap ? da0 : da + DESC_STEP;
+      db = wrap ? db0 : db + DESC_STEP;
+      stage = nstage;
+      phase = nphase;
     }
     if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
     __syncwarp();
