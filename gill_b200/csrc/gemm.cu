@@ -77,7 +77,7 @@ bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     // opt-in: measured on B200 inside the captured UNet graph it buys nothing (22.19 vs 22.02 ms per evaluation, the
-    // graph already launches back to back) and one full-UNet parity run failed with it on, so it stays off by default
+    // graph already launches back to back), so it stays off by default
     const char* e = getenv("GILLB200_PDL");
     v = e ? (atoi(e) != 0) : 0;
   }
@@ -288,7 +288,12 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   // (tools/gpu_sweep_shapes.py): 16x16 C1280 150 -> 111 us, 8x8 C2560 149 -> 102 us; plain short-K linears lose
   // (the fix-up costs more than the idle SMs), so auto mode is limited to convolutions.
   bool want_sk = false;
-  if (a->sk_workspace && a->stream_k != 1 && a->tile_order != 2 && a->cta_pair != 2) {
+  static int env_sk = -1;
+  if (env_sk < 0) {
+    const char* e = getenv("GILLB200_STREAMK");  // "0": never stream-K in auto mode (A/B aid)
+    env_sk = e ? atoi(e) : 1;
+  }
+  if (a->sk_workspace && a->stream_k != 1 && (a->stream_k == 2 || env_sk) && a->tile_order != 2 && a->cta_pair != 2) {
     if (a->stream_k == 2) {
       want_sk = true;
     } else if (a->conv3x3 && a->out_dtype != DT_F32 && p.num_k_blocks >= 16) {

@@ -716,7 +716,9 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       }
       __threadfence();
       __syncwarp();
-      if (lane == 0) {
+      // raise the flag only when the finisher's same-index warp will consume (and re-arm) it: a warp whose rows lie
+      // beyond M or whose panels lie beyond N has pb0 >= pe on both sides and must leave the flag alone
+      if (lane == 0 && pb0 < pe) {
         int* flag = p.sk_flags + static_cast<size_t>(blockIdx.x) * GEMM_EPI_WARPS + ew;
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
       }

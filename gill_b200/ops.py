@@ -249,7 +249,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
               kv_lens: Optional[torch.Tensor] = None, ones_col: int = 0) -> torch.Tensor:
     """q [B,Lq,>=H*hd_pad], k/v [B,Lk,>=H*hd_pad] (views into fused QKV buffers allowed; last dim contiguous).
     Returns out [B,Lq,H*hd_pad]. Pad columns of each head must be zero in q, k, v -- except that v may carry 1.0 in
-    pad column `ones_col` (> 0) of every head, which moves the softmax row sum onto the tensor core (fp16 only)."""
+    pad column `ones_col` (> 0) of every head, which moves the softmax row sum onto the tensor core."""
     B, Lq, _ = q.shape
     Lk = k.shape[1]
     for t in (q, k, v):

@@ -16,6 +16,15 @@ from . import ops
 SD = Dict[str, torch.Tensor]
 
 
+class KVCache:
+    """Key/value buffers of every decoder layer, [B, max_len, D] in the model dtype, plus the number of tokens held."""
+
+    def __init__(self, layers: int, batch: int, max_len: int, hidden: int, device, dtype):
+        self.batch, self.max_len, self.len = batch, max_len, 0
+        self.k = [torch.empty((batch, max_len, hidden), device=device, dtype=dtype) for _ in range(layers)]
+        self.v = [torch.empty((batch, max_len, hidden), device=device, dtype=dtype) for _ in range(layers)]
+
+
 class OPTB200:
     def __init__(self, sd: SD, hidden: int, layers: int, heads: int, ffn: int, device="cuda", dtype=torch.bfloat16):
         """sd: OPTForCausalLM-named state dict (`model.decoder.*`); weights are stored bf16, biases / norms fp32."""
@@ -71,24 +80,44 @@ class OPTB200:
         flat = ids.reshape(-1).to(self.dev, torch.int64).contiguous()
         return ops.gather_add_rows(self.embed, flat).view(*ids.shape, self.D)
 
+    def new_cache(self, batch: int, max_len: int) -> "KVCache":
+        """Per-layer K/V buffers for incremental decoding (the reference itself decodes without a cache,
+        gill/models.py:465 `use_cache=False`, recomputing the whole sequence at every step)."""
+        return KVCache(self.L, batch, max_len, self.D, self.dev, self.dt)
+
     @torch.no_grad()
-    def forward(self, inputs_embeds: torch.Tensor, need_logits: bool = True, logit_positions=None):
+    def forward(self, inputs_embeds: torch.Tensor, need_logits: bool = True, logit_positions=None,
+                cache: Optional["KVCache"] = None):
         """inputs_embeds [B,T,D] -> (hidden_states[-1] [B,T,D] in the model dtype, logits fp32).
-        logits: [B,V] at the last position, or [B,len(logit_positions),V] at the requested positions."""
+        logits: [B,V] at the last position, or [B,len(logit_positions),V] at the requested positions.
+        With `cache`, inputs_embeds are the T NEW tokens following the cache.len tokens already processed: their K/V are
+        appended and attention runs over the cached keys (causal with offset). Every position's arithmetic is the same
+        as in the uncached forward (row-independent GEMMs, same KV tiling), so hidden states are bit-identical."""
         B, T, D = inputs_embeds.shape
         H, hd = self.H, self.hd
+        past = 0 if cache is None else cache.len
+        if cache is not None and (B != cache.batch or past + T > cache.max_len):
+            raise ValueError(f"KV cache holds batch {cache.batch} x {cache.max_len} tokens; got batch {B}, {past}+{T} tokens")
         x = inputs_embeds.to(self.dev, self.dt).contiguous().view(B * T, D)
-        pos_idx = torch.arange(T, device=self.dev, dtype=torch.int64).repeat(B)
+        pos_idx = torch.arange(past, past + T, device=self.dev, dtype=torch.int64).repeat(B)
         h16 = ops.gather_add_rows(self.pos, pos_idx, x=x, idx_offset=2)           # + embed_positions(pos + 2)
         h = ops.cast_add(h16, None, torch.float32)                                # fp32 residual stream
-        for ly in self.layers:
+        for li, ly in enumerate(self.layers):
             n = ops.layernorm(h, ly["ln1_w"], ly["ln1_b"], 1e-5, out_dtype=self.dt)
             qkv = ops.gemm(n, ly["qkv_w"], bias=ly["qkv_b"]).view(B, T, 3 * D)
-            a = ops.attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], H, hd, hd ** -0.5, causal=True)
+            if cache is None:
+                a = ops.attention(qkv[:, :, :D], qkv[:, :, D:2 * D], qkv[:, :, 2 * D:], H, hd, hd ** -0.5, causal=True)
+            else:
+                cache.k[li][:, past:past + T].copy_(qkv[:, :, D:2 * D])
+                cache.v[li][:, past:past + T].copy_(qkv[:, :, 2 * D:])
+                a = ops.attention(qkv[:, :, :D], cache.k[li][:, :past + T], cache.v[li][:, :past + T], H, hd, hd ** -0.5,
+                                  causal=True, causal_offset=past)
             h = ops.gemm(a.view(B * T, D), ly["o_w"], bias=ly["o_b"], residual=h, out_dtype=torch.float32)
             n = ops.layernorm(h, ly["ln2_w"], ly["ln2_b"], 1e-5, out_dtype=self.dt)
             f = ops.gemm(n, ly["fc1_w"], bias=ly["fc1_b"], act="relu")
             h = ops.gemm(f, ly["fc2_w"], bias=ly["fc2_b"], residual=h, out_dtype=torch.float32)
+        if cache is not None:
+            cache.len = past + T
         hs = ops.layernorm(h, self.lnf_w, self.lnf_b, 1e-5, out_dtype=self.dt).view(B, T, D)
         logits = None
         if logit_positions is not None:

@@ -122,6 +122,11 @@ def test_gemm_stream_k(ops, case):
     # fp32 output goes through the generic staged epilogue
     o32 = ops.gemm(a, b, bias=bias, stream_k=2, block_n=bn, out_dtype=torch.float32)
     assert rel(o32, a.float() @ b.float().T + bias) < 1e-5
+    # ragged M (rows beyond M in the last tile) must not leave arrival flags behind for the next launch
+    from gill_b200 import ops as _o
+    for ws in _o._sk_ws.values():
+        torch.cuda.synchronize()
+        assert int(ws[:16384].view(torch.int32).abs().sum().item()) == 0
 
 
 @pytest.mark.parametrize("case", [(16, 8, 1280, 1280), (4, 16, 640, 1280), (2, 8, 2560, 320)])

@@ -135,6 +135,30 @@ def test_generate_matches_reference_generate_fixture(golden, speculative):
     assert ids.shape[0] == 1 and ids.shape[1] >= 3
 
 
+def test_generate_with_kv_cache_is_bit_identical(golden):
+    """Incremental decoding (use_cache=True) == the reference-style full recompute: same ids, same golden
+    ids, and bit-identical hidden states / logits at every step (forced [IMG] expansion appends 8 tokens at once)."""
+    g = golden("generate_tiny.npz")
+    gm, cfg = tiny_gill_model()
+    ge = torch.Generator().manual_seed(11)
+    emb = (torch.randn(1, 9, cfg["hidden"], generator=ge) * 0.05).bfloat16().to(dev)
+    for name, kw in (("forced", dict(max_len=2, gen_scale_factor=1e5)), ("greedy", dict(max_len=4)),
+                     ("minwords", dict(max_len=3, min_word_tokens=2, gen_scale_factor=1e5))):
+        ids0, embs0, lg0 = gm.generate(emb, speculative=False, **kw)
+        ids1, embs1, lg1 = gm.generate(emb, use_cache=True, **kw)
+        assert np.array_equal(ids1.cpu().numpy(), g[name + "_ids"]) and torch.equal(ids0, ids1)
+        assert len(embs1) == len(embs0) == kw["max_len"]
+        for a, b in zip(embs0, embs1):
+            assert a.shape == b.shape and torch.equal(a, b), name
+        for a, b in zip(lg0, lg1):
+            assert torch.equal(a, b), name
+    # batch 2 (no forced expansion in the reference for batch > 1, models.py:518)
+    emb2 = torch.cat([emb, emb.flip(1)], 0)
+    i0, e0, _ = gm.generate(emb2, speculative=False, max_len=3)
+    i1, e1, _ = gm.generate(emb2, use_cache=True, max_len=3)
+    assert torch.equal(i0, i1) and torch.equal(e0[-1], e1[-1])
+
+
 # ------------------------------------------------------------------------------------------------ SD-1.5
 @pytest.fixture(scope="module")
 def tiny_sd():
