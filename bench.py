@@ -161,7 +161,8 @@ def stage_breakdown(gill, vis, ids, lat, reps=2):
 
 
 def run_ours(args):
-    from gill_b200 import ops, synthetic
+    from gill_b200 import ops
+    from harness import synthetic
     from gill_b200._lib import lib
     from gill_b200 import retrieval
 

@@ -14,7 +14,8 @@ def _rel(a, b):
 def run():
     if not torch.cuda.is_available():
         raise RuntimeError("smoke() needs a CUDA device (sm_100a)")
-    from . import ops, retrieval, synthetic
+    from gill_b200 import ops, retrieval
+    from harness import synthetic
     from oracle import mapper as omap, retrieval as oret, sd15 as osd
 
     dev = torch.device("cuda", 0)

@@ -113,7 +113,7 @@ def build_sd(device="cuda", seed_unet=0, seed_vae=1, tiny=False):
     """SD-1.5-shaped UNet + VAE decoder with seeded PyTorch-default init (oracle/sd15.py holds the init so that the
     CPU oracle and the CUDA path see identical weights) and a seeded stand-in for the CLIP-text embedding of ""."""
     from oracle import sd15 as osd
-    from . import sd as psd
+    from gill_b200 import sd as psd
 
     ucfg, vcfg = (osd.tiny_unet_cfg(), osd.tiny_vae_cfg()) if tiny else (None, None)
     usd = osd.init_unet(seed_unet, ucfg)
@@ -127,8 +127,8 @@ def build_sd(device="cuda", seed_unet=0, seed_vae=1, tiny=False):
 
 def build_gill(device="cuda", opt="opt-6.7b", tiny_sd=False, with_sd=True, seed=0):
     """The full pipeline object with synthetic frozen models + (real if present) GILL-trained weights."""
-    from .models import GILL
-    from .opt import OPTB200
+    from gill_b200.models import GILL
+    from gill_b200.opt import OPTB200
 
     cfgs = {"opt-6.7b": dict(hidden=4096, layers=32, heads=32, ffn=16384),
             "opt-2l": dict(hidden=4096, layers=2, heads=32, ffn=16384)}

@@ -18,7 +18,7 @@ def test_truncate_caption_behaviour():
 
 
 def test_synthetic_tokenizer_contract():
-    from gill_b200.synthetic import IMG_IDS, SyntheticTokenizer
+    from harness.synthetic import IMG_IDS, SyntheticTokenizer
 
     t = SyntheticTokenizer()
     assert len(t) == 50274 and t.cls_token_id == 50265

@@ -35,7 +35,8 @@ def test_mapper_matches_reference_fixture_synthetic_weights(golden):
 
 
 def test_mapper_and_ret_head_match_reference_fixture_real_checkpoint(golden):
-    from gill_b200 import ops, synthetic
+    from gill_b200 import ops
+    from harness import synthetic
     from gill_b200.layers import TextFcLayer
 
     if not synthetic.real_checkpoint_available():
@@ -104,7 +105,7 @@ class _Tok:
 
 def tiny_gill_model():
     from gill_b200 import models
-    from gill_b200.synthetic import model_args
+    from harness.synthetic import model_args
 
     lm, cfg, sd = tiny_opt()
     img_ids = list(range(512 - 8, 512))
@@ -162,7 +163,7 @@ def test_generate_with_kv_cache_is_bit_identical(golden):
 # ------------------------------------------------------------------------------------------------ SD-1.5
 @pytest.fixture(scope="module")
 def tiny_sd():
-    from gill_b200 import synthetic
+    from harness import synthetic
 
     return synthetic.build_sd(dev, tiny=True)
 
@@ -251,7 +252,7 @@ def test_full_unet_single_eval_matches_oracle():
 # ------------------------------------------------------------------------------------------------ GILL surface
 @pytest.fixture(scope="module")
 def gill_small():
-    from gill_b200 import synthetic
+    from harness import synthetic
 
     gill, kind = synthetic.build_gill(dev, "opt-2l", tiny_sd=True, with_sd=True)
     return gill

@@ -26,7 +26,7 @@ def test_mapper_oracle_matches_reference_class_synthetic_weights(golden):
 
 
 def test_mapper_oracle_matches_reference_class_real_checkpoint(golden):
-    from gill_b200 import synthetic
+    from harness import synthetic
 
     if not synthetic.real_checkpoint_available():
         pytest.skip("shipped checkpoint not present")

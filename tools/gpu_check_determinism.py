@@ -2,7 +2,8 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from gill_b200 import ops, synthetic, sd as psd
+from gill_b200 import ops, sd as psd
+from harness import synthetic
 dev = "cuda"
 torch.manual_seed(0)
 

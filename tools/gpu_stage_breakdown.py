@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
-from gill_b200 import synthetic
+from harness import synthetic
 
 dev = torch.device("cuda", 0)
 gill, _ = synthetic.build_gill(dev, "opt-6.7b", tiny_sd=False, with_sd=True)

@@ -3,7 +3,8 @@ GILLMapper (B=8), one UNet evaluation (B=16) + PLMS step, VAE decode (B=8), retr
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from gill_b200 import ops, synthetic, sd as psd, retrieval
+from gill_b200 import ops, sd as psd, retrieval
+from harness import synthetic
 dev = "cuda"
 gill, kind = synthetic.build_gill(dev, "opt-6.7b", tiny_sd=False, with_sd=True)
 m = gill.model
