@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgillb200.so")
 
 BF16, F16, F32 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_GEGLU = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SILU, ACT_GEGLU, ACT_QUICK_GELU = 0, 1, 2, 3, 4, 5
 
 _c_void_p = ctypes.c_void_p
 _c_int = ctypes.c_int

@@ -29,7 +29,7 @@ constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warps 0-3: producer 
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 enum { A_PLAIN = 0, A_CONV3X3 = 1 };
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_GEGLU = 4 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_GEGLU = 4, ACT_QUICK_GELU = 5 };
 enum { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
 
 struct alignas(64) GemmParams {
@@ -122,6 +122,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_GELU) return gelu_erf(v);
   if (act == ACT_SILU) return v / (1.f + __expf(-v));
+  if (act == ACT_QUICK_GELU) return v / (1.f + __expf(-1.702f * v));
   return v;
 }
 

@@ -4,7 +4,7 @@
 Same names, argument order, defaults, return structure and error behaviour as the reference (file:line cited inline).
 Differences that are deliberate and documented in DESIGN.md:
   * the three frozen third-party models cannot be downloaded here, so they are injected: `lm` (an `OPTB200`),
-    `sd_pipe` (a `StableDiffusionB200`) and optionally `visual_model` (CLIP vision tower: out of scope, SURVEY §8f-1;
+    `sd_pipe` (a `StableDiffusionB200`) and optionally `visual_model` (CLIP vision tower: `gill_b200.clip.CLIPVisionB200`;
     prompts may instead carry already CLIP-encoded images as tensors);
   * `generate` speculatively appends the 8 [IMG] embeddings to every forward: OPT is causal, so the logits at the last
     real position are unchanged, and when [IMG0] is emitted the same forward already contains the next step's hidden
@@ -154,8 +154,8 @@ class GILLModel(nn.Module):
             encoder_outputs = pixel_values
         else:
             if self.visual_model is None:
-                raise NotImplementedError("the CLIP vision tower is outside the B200 hot path (SURVEY.md §8f-1); pass "
-                                          "pooled CLIP features [n, hidden] or a visual_model")
+                raise NotImplementedError("raw pixels need a vision tower: pass visual_model=gill_b200.clip."
+                                          "CLIPVisionB200(...) (SURVEY.md §8f-1) or pooled CLIP features [n, hidden]")
             encoder_outputs = self.visual_model(pixel_values).pooler_output
         if mode == "captioning":
             v = self.visual_embeddings(encoder_outputs)

@@ -5,10 +5,11 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_RELU, ACT_SILU, BF16, F16, F32, GemmArgs, check, lib
+from ._lib import ACT_GEGLU, ACT_GELU, ACT_NONE, ACT_QUICK_GELU, ACT_RELU, ACT_SILU, BF16, F16, F32, GemmArgs, check, lib
 
 _DT = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
-_ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "silu": ACT_SILU, "geglu": ACT_GEGLU}
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "gelu": ACT_GELU, "silu": ACT_SILU, "geglu": ACT_GEGLU,
+        "quick_gelu": ACT_QUICK_GELU}
 
 
 def _stream() -> int:

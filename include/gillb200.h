@@ -25,7 +25,8 @@ extern "C" {
 #define GILLB200_VERSION 100
 
 enum { GILLB200_BF16 = 0, GILLB200_F16 = 1, GILLB200_F32 = 2 };
-enum { GILLB200_ACT_NONE = 0, GILLB200_ACT_RELU = 1, GILLB200_ACT_GELU = 2, GILLB200_ACT_SILU = 3, GILLB200_ACT_GEGLU = 4 };
+enum { GILLB200_ACT_NONE = 0, GILLB200_ACT_RELU = 1, GILLB200_ACT_GELU = 2, GILLB200_ACT_SILU = 3, GILLB200_ACT_GEGLU = 4,
+       GILLB200_ACT_QUICK_GELU = 5 /* x * sigmoid(1.702 x): CLIP's activation */ };
 
 int gillb200_version(void);
 const char* gillb200_last_error(void);

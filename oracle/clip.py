@@ -1,0 +1,75 @@
+"""ORACLE (test infrastructure, not product code): CPU fp32 restatement of the CLIP vision tower the reference calls at
+gill/models.py:129-143 (`self.visual_model(pixel_values).pooler_output`, `CLIPVisionModel` of transformers==4.30.2,
+`openai/clip-vit-large-patch14`; module math in transformers/models/clip/modeling_clip.py -- not under
+/root/reference, the installed transformers 5.5 copy is the stand-in: tests/test_oracle.py pins this file against it).
+
+ViT: patch conv (stride = kernel = patch, no bias) -> [CLS | patches] + learned positions -> pre-LN -> L x
+[LN -> MHA(heads, scale hd^-0.5) -> + ; LN -> fc1 -> quick_gelu -> fc2 -> +] -> post-LN of the CLS token = pooler_output.
+State-dict names are HF's (`vision_model.*`).
+"""
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+CLIP_L14 = dict(hidden=1024, layers=24, heads=16, mlp=4096, patch=14, image=224)
+
+
+def tiny_cfg():
+    return dict(hidden=256, layers=2, heads=4, mlp=1024, patch=14, image=56)
+
+
+def init_clip(cfg, seed: int = 0) -> SD:
+    """Seeded random weights with HF-like scales (no pretrained weights exist offline)."""
+    g = torch.Generator().manual_seed(seed)
+    h, m, p = cfg["hidden"], cfg["mlp"], cfg["patch"]
+    n = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    npos = (cfg["image"] // p) ** 2 + 1
+    v = "vision_model."
+    sd = {v + "embeddings.class_embedding": n(h), v + "embeddings.patch_embedding.weight": n(h, 3, p, p),
+          v + "embeddings.position_embedding.weight": n(npos, h)}
+    for nm in ("pre_layrnorm", "post_layernorm"):
+        sd[v + nm + ".weight"] = 1 + n(h, std=0.05)
+        sd[v + nm + ".bias"] = n(h, std=0.05)
+    for i in range(cfg["layers"]):
+        l = f"{v}encoder.layers.{i}."
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[l + f"self_attn.{nm}.weight"], sd[l + f"self_attn.{nm}.bias"] = n(h, h, std=0.03), n(h)
+        sd[l + "mlp.fc1.weight"], sd[l + "mlp.fc1.bias"] = n(m, h, std=0.03), n(m)
+        sd[l + "mlp.fc2.weight"], sd[l + "mlp.fc2.bias"] = n(h, m, std=0.03), n(h)
+        for nm in ("layer_norm1", "layer_norm2"):
+            sd[l + nm + ".weight"] = 1 + n(h, std=0.05)
+            sd[l + nm + ".bias"] = n(h, std=0.05)
+    return sd
+
+
+def quick_gelu(x):
+    return x * torch.sigmoid(1.702 * x)
+
+
+def clip_vision_forward(sd: SD, pixel_values: torch.Tensor, cfg):
+    """pixel_values [B,3,S,S] -> (last_hidden_state [B,1+P,h], pooler_output [B,h])."""
+    v = "vision_model."
+    h, heads, p = cfg["hidden"], cfg["heads"], cfg["patch"]
+    B = pixel_values.shape[0]
+    x = F.conv2d(pixel_values, sd[v + "embeddings.patch_embedding.weight"], stride=p)      # [B,h,g,g]
+    x = x.flatten(2).transpose(1, 2)                                                         # [B,P,h]
+    cls = sd[v + "embeddings.class_embedding"].expand(B, 1, h)
+    x = torch.cat([cls, x], 1) + sd[v + "embeddings.position_embedding.weight"][None]
+    x = F.layer_norm(x, (h,), sd[v + "pre_layrnorm.weight"], sd[v + "pre_layrnorm.bias"], 1e-5)
+    hd = h // heads
+    for i in range(cfg["layers"]):
+        l = f"{v}encoder.layers.{i}."
+        n = F.layer_norm(x, (h,), sd[l + "layer_norm1.weight"], sd[l + "layer_norm1.bias"], 1e-5)
+        q, k, vv = (F.linear(n, sd[l + f"self_attn.{nm}.weight"], sd[l + f"self_attn.{nm}.bias"])
+                    .view(B, -1, heads, hd).transpose(1, 2) for nm in ("q_proj", "k_proj", "v_proj"))
+        a = torch.softmax((q * hd ** -0.5) @ k.transpose(-1, -2), -1) @ vv
+        a = a.transpose(1, 2).reshape(B, -1, h)
+        x = x + F.linear(a, sd[l + "self_attn.out_proj.weight"], sd[l + "self_attn.out_proj.bias"])
+        n = F.layer_norm(x, (h,), sd[l + "layer_norm2.weight"], sd[l + "layer_norm2.bias"], 1e-5)
+        f = quick_gelu(F.linear(n, sd[l + "mlp.fc1.weight"], sd[l + "mlp.fc1.bias"]))
+        x = x + F.linear(f, sd[l + "mlp.fc2.weight"], sd[l + "mlp.fc2.bias"])
+    pooled = F.layer_norm(x[:, 0], (h,), sd[v + "post_layernorm.weight"], sd[v + "post_layernorm.bias"], 1e-5)
+    return x, pooled

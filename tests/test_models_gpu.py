@@ -160,6 +160,56 @@ def test_generate_with_kv_cache_is_bit_identical(golden):
     assert torch.equal(i0, i1) and torch.equal(e0[-1], e1[-1])
 
 
+# ------------------------------------------------------------------------------------------------ CLIP vision tower
+@pytest.mark.parametrize("which", ["tiny", "vit-l14-2layers"])
+def test_clip_vision_tower_matches_oracle(which):
+    """`visual_model(pixel_values).pooler_output` (gill/models.py:135) on the B200 kernels vs the CPU
+    oracle (pinned against transformers in tests/test_oracle.py). bf16 operands, as the reference runs the tower."""
+    from gill_b200.clip import CLIPVisionB200
+    from oracle import clip as oclip
+
+    cfg = oclip.tiny_cfg() if which == "tiny" else dict(oclip.CLIP_L14, layers=2)
+    sd = {k: v.bfloat16().float() for k, v in oclip.init_clip(cfg, seed=4).items()}
+    g = torch.Generator().manual_seed(5)
+    px = torch.randn(3, 3, cfg["image"], cfg["image"], generator=g).bfloat16().float()
+    tower = CLIPVisionB200(sd, cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"], cfg["patch"], cfg["image"], device=dev)
+    out = tower(px.to(dev))
+    hs, pooled = oclip.clip_vision_forward(sd, px, cfg)
+    assert out.pooler_output.shape == pooled.shape and out.last_hidden_state.shape == hs.shape
+    assert rel(out.last_hidden_state, hs) < 1.5e-2 and rel(out.pooler_output, pooled) < 1.5e-2
+    with pytest.raises(RuntimeError):
+        tower(px)                                                   # CPU tensor: no fallback
+    # batch independence
+    one = tower(px[:1].to(dev))
+    assert torch.equal(one.pooler_output[0], out.pooler_output[0])
+
+
+def test_get_visual_embs_from_pixels_with_the_tower():
+    """GILLModel.get_visual_embs (gill/models.py:129-152) end to end from pixels: tower -> visual_embeddings / visual_fc."""
+    from gill_b200 import models
+    from gill_b200.clip import CLIPVisionB200
+    from harness.synthetic import model_args
+    from oracle import clip as oclip
+
+    cfg = oclip.tiny_cfg()
+    sd = {k: v.bfloat16().float() for k, v in oclip.init_clip(cfg, seed=6).items()}
+    tower = CLIPVisionB200(sd, cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"], cfg["patch"], cfg["image"], device=dev)
+    lm, ocfg, _ = tiny_opt()
+    img_ids = list(range(512 - 8, 512))
+    a = model_args()._replace(retrieval_token_idx=img_ids, gen_token_idx=img_ids)
+    gm = models.GILLModel(_Tok(), a, lm=lm, visual_model=tower, visual_hidden_size=cfg["hidden"]).to(dev)
+    g = torch.Generator().manual_seed(7)
+    px = torch.randn(2, 3, cfg["image"], cfg["image"], generator=g)
+    v = gm.get_visual_embs(px.to(dev), mode="captioning")
+    assert v.shape == (2, a.n_visual_tokens, ocfg["hidden"])
+    _, pooled = oclip.clip_vision_forward(sd, px.bfloat16().float(), cfg)
+    w, b = gm.visual_embeddings.weight.float().cpu(), gm.visual_embeddings.bias.float().cpu()
+    ref = (pooled @ w.T + b).view(2, a.n_visual_tokens, -1)
+    assert rel(v, ref) < 2e-2
+    r = gm.get_visual_embs(px.to(dev), mode="retrieval")
+    assert r.shape[0] == 2 and r.shape[-1] == a.ret_emb_dim
+
+
 # ------------------------------------------------------------------------------------------------ SD-1.5
 @pytest.fixture(scope="module")
 def tiny_sd():

@@ -136,3 +136,26 @@ def test_tiny_unet_and_vae_oracle_shapes():
     img = osd.vae_decode(v, torch.randn(1, 4, 16, 16, generator=g), vcfg)
     assert img.shape == (1, 3, 32, 32) and img.min() >= 0 and img.max() <= 1
     assert osd.to_uint8_nhwc(img).dtype == torch.uint8
+
+
+def test_clip_oracle_matches_transformers_clip_vision_model():
+    """oracle/clip.py is pinned by the installed transformers CLIPVisionModel (stand-in for the un-vendored 4.30.2 the
+    reference uses at gill/models.py:79,135): same weights, same pixels -> same last_hidden_state / pooler_output."""
+    import torch
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from oracle import clip as oclip
+
+    cfg = oclip.tiny_cfg()
+    hf = CLIPVisionModel(CLIPVisionConfig(hidden_size=cfg["hidden"], intermediate_size=cfg["mlp"],
+                                          num_hidden_layers=cfg["layers"], num_attention_heads=cfg["heads"],
+                                          image_size=cfg["image"], patch_size=cfg["patch"], hidden_act="quick_gelu")).eval()
+    sd = oclip.init_clip(cfg, seed=4)
+    missing, unexpected = hf.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(5)
+    px = torch.randn(2, 3, cfg["image"], cfg["image"], generator=g)
+    with torch.no_grad():
+        ref = hf(pixel_values=px)
+        hs, pooled = oclip.clip_vision_forward(sd, px, cfg)
+    assert (hs - ref.last_hidden_state).abs().max() < 2e-5
+    assert (pooled - ref.pooler_output).abs().max() < 2e-5
