@@ -96,3 +96,45 @@ def test_sharded_bank_exchange_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == {0: True, 1: True}
+
+
+def test_bank_disk_format_roundtrip_and_reference_conversion(tmp_path):
+    """flat prepared-bank shards. Conversion from the reference's pickle format reproduces
+    retrieval.prepare_bank bit for bit; any (rank, world) row block reads back exactly; paths keep their order."""
+    import pickle
+    import numpy as np
+    import torch
+    from gill_b200 import bank as gbank, retrieval
+
+    g = torch.Generator().manual_seed(3)
+    n, d = 1003, 256
+    emb = torch.randn(n, d, generator=g)
+    paths = [f"http://example.invalid/{i}.jpg" for i in range(n)]
+    files = []
+    for j, (lo, hi) in enumerate(((0, 400), (400, n))):                    # two cc3m*.npy-style pickles
+        fn = tmp_path / f"cc3m_{j}.npy"
+        with open(fn, "wb") as f:
+            pickle.dump({"paths": paths[lo:hi], "embeddings": [emb[i] for i in range(lo, hi)]}, f)
+        files.append(str(fn))
+    logit_scale = torch.tensor(2.6562, dtype=torch.bfloat16)
+    out = tmp_path / "bank"
+    gbank.convert_reference_bank(files, logit_scale, str(out), shards=3)
+    expect = retrieval.prepare_bank(emb.numpy(), logit_scale)
+    meta = gbank.bank_meta(str(out))
+    assert meta["n"] == n and meta["d"] == d and meta["shards"] == 3
+    assert meta["rows"] == [list(retrieval.shard_rows(n, 3, s)) for s in range(3)]
+    full = gbank.load_bank_rows(str(out), 0, n, device="cpu")
+    assert full.dtype == torch.bfloat16 and torch.equal(full.view(torch.int16), expect.view(torch.int16))
+    for world in (1, 2, 4, 8):                                              # any world size reads its own row block
+        got = []
+        for r in range(world):
+            t, lo, ntot = gbank.load_bank_shard(str(out), r, world, device="cpu")
+            assert ntot == n and lo == retrieval.shard_rows(n, world, r)[0]
+            got.append(t)
+        assert torch.equal(torch.cat(got).view(torch.int16), expect.view(torch.int16))
+    assert gbank.load_paths(str(out)) == paths
+    import pytest
+    with pytest.raises(ValueError):
+        gbank.load_bank_rows(str(out), 10, n + 1, device="cpu")
+    with pytest.raises(ValueError):
+        gbank.save_prepared_bank(expect.float(), paths, str(out))
