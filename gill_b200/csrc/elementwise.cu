@@ -295,6 +295,89 @@ static inline int grid_for(long long total, int block) {
   return static_cast<int>(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CLIP pre-processing of generated images on the device: uint8 NHWC [B,H,W,3] -> bicubic resize to S x S -> /255 ->
+// (x - mean) / std -> NCHW [B,3,S,S]. Replaces `img.resize((224, 224))` + the HF feature extractor of the re-rank step
+// (gill/models.py:733-737, gill/utils.py:117-119), i.e. PIL's ImagingResample for 8-bit images, restated exactly:
+// separable two-pass (horizontal, then vertical) convolution, support = 2 * scale for down-scaling, cubic a = -0.5,
+// per-output-pixel coefficient windows normalised in double, converted to 22-bit fixed point, each pass rounded and
+// clipped to uint8. One thread per output pixel recomputes the <= KS horizontal results it needs.
+constexpr int RESIZE_KS = 23;  // window size bound: ceil(2 * scale) * 2 + 1 with scale <= 5
+
+__device__ __forceinline__ double pil_bicubic(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// fixed-point coefficient window of output index `o` (libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc)
+__device__ __forceinline__ void pil_coeffs(int in_size, int out_size, int o, int* xmin_out, int* n_out, int* kk) {
+  const double scale = static_cast<double>(in_size) / out_size;
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 2.0 * filterscale;
+  const double center = (o + 0.5) * scale;
+  const double ss = 1.0 / filterscale;
+  int xmin = static_cast<int>(center - support + 0.5);
+  if (xmin < 0) xmin = 0;
+  int xmax = static_cast<int>(center + support + 0.5);
+  if (xmax > in_size) xmax = in_size;
+  xmax -= xmin;
+  double w[RESIZE_KS];
+  double ww = 0.0;
+  for (int x = 0; x < xmax; ++x) {
+    w[x] = pil_bicubic((x + xmin - center + 0.5) * ss);
+    ww += w[x];
+  }
+  for (int x = 0; x < xmax; ++x) {
+    const double k = ww != 0.0 ? w[x] / ww : w[x];
+    kk[x] = k < 0 ? static_cast<int>(-0.5 + k * (1 << 22)) : static_cast<int>(0.5 + k * (1 << 22));
+  }
+  *xmin_out = xmin;
+  *n_out = xmax;
+}
+
+__device__ __forceinline__ int pil_clip8(int v) {
+  v >>= 22;
+  return v < 0 ? 0 : v > 255 ? 255 : v;
+}
+
+__global__ void clip_preprocess_u8_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int S, float m0, float m1,
+                                          float m2, float s0, float s1, float s2, void* __restrict__ out, int out_dtype,
+                                          uint8_t* __restrict__ resized /* optional [B,S,S,3] */) {
+  pdl_wait();
+  pdl_launch();
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= 1LL * B * S * S) return;
+  const int ox = static_cast<int>(t % S), oy = static_cast<int>((t / S) % S), b = static_cast<int>(t / (1LL * S * S));
+  int kx[RESIZE_KS], ky[RESIZE_KS], x0, nx, y0, ny;
+  pil_coeffs(W, S, ox, &x0, &nx, kx);
+  pil_coeffs(H, S, oy, &y0, &ny, ky);
+  const uint8_t* base = img + static_cast<long long>(b) * H * W * 3;
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int j = 0; j < ny; ++j) {
+    const uint8_t* row = base + (static_cast<long long>(y0 + j) * W + x0) * 3;
+    int h[3] = {1 << 21, 1 << 21, 1 << 21};
+    for (int i = 0; i < nx; ++i) {
+      h[0] += row[3 * i] * kx[i];
+      h[1] += row[3 * i + 1] * kx[i];
+      h[2] += row[3 * i + 2] * kx[i];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[c] += pil_clip8(h[c]) * ky[j];  // horizontal pass result is an 8-bit image
+  }
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int v = pil_clip8(acc[c]);
+    if (resized) resized[(static_cast<long long>(b) * S * S + static_cast<long long>(oy) * S + ox) * 3 + c] = static_cast<uint8_t>(v);
+    // HF image processor: rescale in float64 -> float32, then (x - mean) / std in float32
+    const float x = static_cast<float>(static_cast<double>(v) * 0.00392156862745098);
+    store_elem(out, ((static_cast<long long>(b) * 3 + c) * S + oy) * S + ox, (x - mean[c]) / sd[c], out_dtype);
+  }
+}
+
 }  // namespace gb
 
 using namespace gb;
@@ -406,5 +489,19 @@ extern "C" int gillb200_channel_mix(const float* x, int cin, const float* w, con
   GB_CUDA(launch_pdl(channel_mix_kernel, dim3(grid_for(n * cout, 256)), dim3(256), 0, stream, x, cin, w, b, cout, n, out, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_clip_preprocess_u8(const void* img, int B, int H, int W, int S, const float* mean3,
+                                           const float* std3, void* out, int out_dtype, void* resized_u8,
+                                           void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(img && out && mean3 && std3 && B > 0 && H > 0 && W > 0 && S > 0, "clip_preprocess_u8: bad args");
+  GB_CHECK_ARG(H <= 5 * S && W <= 5 * S, "clip_preprocess_u8: down-scaling factor above 5 (H=%d W=%d S=%d)", H, W, S);
+  GB_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "clip_preprocess_u8: bad out dtype");
+  GB_CUDA(launch_pdl(clip_preprocess_u8_kernel, dim3(grid_for(1LL * B * S * S, 128)), dim3(128), 0, stream,
+                     reinterpret_cast<const uint8_t*>(img), B, H, W, S, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
+                     std3[2], out, out_dtype, reinterpret_cast<uint8_t*>(resized_u8)));
+  GB_COUNT_LAUNCH(1);
   return 0;
 }

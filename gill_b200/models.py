@@ -431,17 +431,34 @@ class GILL(nn.Module):
                     if self.load_sd:                                                           # models.py:724-731
                         gen_max_bs = 8
                         gen_images = []
+                        rerank = self.emb_matrix is not None and m.visual_model is not None
+                        # our pipeline can hand the uint8 images over on the device: the re-rank pre-processing
+                        # (PIL-exact bicubic 512 -> 224 + CLIP normalisation) then runs there too, models.py:733-737
+                        on_device = rerank and m.feature_extractor is None and hasattr(self.sd_pipe, "vae")
+                        gen_u8 = []
                         for i in range(0, self.num_gen_images, gen_max_bs):
-                            gen_images.extend(self.sd_pipe(
+                            res = self.sd_pipe(
                                 prompt_embeds=gen_emb[i:i + gen_max_bs], generator=generator,
-                                guidance_scale=guidance_scale, num_inference_steps=num_inference_steps).images)
-                        if self.emb_matrix is not None and m.visual_model is not None:         # models.py:733-751
-                            all_gen_pixels = []
-                            for img in gen_images:
-                                pv = m.feature_extractor(img.resize((224, 224)).convert("RGB"),
-                                                         return_tensors="pt").pixel_values[0, ...]
-                                all_gen_pixels.append(pv.to(device=m.lm.dev, dtype=m.lm.dt))
-                            all_gen_pixels = torch.stack(all_gen_pixels, dim=0)
+                                guidance_scale=guidance_scale, num_inference_steps=num_inference_steps,
+                                **({"output_type": "uint8"} if on_device else {})).images
+                            if on_device:
+                                from PIL import Image
+
+                                gen_u8.append(res)
+                                gen_images.extend(Image.fromarray(a) for a in res.cpu().numpy())
+                            else:
+                                gen_images.extend(res)
+                        if rerank:                                                             # models.py:733-751
+                            if on_device:
+                                all_gen_pixels = ops.clip_preprocess_u8(torch.cat(gen_u8, 0).contiguous(), 224,
+                                                                        out_dtype=m.lm.dt)
+                            else:
+                                all_gen_pixels = []
+                                for img in gen_images:
+                                    pv = m.feature_extractor(img.resize((224, 224)).convert("RGB"),
+                                                             return_tensors="pt").pixel_values[0, ...]
+                                    all_gen_pixels.append(pv.to(device=m.lm.dev, dtype=m.lm.dt))
+                                all_gen_pixels = torch.stack(all_gen_pixels, dim=0)
                             gen_visual_embs = m.get_visual_embs(all_gen_pixels, mode="retrieval")
                             gen_visual_embs = gen_visual_embs / gen_visual_embs.norm(dim=-1, keepdim=True)
                             gen_visual_embs = gen_visual_embs.type(self.emb_matrix.dtype)
@@ -453,7 +470,7 @@ class GILL(nn.Module):
                             else:
                                 image_outputs["gen"] = [(gen_images[0], gen_rank_scores.item())]
                         else:
-                            # no bank (reference behaviour, models.py:753) or no CLIP tower to re-rank with (§8f-1)
+                            # no bank (reference behaviour, models.py:753) or no CLIP tower to re-rank with
                             image_outputs["gen"] = [(gen_images[0], 0)]
                     else:
                         image_outputs["gen"] = [gen_emb]                                       # models.py:755

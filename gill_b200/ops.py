@@ -386,6 +386,26 @@ def image_to_u8(x: torch.Tensor, channels: int = 3) -> torch.Tensor:
     return out
 
 
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # openai/clip-vit-large-patch14 preprocessor_config.json
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def clip_preprocess_u8(img_u8: torch.Tensor, size: int = 224, out_dtype: torch.dtype = torch.bfloat16,
+                       mean=CLIP_MEAN, std=CLIP_STD, return_resized: bool = False):
+    """uint8 NHWC [B,H,W,3] on the device -> CLIP pixel_values NCHW [B,3,size,size]: PIL-exact bicubic resize
+    (`img.resize((224, 224))`, gill/models.py:735) + rescale + normalise (HF feature extractor, gill/utils.py:117-119)."""
+    assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.is_contiguous() and img_u8.shape[-1] == 3
+    B, H, W, _ = img_u8.shape
+    out = torch.empty((B, 3, size, size), device=img_u8.device, dtype=out_dtype)
+    rz = torch.empty((B, size, size, 3), device=img_u8.device, dtype=torch.uint8) if return_resized else None
+    m3 = (ctypes.c_float * 3)(*mean)
+    s3 = (ctypes.c_float * 3)(*std)
+    with _P("clip_preprocess_u8"):
+        check(lib().gillb200_clip_preprocess_u8(img_u8.data_ptr(), B, H, W, size, m3, s3, out.data_ptr(), _DT[out_dtype],
+                                                _ptr(rz), _stream()), "gillb200_clip_preprocess_u8")
+    return (out, rz) if return_resized else out
+
+
 def l2norm_rows(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     _chk2d(x, "x")
     assert x.dtype == torch.float32

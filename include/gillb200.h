@@ -176,6 +176,12 @@ int gillb200_plms_step(const void* eps_pair, int eps_dtype, float guidance, floa
                        float c_sample, float c_eps, float* latents, float* cur_sample, void* lat16_pair, int lat16_dtype,
                        long long n, void* stream);
 int gillb200_image_to_u8(const void* x, int dtype, long long pixels, int ldx, int channels, void* out, void* stream);
+/* CLIP pre-processing of generated images for the re-rank step (gill/models.py:733-737 `img.resize((224,224))` + the HF
+ * feature extractor, gill/utils.py:117-119): uint8 NHWC [B,H,W,3] -> PIL-exact bicubic resize to S x S (8-bit two-pass
+ * fixed-point ImagingResample) -> /255 -> (x - mean)/std -> NCHW [B,3,S,S] in out_dtype. mean3 / std3 are HOST pointers.
+ * resized_u8 (optional, device) receives the intermediate uint8 [B,S,S,3] image. */
+int gillb200_clip_preprocess_u8(const void* img, int B, int H, int W, int S, const float* mean3, const float* std3,
+                                void* out, int out_dtype, void* resized_u8, void* stream);
 int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int n, void* out, long long ldo, int out_dtype,
                          void* stream);
 int gillb200_cast_add(const void* x, int x_dtype, const void* y, int y_dtype, long long y_period, void* out,

@@ -73,3 +73,66 @@ def clip_vision_forward(sd: SD, pixel_values: torch.Tensor, cfg):
         x = x + F.linear(f, sd[l + "mlp.fc2.weight"], sd[l + "mlp.fc2.bias"])
     pooled = F.layer_norm(x[:, 0], (h,), sd[v + "post_layernorm.weight"], sd[v + "post_layernorm.bias"], 1e-5)
     return x, pooled
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pre-processing of generated images for the re-rank step (gill/models.py:733-737; gill/utils.py:117-119):
+# PIL `img.resize((224, 224))` (bicubic) + HF CLIP feature extractor (rescale 1/255, normalise). The resize is restated
+# from Pillow's libImaging/Resample.c (8-bit path: double coefficients -> 22-bit fixed point, horizontal then vertical
+# pass, each rounded and clipped to uint8); tests/test_oracle.py pins it bit-exactly against PIL itself.
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def _pil_bicubic(x: float) -> float:
+    a = -0.5
+    x = abs(x)
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def _pil_coeffs(in_size: int, out_size: int):
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    out = []
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [_pil_bicubic((x + xmin - center + 0.5) / filterscale) for x in range(xmax)]
+        ww = sum(w)
+        k = [wi / ww if ww != 0.0 else wi for wi in w]
+        out.append((xmin, [int(-0.5 + ki * (1 << 22)) if ki < 0 else int(0.5 + ki * (1 << 22)) for ki in k]))
+    return out
+
+
+def pil_bicubic_resize_u8(img, size: int):
+    """img: uint8 numpy [H,W,3] -> uint8 [size,size,3], bit-identical to PIL.Image.resize((size,size), BICUBIC)."""
+    import numpy as np
+
+    H, W, _ = img.shape
+    a = img.astype(np.int64)
+    tmp = np.empty((H, size, 3), dtype=np.int64)
+    for o, (x0, kk) in enumerate(_pil_coeffs(W, size)):
+        acc = (1 << 21) + (a[:, x0:x0 + len(kk), :] * np.asarray(kk, dtype=np.int64)[None, :, None]).sum(1)
+        tmp[:, o, :] = np.clip(acc >> 22, 0, 255)
+    out = np.empty((size, size, 3), dtype=np.int64)
+    for o, (y0, kk) in enumerate(_pil_coeffs(H, size)):
+        acc = (1 << 21) + (tmp[y0:y0 + len(kk), :, :] * np.asarray(kk, dtype=np.int64)[:, None, None]).sum(0)
+        out[o] = np.clip(acc >> 22, 0, 255)
+    return out.astype(np.uint8)
+
+
+def clip_preprocess(img, size: int = 224):
+    """uint8 [H,W,3] -> float32 [3,size,size] pixel_values (HF CLIPImageProcessor: rescale in float64 -> float32, then
+    (x - mean) / std in float32)."""
+    import numpy as np
+
+    r = pil_bicubic_resize_u8(img, size)
+    x = (r.astype(np.float64) * (1 / 255)).astype(np.float32)
+    x = (x - np.asarray(CLIP_MEAN, dtype=np.float32)) / np.asarray(CLIP_STD, dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 1)))

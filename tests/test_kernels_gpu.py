@@ -376,3 +376,24 @@ def test_bad_arguments_raise(ops):
         ops.gemm(a, b)
     with pytest.raises(GillB200Error):
         ops.topk_scores(torch.randn(64, 64, device=dev).bfloat16(), torch.randn(2, 64, device=dev).bfloat16(), 17)
+
+
+@pytest.mark.parametrize("hw", [(512, 512), (300, 400), (96, 128)])
+def test_clip_preprocess_u8_is_pil_exact(ops, hw):
+    """Device pre-processing of generated images for the re-rank step == PIL `img.resize((224, 224))` bit for bit, and
+    == the HF CLIP normalisation to fp32 rounding (gill/models.py:733-737, gill/utils.py:117-119)."""
+    import numpy as np
+    from PIL import Image
+    from oracle import clip as oclip
+
+    h, w = hw
+    rng = np.random.default_rng(1)
+    imgs = rng.integers(0, 256, size=(3, h, w, 3), dtype=np.uint8)
+    imgs[:, : h // 3] = (np.linspace(0, 255, w)[None, None, :, None]).astype(np.uint8)
+    pv, rz = ops.clip_preprocess_u8(torch.from_numpy(imgs).to(dev), 224, out_dtype=torch.float32, return_resized=True)
+    for b in range(3):
+        ref = np.asarray(Image.fromarray(imgs[b]).resize((224, 224)).convert("RGB"))
+        assert np.array_equal(rz[b].cpu().numpy(), ref)
+        assert (pv[b].cpu() - oclip.clip_preprocess(imgs[b], 224)).abs().max() < 1e-6
+    pv16 = ops.clip_preprocess_u8(torch.from_numpy(imgs).to(dev), 224)
+    assert pv16.dtype == torch.bfloat16 and torch.equal(pv16, pv.bfloat16())

@@ -348,6 +348,34 @@ def test_retrieval_branch_inside_the_surface(gill_small):
         gill.emb_matrix, gill.path_array = None, None
 
 
+def test_generated_images_are_reranked_with_the_clip_tower(gill_small):
+    """gill/models.py:733-751 with a vision tower present: generated images are scored against the retrieval embedding
+    (device-side PIL-exact resize -> CLIPVisionB200 -> visual_fc -> cosine) and returned best first."""
+    from PIL import Image
+    from gill_b200.clip import CLIPVisionB200
+    from oracle import clip as oclip, retrieval as orc
+
+    gill = gill_small
+    m = gill.model
+    cfg = dict(oclip.CLIP_L14, layers=1)
+    tower = CLIPVisionB200(oclip.init_clip(cfg, seed=8), cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"],
+                           cfg["patch"], cfg["image"], device=dev)
+    gill.emb_matrix = orc.synthetic_bank_chunk(0, 5000, 256).to(dev)
+    gill.path_array = [f"http://127.0.0.1:9/{i}.jpg" for i in range(5000)]
+    old = (m.visual_model, gill.num_gen_images)
+    m.visual_model, gill.num_gen_images = tower, 3
+    try:
+        out = gill.generate_for_images_and_texts(["a dog"], num_words=2, gen_scale_factor=1e5, num_inference_steps=2)
+        gen = out[1]["gen"]
+        assert len(gen) == 3 and all(isinstance(im, Image.Image) and im.size[0] == im.size[1] for im, _ in gen)
+        scores = [sc for _, sc in gen]
+        assert all(np.isfinite(scores)) and scores == sorted(scores, reverse=True)
+        assert all(abs(sc) <= 1.0 + 1e-2 for sc in scores)                      # cosine of two unit vectors
+    finally:
+        m.visual_model, gill.num_gen_images = old
+        gill.emb_matrix, gill.path_array = None, None
+
+
 def test_emit_images_batch_equals_per_prompt_calls(gill_small):
     """The batched path is the per-sample loop of generate_for_images_and_texts: same mapper embeddings per prompt."""
     gill = gill_small

@@ -159,3 +159,21 @@ def test_clip_oracle_matches_transformers_clip_vision_model():
         hs, pooled = oclip.clip_vision_forward(sd, px, cfg)
     assert (hs - ref.last_hidden_state).abs().max() < 2e-5
     assert (pooled - ref.pooler_output).abs().max() < 2e-5
+
+
+def test_clip_preprocess_oracle_is_bit_exact_with_pil():
+    """The restated 8-bit bicubic resample equals PIL's `img.resize((224, 224))` (gill/models.py:735) bit for bit, for the
+    512 -> 224 case of the pipeline, a non-square input and an up-scaling one."""
+    import numpy as np
+    from PIL import Image
+    from oracle import clip as oclip
+
+    rng = np.random.default_rng(0)
+    for (h, w, s) in ((512, 512, 224), (300, 400, 224), (96, 128, 224), (64, 64, 28)):
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        img[: h // 3] = (np.linspace(0, 255, w)[None, :, None]).astype(np.uint8)       # smooth band + noise
+        ref = np.asarray(Image.fromarray(img).resize((s, s)).convert("RGB"))
+        got = oclip.pil_bicubic_resize_u8(img, s)
+        assert np.array_equal(got, ref), (h, w, s, int(np.abs(got.astype(int) - ref.astype(int)).max()))
+    pv = oclip.clip_preprocess(img, 28)
+    assert pv.shape == (3, 28, 28) and pv.dtype == torch.float32
