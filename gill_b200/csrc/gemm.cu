@@ -307,10 +307,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   if (a->cta_pair == 2) {
     pair = true;
   } else if (!want_sk && a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
-    // measured: the pair kernel wins (+3..17 %) only when the K loop is long enough to amortise the cluster
-    // handshakes, and loses on short-K, epilogue-heavy shapes
+    // measured (tools/gpu_sweep_shapes.py, with the staged epilogue): the pair kernel wins 3..8 % from 10 k-blocks up
+    // (K >= 640: M16384 N5120 121 -> 115 us, M4096 N10240 97 -> 91 us) and loses on the K = 320 linears of the 64x64
+    // level, whose time is all epilogue (152 vs 170 us)
     const long long tiles2 = 1LL * ((a->M + 255) / 256) * ((a->N + bn - 1) / bn);
-    pair = tiles2 >= (num_sms() / 2) * 3 / 4 && p.num_k_blocks >= 32;
+    pair = tiles2 >= (num_sms() / 2) * 3 / 4 && p.num_k_blocks >= (bn == 256 ? 10 : 32);
   }
   if (pair) GB_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "cta_pair needs block_n in {64,128,160,256}");
   {
