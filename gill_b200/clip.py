@@ -84,3 +84,44 @@ class CLIPVisionB200:
     def __call__(self, pixel_values=None, **kw):
         hs, pooled = self.forward(pixel_values)
         return SimpleNamespace(last_hidden_state=hs, pooler_output=pooled)
+
+
+class SafetyCheckerB200:
+    """`StableDiffusionSafetyChecker` (diffusers) for `sd_pipe` (gill/custom_sd.py:375-383): CLIP tower -> visual_projection
+    -> cosine against the concept embeddings -> thresholds; flagged images are blacked out by the caller. Built from the
+    checker's own state dict (`vision_model.vision_model.*`, `visual_projection.weight`, `concept_embeds`,
+    `special_care_embeds`, `*_weights`). Takes the generated uint8 images on the device: the feature-extractor step
+    (PIL bicubic resize + normalise) is `ops.clip_preprocess_u8`."""
+
+    def __init__(self, sd: SD, hidden: int = 1024, layers: int = 24, heads: int = 16, mlp: int = 4096, patch: int = 14,
+                 image: int = 224, device="cuda", dtype=torch.float16):
+        vsd = {k[len("vision_model."):]: v for k, v in sd.items() if k.startswith("vision_model.")}
+        self.tower = CLIPVisionB200(vsd, hidden, layers, heads, mlp, patch, image, device=device, dtype=dtype)
+        self.dev, self.dt, self.image = self.tower.dev, dtype, image
+        self.proj = sd["visual_projection.weight"].to(self.dev, dtype).contiguous()
+        embeds = torch.cat([sd["special_care_embeds"], sd["concept_embeds"]], 0).float()
+        self.n_special = sd["special_care_embeds"].shape[0]
+        self.embeds = (embeds / embeds.norm(dim=-1, keepdim=True)).to(self.dev, dtype).contiguous()   # [3+17, 768]
+        self.special_thr = sd["special_care_embeds_weights"].float().tolist()
+        self.thr = sd["concept_embeds_weights"].float().tolist()
+
+    @torch.no_grad()
+    def __call__(self, images_u8: torch.Tensor):
+        """images_u8: uint8 NHWC [B,H,W,3] (square) on the device -> list of bool (True = flagged)."""
+        B, H, W, _ = images_u8.shape
+        if H != W:
+            raise ValueError("SafetyCheckerB200 expects square images (the CLIP processor's centre crop is not built)")
+        px = ops.clip_preprocess_u8(images_u8.contiguous(), self.image, out_dtype=self.dt)
+        _, pooled = self.tower.forward(px)
+        emb = ops.gemm(pooled.to(self.dt).contiguous(), self.proj, out_dtype=torch.float32)       # [B, 768]
+        emb = ops.l2norm_rows(emb, self.dt)
+        cos = ops.gemm(emb, self.embeds, out_dtype=torch.float32).cpu()                            # [B, 3+17]
+        flags = []
+        for i in range(B):                                                                         # host logic, as upstream
+            adjustment = 0.0
+            for c in range(self.n_special):
+                if round(cos[i, c].item() - self.special_thr[c] + adjustment, 3) > 0:
+                    adjustment = 0.01
+            flags.append(any(round(cos[i, self.n_special + c].item() - self.thr[c] + adjustment, 3) > 0
+                             for c in range(len(self.thr))))
+        return flags

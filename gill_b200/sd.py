@@ -470,10 +470,11 @@ class VAEDecoderB200:
 class StableDiffusionB200:
     """Callable with the `sd_pipe` signature GILL uses (gill/models.py:730; gill/custom_sd.py:477-496)."""
 
-    def __init__(self, unet: UNetB200, vae: VAEDecoderB200, negative_prompt_embeds: torch.Tensor):
+    def __init__(self, unet: UNetB200, vae: VAEDecoderB200, negative_prompt_embeds: torch.Tensor, safety_checker=None):
         """negative_prompt_embeds: the (77,768) CLIP-text embedding of "" that gill/custom_sd.py:319-357 recomputes on
         every call; it is a constant of the pipeline, so it is supplied once here."""
         self.unet, self.vae = unet, vae
+        self.safety_checker = safety_checker   # optional gill_b200.clip.SafetyCheckerB200 (custom_sd.py:375-383)
         self.device = unet.dev
         self.neg = negative_prompt_embeds.to(unet.dev, unet.dt).reshape(1, 77, -1)
         self.latent_hw = 64
@@ -559,11 +560,23 @@ class StableDiffusionB200:
             raise ValueError(f"Unexpected latents shape, got {tuple(latents.shape)}, expected {shape}")
         lat = self.denoise(prompt_embeds.to(self.device), latents.to(self.device), guidance_scale, num_inference_steps)
         u8 = self.vae.decode_u8(lat)                                                            # custom_sd.py:654
+        nsfw = None
+        if self.safety_checker is not None:                                                      # custom_sd.py:657
+            nsfw = self.safety_checker(u8)
+            for i, bad in enumerate(nsfw):
+                if bad:
+                    u8[i].zero_()                                                                # black image
         if output_type == "uint8":
-            return _Out(u8)
+            o = _Out(u8)
+            o.nsfw_content_detected = nsfw
+            return o
         arr = u8.cpu().numpy()                                                                  # custom_sd.py:391
         if output_type == "np":
-            return _Out(arr.astype("float32") / 255.0)
+            o = _Out(arr.astype("float32") / 255.0)
+            o.nsfw_content_detected = nsfw
+            return o
         from PIL import Image
 
-        return _Out([Image.fromarray(a) for a in arr])                                           # custom_sd.py:661
+        o = _Out([Image.fromarray(a) for a in arr])                                              # custom_sd.py:661
+        o.nsfw_content_detected = nsfw
+        return o

@@ -210,6 +210,47 @@ def test_get_visual_embs_from_pixels_with_the_tower():
     assert r.shape[0] == 2 and r.shape[-1] == a.ret_emb_dim
 
 
+def test_safety_checker_matches_oracle_and_blacks_out_flagged_images(tiny_sd):
+    """custom_sd.py:375-383 / :657: CLIP tower -> projection -> concept cosines -> thresholds, on generated uint8 images;
+    flagged images come back black. Oracle module math is unpinned (diffusers is not installable), see oracle/safety.py."""
+    from gill_b200 import ops
+    from gill_b200.clip import SafetyCheckerB200
+    from oracle import clip as oclip, safety as osafe
+
+    cfg = oclip.tiny_cfg()
+    sd = {k: (v.half().float() if v.dim() > 1 else v) for k, v in osafe.init_safety_checker(cfg, seed=9).items()}
+    sd["concept_embeds_weights"] = torch.full((17,), 0.0725)      # between the seeded images' concept scores
+    chk = SafetyCheckerB200(sd, cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"], cfg["patch"], cfg["image"], device=dev)
+    g = torch.Generator().manual_seed(10)
+    H = 128
+    imgs = torch.zeros(6, H, H, 3, dtype=torch.uint8)
+    imgs[0] = torch.randint(0, 256, (H, H, 3), generator=g, dtype=torch.uint8)
+    imgs[2] = 255
+    imgs[3] = torch.linspace(0, 255, H)[None, :, None].expand(H, H, 3).to(torch.uint8)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(H), indexing="ij")
+    imgs[4] = (((yy // 16 + xx // 16) % 2) * 255)[..., None].expand(H, H, 3).to(torch.uint8)
+    imgs[5, ..., 0], imgs[5, ..., 1], imgs[5, ..., 2] = 230, 20, 40
+    px = ops.clip_preprocess_u8(imgs.to(dev), cfg["image"], out_dtype=torch.float32).cpu()
+    ref_flags, sp, cs = osafe.safety_check(sd, px.half().float(), cfg)
+    got = chk(imgs.to(dev))
+    # decisions may only differ where a score sits within fp16 noise of its threshold
+    margin = torch.cat([sp - sd["special_care_embeds_weights"], cs - sd["concept_embeds_weights"]], 1).abs().min(dim=1).values
+    for i in range(6):
+        assert got[i] == ref_flags[i] or margin[i] < 5e-3, (i, got[i], ref_flags[i], margin[i])
+    assert any(ref_flags) and not all(ref_flags) and any(got) and not all(got)
+    # wired into the pipeline: flagged outputs are black, the flag list is returned
+    pipe = tiny_sd[0]
+    pipe.safety_checker = lambda u8: [True] + [False] * (u8.shape[0] - 1)
+    try:
+        gen = torch.Generator(device=dev).manual_seed(3)
+        out = pipe(prompt_embeds=torch.randn(2, 77, 768, device=dev), generator=gen, num_inference_steps=2,
+                   output_type="uint8")
+        assert out.nsfw_content_detected == [True, False]
+        assert int(out.images[0].max()) == 0 and int(out.images[1].max()) > 0
+    finally:
+        pipe.safety_checker = None
+
+
 # ------------------------------------------------------------------------------------------------ SD-1.5
 @pytest.fixture(scope="module")
 def tiny_sd():
