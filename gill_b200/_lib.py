@@ -40,6 +40,7 @@ class GemmArgs(ctypes.Structure):
         ("cta_pair", _c_int),
         ("sk_workspace", _c_void_p),
         ("stream_k", _c_int),
+        ("stats_out", _c_void_p),
         ("conv_stride", _c_int),
     ]
 

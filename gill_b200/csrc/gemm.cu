@@ -412,6 +412,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   }
 
   // ---- stream-K (see want_sk above): only the 1-CTA kernel with the staged epilogue
+  if (a->stats_out) {
+    GB_CHECK_ARG(p.epi_tma && a->act != ACT_GEGLU && a->out_dtype != DT_F32 && a->M % 32 == 0 && a->N % 32 == 0,
+                 "stats_out needs the staged epilogue: 16-bit output, 16-byte aligned rows, M %% 32 == 0, N %% 32 == 0, no GEGLU");
+    p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  }
   if (want_sk && !pair && p.epi_tma) {
     const long long tiles = 1LL * ((a->M + BLOCK_M - 1) / BLOCK_M) * ((a->N + bn - 1) / bn);
     const int sms = num_sms();

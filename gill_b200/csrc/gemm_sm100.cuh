@@ -76,6 +76,11 @@ struct alignas(64) GemmParams {
   int sk_per;
   float* sk_ws;
   int* sk_flags;
+  // optional GroupNorm statistics of the OUTPUT (staged epilogue, 16-bit output): per 32-row slab and output column the
+  // sum and the sum of squares of the rounded values, stats_out[(row / 32) * N_out + col] = {sum, sumsq}. The consumer
+  // (gillb200_groupnorm_from_stats) reduces slabs and channels per (sample, group) -- the separate statistics pass
+  // over the activation (one full read) disappears.
+  float2* stats_out;
   int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
@@ -842,6 +847,22 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         epi_f16_units<4, VAR == EV_BIAS_RES>(sbuf, lane, 0, f);
       }
 
+      if (p.stats_out != nullptr) {
+        // lane = column of this panel: read the 32 rounded values of the column back from the staged panel
+        __syncwarp();
+        const int su = lane >> 3, se = (lane & 7) * 2;
+        const bool sbf = p.out_dtype == DT_BF16;
+        float cs = 0.f, cq = 0.f;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+          const uint16_t hv = *reinterpret_cast<const uint16_t*>(sbuf + rr * 64 + ((su ^ ((rr >> 1) & 3)) << 4) + se);
+          const float xv = sbf ? __uint_as_float(static_cast<uint32_t>(hv) << 16) : __half2float(__ushort_as_half(hv));
+          cs += xv;
+          cq = fmaf(xv, xv, cq);
+        }
+        p.stats_out[static_cast<size_t>(row0 >> 5) * n_out_total + (no0 + pnl * EPI_PANEL_COLS + lane)] =
+            make_float2(cs, cq);
+      }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {

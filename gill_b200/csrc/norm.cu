@@ -370,6 +370,50 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int chunks
   }
 }
 
+// GroupNorm statistics from the producers' epilogues: stats[(sample * slabs + s) * Csrc + c] = {sum, sumsq} of channel c
+// over the 32 pixels of slab s (gemm stats_out). One CTA per (group, sample) adds slabs x channels-of-the-group in a
+// fixed order (deterministic) and writes the group's part of the per-channel affine y = x * scale + shift.
+__global__ void __launch_bounds__(128) gn_finalize_stats_kernel(const float2* __restrict__ st0, int C0,
+                                                                const float2* __restrict__ st1, int C1, int slabs,
+                                                                int G, int HW, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, float eps,
+                                                                float* __restrict__ scale_shift /* [B, 2, C] */) {
+  pdl_wait();
+  pdl_launch();
+  __shared__ float rs[128], rq[128];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C = C0 + C1, cpg = C / G;
+  const int n = slabs * cpg;
+  float s = 0.f, q = 0.f;
+  for (int i = threadIdx.x; i < n; i += 128) {
+    const int sl = i / cpg, c = g * cpg + (i - sl * cpg);
+    const float2 v = c < C0 ? st0[(static_cast<size_t>(b) * slabs + sl) * C0 + c]
+                            : st1[(static_cast<size_t>(b) * slabs + sl) * C1 + (c - C0)];
+    s += v.x;
+    q += v.y;
+  }
+  rs[threadIdx.x] = s;
+  rq[threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      rs[threadIdx.x] += rs[threadIdx.x + o];
+      rq[threadIdx.x] += rq[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  const float cnt = static_cast<float>(cpg) * HW;
+  const float mean = rs[0] / cnt;
+  const float var = fmaxf(rq[0] / cnt - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  float* sc = scale_shift + static_cast<long long>(b) * 2 * C;
+  for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 128) {
+    const float a = rstd * w[c];
+    sc[c] = a;
+    sc[C + c] = bias[c] - mean * a;
+  }
+}
+
 // Elementwise normalise (+SiLU). Thread t owns channel vector v = t % nvec (scale/shift live in 16 registers) and
 // walks pixels with stride (256 / nvec): 256 consecutive threads touch 256 consecutive 16-byte vectors.
 __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int HW, const float* __restrict__ scale_shift,
@@ -553,6 +597,37 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   GB_CUDA(launch_pdl(gn_apply_kernel, dim3(dim3(blocks, B)), dim3(256), 0, stream, src, dtype, HW, scale_shift, silu, out, out_dtype, pix_per_block));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_groupnorm_from_stats(const void* x0, int C0, const void* stats0, const void* x1, int C1,
+                                             const void* stats1, int dtype, int B, int HW, int G, const float* w,
+                                             const float* b, float eps, int silu, void* out, int out_dtype,
+                                             void* workspace, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(x0 && stats0 && w && b && out && workspace, "null pointer");
+  const int C = C0 + C1;
+  GB_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % G == 0 && G <= 64 && C <= 4096, "groupnorm: C0=%d C1=%d G=%d", C0, C1, G);
+  GB_CHECK_ARG(C1 == 0 || (x1 != nullptr && stats1 != nullptr), "groupnorm: second source / its statistics missing");
+  GB_CHECK_ARG(HW % 32 == 0, "groupnorm_from_stats: HW=%d must be a multiple of the 32-row statistics slabs", HW);
+  GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16, "groupnorm_from_stats: 16-bit activations only");
+  GB_CHECK_ARG(B <= 1024, "groupnorm: batch %d > 1024", B);
+  GnSrc src{x0, x1, C0, C1};
+  float* partial = reinterpret_cast<float*>(workspace) + 1024;
+  float* scale_shift = partial + 128LL * B * G * 2;  // same workspace layout as gillb200_groupnorm
+  GB_CUDA(launch_pdl(gn_finalize_stats_kernel, dim3(G, B), dim3(128), 0, stream, reinterpret_cast<const float2*>(stats0), C0,
+                     reinterpret_cast<const float2*>(stats1), C1, HW / 32, G, HW, w, b, eps, scale_shift));
+  GB_COUNT_LAUNCH(1);
+  const int nvec = C / 8;
+  int pix_per_block = (65536 + C - 1) / C;
+  const int sgs = nvec >= 256 ? 1 : 256 / nvec;
+  const int want_blocks = (8 * num_sms() + B - 1) / B;
+  if (pix_per_block * want_blocks > HW) pix_per_block = (HW + want_blocks - 1) / want_blocks;
+  pix_per_block = ((pix_per_block + 4 * sgs - 1) / (4 * sgs)) * (4 * sgs);
+  const int blocks = (HW + pix_per_block - 1) / pix_per_block;
+  GB_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks, B), dim3(256), 0, stream, src, dtype, HW, scale_shift, silu, out, out_dtype,
+                     pix_per_block));
+  GB_COUNT_LAUNCH(1);
   return 0;
 }
 

@@ -79,6 +79,14 @@ def _streamk_ws(device: torch.device) -> int:
     return ws.data_ptr()
 
 
+def _attach_stats(g: GemmArgs, M: int, n_out: int, device) -> torch.Tensor:
+    """GroupNorm statistics of the output, produced by the GEMM epilogue: float [M/32, N, 2] = per 32-row slab and column
+    {sum, sum of squares}. Returned tensor is hung on the output as `.gn_stats` (views must carry it over by hand)."""
+    st = torch.empty((M // 32, n_out, 2), device=device, dtype=torch.float32)
+    g.stats_out = st.data_ptr()
+    return st
+
+
 def gemm(
     a: torch.Tensor,
     b: torch.Tensor,
@@ -99,6 +107,7 @@ def gemm(
     cta_pair: int = 0,
     tile_order: int = 0,
     stream_k: int = 0,
+    stats: bool = False,
 ) -> torch.Tensor:
     """out = act(alpha * a @ b.T + bias + rowbias) + residual     (a: [M,K], b: [N,K], 16-bit; fp32 accumulate).
 
@@ -137,6 +146,8 @@ def gemm(
     g.stream_k = stream_k
     if stream_k != 1:
         g.sk_workspace = _streamk_ws(a.device)
+    if stats:
+        out.gn_stats = _attach_stats(g, M, n_out, a.device)
     ktot = K + (g.k2 if a2_mode == 1 else 0)
     with _P("gemm" if a2_mode != 2 else "gemm_split", 2.0 * M * N * ktot * (2 if a2_mode == 2 else 1),
             2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out, f"M{M} N{N} K{ktot} {act or ''}"):
@@ -160,6 +171,7 @@ def conv3x3(
     tile_order: int = 0,
     stream_k: int = 0,
     stride: int = 1,
+    stats: bool = False,
 ) -> torch.Tensor:
     """3x3 / pad 1 convolution (stride 1 or 2) as an implicit GEMM.
 
@@ -202,6 +214,8 @@ def conv3x3(
     g.stream_k = stream_k
     if stream_k != 1:
         g.sk_workspace = _streamk_ws(x.device)
+    if stats:
+        out.gn_stats = _attach_stats(g, B * H * W, N, x.device)
     with _P("conv3x3", 2.0 * B * H * W * N * (9 * C + (g.k2 or 0)), 2.0 * (B * H * W * C + N * 9 * C + B * H * W * N),
             f"B{B} {H}x{W} C{C}->{N}"):
         check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3)")
@@ -290,6 +304,7 @@ def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float = 1e
 
 
 _gn_ws = {}
+USE_EPILOGUE_GN_STATS = True   # groupnorm() uses `.gn_stats` left by the producing GEMM when present (A/B: set False)
 
 
 def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, eps: float, *, silu: bool = False,
@@ -307,6 +322,16 @@ def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, ep
         # zero-initialised once: the kernel's per-sample arrival counters reset themselves after every launch
         ws = torch.zeros(lib().gillb200_groupnorm_workspace_bytes(B, groups), device=x.device, dtype=torch.uint8)
         _gn_ws[key] = ws
+    st0, st1 = getattr(x, "gn_stats", None), (getattr(x2, "gn_stats", None) if x2 is not None else None)
+    if USE_EPILOGUE_GN_STATS and st0 is not None and (x2 is None or st1 is not None) and (H * W) % 32 == 0 \
+            and x.dtype != torch.float32:
+        # the producing GEMMs already left per-slab channel sums: only the (sample, group) reduction + elementwise pass
+        with _P("groupnorm", 0.0, (x.element_size() + out.element_size()) * B * H * W * (C0 + C1), f"B{B} {H}x{W} C{C0 + C1} (stats from epilogue)"):
+            check(lib().gillb200_groupnorm_from_stats(x.data_ptr(), C0, st0.data_ptr(), _ptr(x2), C1, _ptr(st1), _DT[x.dtype],
+                                                      B, H * W, groups, w.data_ptr(), b.data_ptr(), eps, int(silu),
+                                                      out.data_ptr(), _DT[out.dtype], ws.data_ptr(), _stream()),
+                  "gillb200_groupnorm_from_stats")
+        return out
     with _P("groupnorm", 0.0, (2 * x.element_size() + out.element_size()) * B * H * W * (C0 + C1), f"B{B} {H}x{W} C{C0 + C1}"):
         check(lib().gillb200_groupnorm(x.data_ptr(), C0, _ptr(x2), C1, _DT[x.dtype], B, H * W, groups, w.data_ptr(),
                                        b.data_ptr(), eps, int(silu), out.data_ptr(), _DT[out.dtype], ws.data_ptr(),

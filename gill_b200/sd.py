@@ -287,7 +287,7 @@ class UNetB200:
         lo, hi = self._temb_off[p]
         rb = self._temb_cur[:, lo:hi]
         n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-5, silu=True, x2=x2)
-        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], rowbias=rb)
+        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], rowbias=rb, stats=True)
         n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-5, silu=True)
         if (p + ".conv_shortcut.weight") in w:
             M = B * H * W
@@ -300,7 +300,7 @@ class UNetB200:
         else:
             assert x2 is None
             sc = x
-        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc)
+        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc, stats=True)
 
     def _transformer(self, x, p, ctx_kv):
         w, G, Hh = self.w, self.G, self.heads
@@ -330,13 +330,15 @@ class UNetB200:
         n3 = ops.layernorm(h, w[t + ".norm3.weight"], w[t + ".norm3.bias"], 1e-5)
         g = ops.gemm(n3, w[t + ".ff.geglu.weight"], bias=w[t + ".ff.geglu.bias"], act="geglu")
         h = ops.gemm(g, w[t + ".ff.out.weight"], bias=w[t + ".ff.out.bias"], residual=h)
-        out = ops.gemm(h, w[p + ".proj_out.weight"], bias=w[p + ".proj_out.bias"], residual=x.view(M, C))
-        return out.view(B, H, W, C)
+        out = ops.gemm(h, w[p + ".proj_out.weight"], bias=w[p + ".proj_out.bias"], residual=x.view(M, C), stats=True)
+        o4 = out.view(B, H, W, C)
+        o4.gn_stats = out.gn_stats      # the next resnet's GroupNorm takes its statistics from this epilogue
+        return o4
 
     def _conv_s2(self, x, p):
         # stride-2 downsampler as an implicit GEMM: the TMA tensor map walks the input with element strides {1,2,2,1}
         # (no [M, 9C] im2col buffer: 94 MB at the 64x64 level)
-        return ops.conv3x3(x, self.w[p + ".weight"], bias=self.w[p + ".bias"], stride=2)
+        return ops.conv3x3(x, self.w[p + ".weight"], bias=self.w[p + ".bias"], stride=2, stats=True)
 
     # ------------------------------------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor, step: Optional[int], ctx_kv: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -348,7 +350,9 @@ class UNetB200:
         boc = cfg["block_out_channels"]
         B, H, W, _ = x.shape
         cols = ops.im2col3x3(x, 1, ld_out=64)
-        h = ops.gemm(cols, w["conv_in.weight"], bias=w["conv_in.bias"]).view(B, H, W, boc[0])
+        h2 = ops.gemm(cols, w["conv_in.weight"], bias=w["conv_in.bias"], stats=True)
+        h = h2.view(B, H, W, boc[0])
+        h.gn_stats = h2.gn_stats
         skips = [h]
         for i in range(len(boc)):
             for j in range(cfg["layers_per_block"]):
@@ -369,7 +373,7 @@ class UNetB200:
                     h = self._transformer(h, f"up_blocks.{i}.attentions.{j}", ctx_kv)
             if i < len(boc) - 1:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
-                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"])
+                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=True)
         n = ops.groupnorm(h, w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.G, 1e-5, silu=True)
         return ops.conv3x3(n, w["conv_out.weight"], bias=w["conv_out.bias"], block_n=32)
 
@@ -414,14 +418,14 @@ class VAEDecoderB200:
         w, G = self.w, self.G
         B, H, W, _ = x.shape
         n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-6, silu=True)
-        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"])
+        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], stats=True)
         n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-6, silu=True)
         if (p + ".conv_shortcut.weight") in w:
             sc = ops.gemm(x.view(B * H * W, -1), w[p + ".conv_shortcut.weight"],
                           bias=w[p + ".conv_shortcut.bias"]).view(B, H, W, -1)
         else:
             sc = x
-        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc)
+        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc, stats=True)
 
     def _mid_attention(self, x):
         """Single-head attention over H*W tokens with head dim 512: too wide for the fused kernel's smem tiles, and
@@ -439,8 +443,10 @@ class VAEDecoderB200:
             s = ops.gemm(q[b * L : (b + 1) * L], k[b * L : (b + 1) * L], out_dtype=torch.float32)   # [L, L]
             pr = ops.softmax_rows(s, C ** -0.5, x.dtype)
             ops.gemm(pr, vT, out=o[b * L : (b + 1) * L])
-        out = ops.gemm(o, w[a + ".to_out.0.weight"], bias=w[a + ".to_out.0.bias"], residual=x.view(B * L, C))
-        return out.view(B, H, W, C)
+        out = ops.gemm(o, w[a + ".to_out.0.weight"], bias=w[a + ".to_out.0.bias"], residual=x.view(B * L, C), stats=True)
+        o4 = out.view(B, H, W, C)
+        o4.gn_stats = out.gn_stats
+        return o4
 
     def decode_u8(self, latents: torch.Tensor) -> torch.Tensor:
         """latents NHWC [B,h,w,4] (fp32 or fp16) -> uint8 NHWC [B,8h,8w,3]."""
@@ -450,7 +456,9 @@ class VAEDecoderB200:
         # latents/0.18215 -> post_quant_conv: one folded 4x4 channel map
         z = ops.channel_mix(latents.float().contiguous(), self.pq_w, self.pq_b, self.dt)
         cols = ops.im2col3x3(z, 1, ld_out=64)
-        h = ops.gemm(cols, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"]).view(B, H, W, boc[-1])
+        h2 = ops.gemm(cols, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"], stats=True)
+        h = h2.view(B, H, W, boc[-1])
+        h.gn_stats = h2.gn_stats
         h = self._resnet(h, "decoder.mid_block.resnets.0")
         h = self._mid_attention(h)
         h = self._resnet(h, "decoder.mid_block.resnets.1")
@@ -459,7 +467,7 @@ class VAEDecoderB200:
                 h = self._resnet(h, f"decoder.up_blocks.{i}.resnets.{j}")
             if i < len(boc) - 1:
                 p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"])
+                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=True)
         n = ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], self.G, 1e-6,
                           silu=True)
         img = ops.conv3x3(n, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"], block_n=32)

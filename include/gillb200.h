@@ -85,6 +85,10 @@ typedef struct gillb200_gemm_args {
    * whose tile count fills the SMs badly (the UNet's 8x8 / 16x16 levels) split their K range evenly over all SMs. */
   void* sk_workspace;
   int stream_k; /* 0 = auto (when sk_workspace is given); 1 = never; 2 = always (if the kernel variant supports it) */
+  /* optional: GroupNorm statistics of the output, float [M/32, N, 2] = per 32-row slab and column {sum, sum of squares} of
+   * the rounded 16-bit output values (consumed by gillb200_groupnorm_from_stats). Needs a 16-bit output, M % 32 == 0,
+   * N % 32 == 0, 16-byte aligned rows and no GEGLU. */
+  void* stats_out;
   int conv_stride; /* conv3x3 only: 0/1 = stride 1; 2 = stride 2 (conv_H/conv_W stay the INPUT size, M = B*(H/2)*(W/2));
                     * the A tensor map then walks the input with TMA element strides, no im2col buffer */
 } gillb200_gemm_args;
@@ -153,6 +157,11 @@ int gillb200_layernorm(const void* x, long long ldx, int in_dtype, const float* 
 long long gillb200_groupnorm_workspace_bytes(int B, int G);
 int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1, int dtype, int B, int HW, int G, const float* w,
                        const float* b, float eps, int silu, void* out, int out_dtype, void* workspace, void* stream);
+/* GroupNorm(+SiLU) whose statistics come from the producing GEMMs' stats_out buffers (stats1 only with a second source):
+ * one small reduction per (sample, group) + the elementwise pass -- no statistics read of the activation. */
+int gillb200_groupnorm_from_stats(const void* x0, int C0, const void* stats0, const void* x1, int C1, const void* stats1,
+                                  int dtype, int B, int HW, int G, const float* w, const float* b, float eps, int silu,
+                                  void* out, int out_dtype, void* workspace, void* stream);
 int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype, float scale, long long rows, int n, void* out,
                           long long ldo, int out_dtype, void* stream);
 

@@ -397,3 +397,65 @@ def test_clip_preprocess_u8_is_pil_exact(ops, hw):
         assert (pv[b].cpu() - oclip.clip_preprocess(imgs[b], 224)).abs().max() < 1e-6
     pv16 = ops.clip_preprocess_u8(torch.from_numpy(imgs).to(dev), 224)
     assert pv16.dtype == torch.bfloat16 and torch.equal(pv16, pv.bfloat16())
+
+
+def _slab_stats(out2d):
+    o = out2d.float().view(out2d.shape[0] // 32, 32, out2d.shape[1])
+    return torch.stack([o.sum(1), (o * o).sum(1)], -1)
+
+
+def test_epilogue_groupnorm_statistics(ops):
+    """stats=True: the GEMM / conv epilogue leaves {sum, sumsq} per 32-row slab and column of the ROUNDED output -- every
+    staged-epilogue variant, the CTA-pair kernel and the stream-K finisher."""
+    torch.manual_seed(30)
+    M, N, K = 2048, 640, 320
+    a = torch.randn(M, K, device=dev).half()
+    b = (torch.randn(N, K, device=dev) * 0.05).half()
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(M, N, device=dev).half()
+    rb = torch.randn(M // 256, N, device=dev)
+    for kw in (dict(), dict(residual=res), dict(rowbias=rb, rows_per_group=256), dict(act="silu"),
+               dict(residual=res, cta_pair=2, block_n=128), dict(stream_k=2)):
+        out = ops.gemm(a, b, bias=bias, stats=True, **kw)
+        assert out.gn_stats.shape == (M // 32, N, 2)
+        ref = _slab_stats(out)
+        assert rel(out.gn_stats, ref) < 1e-5, kw
+    ob = ops.gemm(a.bfloat16(), b.bfloat16(), bias=bias, stats=True)
+    assert rel(ob.gn_stats, _slab_stats(ob)) < 1e-5
+    x = torch.randn(2, 16, 16, 1280, device=dev).half()                       # 20 tiles x 180 k-blocks: stream-K finisher
+    w = (torch.randn(1280, 9 * 1280, device=dev) * 0.01).half()
+    oc = ops.conv3x3(x, w, bias=torch.randn(1280, device=dev), stats=True, stream_k=2)
+    assert rel(oc.gn_stats, _slab_stats(oc.view(-1, 1280))) < 1e-5
+    with pytest.raises(Exception):
+        ops.gemm(a, b, bias=bias, stats=True, out_dtype=torch.float32)
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 320, 0, True), (2, 32, 32, 640, 320, True), (2, 8, 8, 1280, 1280, False),
+                                  (2, 16, 16, 1280, 640, True)])
+def test_groupnorm_from_epilogue_statistics_equals_two_pass(ops, case):
+    B, H, W, C0, C1, silu = case
+    torch.manual_seed(31)
+
+    def produce(C):
+        a = torch.randn(B * H * W, 64, device=dev).half()
+        wt = (torch.randn(C, 64, device=dev) * 0.2).half()
+        o = ops.gemm(a, wt, bias=torch.randn(C, device=dev), stats=True)
+        o4 = o.view(B, H, W, C)
+        o4.gn_stats = o.gn_stats
+        return o4
+
+    x0 = produce(C0)
+    x1 = produce(C1) if C1 else None
+    C = C0 + C1
+    w, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    fast = ops.groupnorm(x0, w, b, 32, 1e-5, silu=silu, x2=x1)
+    ops.USE_EPILOGUE_GN_STATS = False
+    try:
+        slow = ops.groupnorm(x0, w, b, 32, 1e-5, silu=silu, x2=x1)
+    finally:
+        ops.USE_EPILOGUE_GN_STATS = True
+    assert rel(fast, slow) < 2e-3 and (fast.float() - slow.float()).abs().max() < 2e-2
+    xc = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = F.group_norm(xc.permute(0, 3, 1, 2).float(), 32, w, b, 1e-5)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+    assert rel(fast, ref) < 2e-3
