@@ -2,17 +2,19 @@
 //
 //   D[M,N] = epilogue( A[M,K] * B[N,K]^T )        A, B: 16-bit (bf16 or fp16), K-major; fp32 accumulate in TMEM.
 //
-// One CTA per SM, 256 threads:
-//   warp 0 lane 0 : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
-//   warp 1 lane 0 : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16 per instruction)
+// One CTA per SM, 384 threads:
+//   warp 0        : TMA producer  (one elected lane: cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1        : MMA issuer    (one elected lane: tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16 per instruction)
 //   warp 2        : TMEM allocator
-//   warps 4..19   : epilogue      (tcgen05.ld 32x32b -> registers -> bias/act/residual -> vectorised global stores);
-//                   warps w, w+4, w+8, w+12 share a TMEM lane quadrant and split the tile's 16-column chunks
+//   warps 4..11   : epilogue. Staged form (default): tcgen05.ld -> registers -> bias / activation / residual -> swizzled
+//                   shared-memory panel -> TMA store (+ optional GroupNorm statistics, + stream-K partial / fix-up);
+//                   direct form (odd layouts only): per-lane vectorised global stores.
+//                   Warps w and w+4 share a TMEM lane quadrant and split the tile's 32-column panels.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // The A operand has two addressing modes:
 //   A_PLAIN   : 2D tensor map {K, M}; optional second source (tma_a2) for K-concatenation / split-precision.
-//   A_CONV3X3 : implicit GEMM for a 3x3, stride-1, pad-1 convolution over an NHWC activation. The tensor map is
+//   A_CONV3X3 : implicit GEMM for a 3x3, pad-1 convolution (stride 1 or 2) over an NHWC activation. The tensor map is
 //               4D {C, W, H, B}; each 128-row M tile is a (bw x bh x bb) pixel box and each K block is one
 //               (tap, 64-channel) slice fetched with the box shifted by (dx, dy). TMA zero-fills out-of-bounds
 //               coordinates, which is exactly the zero padding. No im2col buffer is ever materialised.
