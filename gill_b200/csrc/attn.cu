@@ -419,7 +419,9 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
 // Tried and dropped (measured on B200, 16x8x4096x4096 hd40): issuing Q.K_{j+1}^T in the middle of tile j's softmax
 // through two alternating K/V slots (no S wait on the critical path) ran 939 us vs 853 us for this version -- with four
 // CTAs per SM the MMA bubble of one CTA is already filled by the others' exponentials; the extra barrier and the probe
-// code only add issue slots. The kernel is bound by MUFU.EX2 (64 per row-tile, 61 % XU utilisation) plus issue slots.
+// code only add issue slots. Moving every 4th pair of exponentials to an FMA-pipe polynomial (Cody-Waite split + degree-3
+// 2^f, 9 instructions per exp) did not help either: 862 us. XU sits at 61 %, issue slots at 48 %: what remains is the
+// serial TMEM-load -> max -> exp -> pack -> st.shared -> barrier -> MMA chain of each CTA, overlapped 4 ways per SM.
 template <int HD_PAD>
 struct Attn2Cfg {
   static constexpr int BKV = 64;
