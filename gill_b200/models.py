@@ -9,7 +9,8 @@ Differences that are deliberate and documented in DESIGN.md:
   * `generate` speculatively appends the 8 [IMG] embeddings to every forward: OPT is causal, so the logits at the last
     real position are unchanged, and when [IMG0] is emitted the same forward already contains the next step's hidden
     states -- one prefill replaces the reference's two no-cache passes on the image-emission path;
-  * `generate_for_images_and_texts_batch` runs several independent prompt lists through the same path at once.
+  * `GILL.emit_images_batch` runs B independent equal-length prompts through the forced-emission path at once
+    (one OPT prefill, one GILLMapper call, SD in chunks of 8) -- the per-sample equivalent of the reference's batch-1 loop.
 """
 import glob
 import json
