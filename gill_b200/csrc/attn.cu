@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
 // through two alternating K/V slots (no S wait on the critical path) ran 939 us vs 853 us for this version -- with four
 // CTAs per SM the MMA bubble of one CTA is already filled by the others' exponentials; the extra barrier and the probe
 // code only add issue slots. Moving every 4th pair of exponentials to an FMA-pipe polynomial (Cody-Waite split + degree-3
-// 2^f, 9 instructions per exp) did not help either: 862 us. XU sits at 61 %, issue slots at 48 %: what remains is the
+// 2^f, 9 instructions per exp) did not help either: 862 us. A K/V-resident cross-attention variant walking 4 query tiles
+// per CTA (set-up and K/V loads paid once) lost too: 71 vs 60 us for 16x8x4096x77 -- fewer CTAs per SM to interleave. XU sits at 61 %, issue slots at 48 %: what remains is the
 // serial TMEM-load -> max -> exp -> pack -> st.shared -> barrier -> MMA chain of each CTA, overlapped 4 ways per SM.
 template <int HD_PAD>
 struct Attn2Cfg {

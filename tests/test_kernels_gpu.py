@@ -274,6 +274,9 @@ CASES = [  # B, H, Lq, Lk, hd, hd_pad, dtype, causal
     (2, 8, 1024, 77, 40, 64, torch.float16, False), (2, 8, 256, 256, 80, 128, torch.float16, False),
     (2, 8, 64, 64, 160, 192, torch.float16, False), (2, 8, 256, 77, 160, 192, torch.float16, False),
     (3, 32, 81, 81, 128, 128, torch.bfloat16, True), (2, 4, 300, 300, 128, 128, torch.bfloat16, True),
+    # cross-attention shapes (Lk <= 128), ragged Lq
+    (2, 4, 1000, 128, 40, 64, torch.float16, False), (1, 4, 512, 50, 80, 128, torch.float16, False),
+    (2, 8, 4096, 77, 40, 64, torch.float16, False), (2, 2, 640, 77, 64, 64, torch.bfloat16, False),
 ]
 
 
