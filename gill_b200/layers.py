@@ -143,11 +143,21 @@ class TextFcLayer(nn.Module):
         m_hi, m_lo = self._ln(pk, "tfm.encoder.norm", h)
         # ---- decoder over the learned queries (layers.py:43: query_embs.repeat(N, 1, 1))
         Lq = self.num_output_tokens
-        y = pk["query_embs"].unsqueeze(0).expand(N, Lq, _D).reshape(N * Lq, _D).contiguous()
+        # The first decoder block's self-attention sees only the learned queries: it does not depend on the input, so it
+        # is computed once per set of weights for ONE sample and broadcast (row-independent arithmetic => bit-identical
+        # to running it on all N samples).
+        y1 = pk.get("_dec0_self")
+        if y1 is None:
+            q0 = pk["query_embs"].reshape(Lq, _D).contiguous()
+            h_hi, h_lo = self._ln(pk, "tfm.decoder.layers.0.norm1", q0)
+            y1 = self._mha(pk, "tfm.decoder.layers.0.self_attn", h_hi, h_lo, None, None, 1, Lq, Lq, q0, True)
+            pk["_dec0_self"] = y1
+        y = y1.unsqueeze(0).expand(N, Lq, _D).reshape(N * Lq, _D).contiguous()
         for i in range(_L):
             p = f"tfm.decoder.layers.{i}"
-            n_hi, n_lo = self._ln(pk, p + ".norm1", y)
-            y = self._mha(pk, p + ".self_attn", n_hi, n_lo, None, None, N, Lq, Lq, y, True)
+            if i > 0:
+                n_hi, n_lo = self._ln(pk, p + ".norm1", y)
+                y = self._mha(pk, p + ".self_attn", n_hi, n_lo, None, None, N, Lq, Lq, y, True)
             n_hi, n_lo = self._ln(pk, p + ".norm2", y)
             y = self._mha(pk, p + ".multihead_attn", n_hi, n_lo, m_hi, m_lo, N, Lq, T, y, False)
             n_hi, n_lo = self._ln(pk, p + ".norm3", y)
