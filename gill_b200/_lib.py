@@ -41,6 +41,7 @@ class GemmArgs(ctypes.Structure):
         ("sk_workspace", _c_void_p),
         ("stream_k", _c_int),
         ("stats_out", _c_void_p),
+        ("rowstats_out", _c_void_p), ("ln_stats", _c_void_p), ("ln_cs", _c_void_p), ("ln_C", _c_int), ("ln_eps", _c_float),
         ("conv_stride", _c_int),
     ]
 

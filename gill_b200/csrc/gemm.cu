@@ -389,13 +389,35 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
         else if (!a->residual && !a->rowbias)
           p.epi_variant = EV_BIAS;
       }
+      if (a->ln_stats) {  // folded LayerNorm: only the two specialised consumers exist
+        const bool lnok = plain && a->ln_cs && a->ln_C > 0 && a->ln_C % 32 == 0 && !a->rowbias && !a->residual &&
+                          reinterpret_cast<uintptr_t>(a->ln_cs) % 16 == 0 && a->K == a->ln_C && a->a2_mode == 0;
+        if (lnok && a->act == ACT_GEGLU && a->N % 64 == 0)
+          p.epi_variant = EV_LN_GEGLU;
+        else if (lnok && a->act == ACT_NONE && a->N % 32 == 0)
+          p.epi_variant = EV_LN_BIAS;
+        else
+          return set_err(-EINVAL, "ln_stats: needs fp16 output, aligned bias and ln_cs, K == ln_C, act none/GEGLU, no residual");
+        p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+        p.ln_cs = a->ln_cs;
+        p.ln_C = a->ln_C;
+        p.ln_np = a->ln_C / 32;
+        p.ln_ld = a->M;
+        p.ln_eps = a->ln_eps;
+      }
+      if (a->rowstats_out) {
+        if (p.epi_variant != EV_BIAS && p.epi_variant != EV_BIAS_RES)
+          return set_err(-EINVAL, "rowstats_out needs the bias (+ residual) staged epilogue: fp16 output, N %% 32 == 0");
+        p.rowstats_out = reinterpret_cast<float2*>(a->rowstats_out);
+        p.rowstats_ld = a->M;
+      }
       {
         static int env_var = -2;
         if (env_var == -2) {
           const char* e = getenv("GILLB200_EPI_GENERIC");  // "1": always the all-runtime staged epilogue (A/B)
           env_var = e ? atoi(e) : 0;
         }
-        if (env_var) p.epi_variant = EV_GENERIC;
+        if (env_var && !a->ln_stats && !a->rowstats_out) p.epi_variant = EV_GENERIC;
       }
       p.epi_nbuf = a->residual ? 3 : 2;
       p.epi_buf_bytes = 32 * EPI_PANEL_COLS * esz;
@@ -412,6 +434,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   }
 
   // ---- stream-K (see want_sk above): only the 1-CTA kernel with the staged epilogue
+  GB_CHECK_ARG(p.epi_tma || (!a->ln_stats && !a->rowstats_out), "ln_stats / rowstats_out need the staged epilogue");
   if (a->stats_out) {
     GB_CHECK_ARG(p.epi_tma && a->act != ACT_GEGLU && a->out_dtype != DT_F32 && a->M % 32 == 0 && a->N % 32 == 0,
                  "stats_out needs the staged epilogue: 16-bit output, 16-byte aligned rows, M %% 32 == 0, N %% 32 == 0, no GEGLU");

@@ -83,6 +83,15 @@ struct alignas(64) GemmParams {
   // (gillb200_groupnorm_from_stats) reduces slabs and channels per (sample, group) -- the separate statistics pass
   // over the activation (one full read) disappears.
   float2* stats_out;
+  // LayerNorm folded into the NEXT GEMM. Producer side: rowstats_out[panel * rowstats_ld + row] = {sum, sumsq} of this
+  // row's 32 output columns of `panel` (global 32-column index) -- the consumer adds the C/32 partials of a row.
+  // Consumer side (EV_LN_* variants): the weights carry the LayerNorm scale (W' = W diag(gamma)), so
+  //   LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (b + W beta);   ln_cs = colsum(W'), bias = b + W beta.
+  float2* rowstats_out;
+  const float2* ln_stats;
+  const float* ln_cs;
+  int rowstats_ld, ln_ld, ln_np, ln_C;
+  float ln_eps;
   int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
@@ -540,7 +549,7 @@ constexpr int EPI_MAX_NBUF = 3;
 // alpha == 1, column bias present); EV_GENERIC keeps every option a runtime branch (fp32 / bf16 outputs, other
 // activations, bias along M, N tails). ncu on the first, all-runtime version: ~400 warp instructions per 32x32 panel,
 // 44 % issue-slot utilisation and the epilogue warps latency-bound -- the specialised bodies are ~100.
-enum { EV_BIAS = 0, EV_BIAS_RES = 1, EV_BIAS_ROWBIAS = 2, EV_GEGLU = 3, EV_GENERIC = 4 };
+enum { EV_BIAS = 0, EV_BIAS_RES = 1, EV_BIAS_ROWBIAS = 2, EV_GEGLU = 3, EV_GENERIC = 4, EV_LN_BIAS = 5, EV_LN_GEGLU = 6 };
 
 // 16-byte unit `u` of row `r` inside a 32-row panel buffer written/read by TMA with SWIZZLE_64B (16-bit elements,
 // 64-byte rows) or SWIZZLE_128B (fp32, 128-byte rows)
@@ -650,7 +659,8 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
   const int ew = warp - 4, quad = warp & 3;
   const int cgrp = ew >> 2, ngrp = p.epi_warps >> 2;
   const int lane = lane_id();
-  constexpr bool GEGLU = VAR == EV_GEGLU;
+  constexpr bool GEGLU = VAR == EV_GEGLU || VAR == EV_LN_GEGLU;
+  constexpr bool LNF = VAR == EV_LN_BIAS || VAR == EV_LN_GEGLU;
   const bool geglu = VAR == EV_GENERIC ? p.act == ACT_GEGLU : GEGLU;
   const bool has_res = VAR == EV_GENERIC ? p.residual != nullptr : VAR == EV_BIAS_RES;
   const int acc_per_panel = geglu ? 2 * EPI_PANEL_COLS : EPI_PANEL_COLS;
@@ -689,6 +699,18 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
     const int row = min(row0 + lane, p.M - 1);  // rows >= M are clipped by the TMA store; clamp only for bias reads
     const float* rb_row = nullptr;
     if (VAR == EV_BIAS_ROWBIAS) rb_row = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ld_rowbias;
+    float ln_rstd = 1.f, ln_rm = 0.f;  // folded LayerNorm of this lane's row: rstd and rstd * mean
+    if (LNF) {
+      float ls = 0.f, lq = 0.f;
+      for (int i = 0; i < p.ln_np; ++i) {
+        const float2 t = __ldg(p.ln_stats + static_cast<size_t>(i) * p.ln_ld + row);
+        ls += t.x;
+        lq += t.y;
+      }
+      const float mean = ls / p.ln_C;
+      ln_rstd = rsqrtf(fmaxf(lq / p.ln_C - mean * mean, 0.f) + p.ln_eps);
+      ln_rm = ln_rstd * mean;
+    }
 
     auto fetch_res = [&](int pnl, uint32_t b) {  // lane 0 only
       mbar_arrive_expect_tx(&res_bar[b], panel_bytes);
@@ -808,6 +830,17 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           tmem_wait_ld();
           if (last && h == 1) release_fn(acc);
           if (sk_reduce) sk_add(r, pnl * 64 + h * 32);
+          if (LNF) {  // x W'^T -> rstd * (x W'^T - mean * colsum(W')) before the bias
+            const float4* c4 = reinterpret_cast<const float4*>(p.ln_cs + nacc + h * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 cs = __ldg(c4 + i);
+              r[4 * i] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i]), -ln_rm * cs.x));
+              r[4 * i + 1] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i + 1]), -ln_rm * cs.y));
+              r[4 * i + 2] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i + 2]), -ln_rm * cs.z));
+              r[4 * i + 3] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i + 3]), -ln_rm * cs.w));
+            }
+          }
           float f[16];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {  // (value, gate) pairs are interleaved along N
@@ -837,6 +870,17 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         tmem_wait_ld();
         if (last) release_fn(acc);
         if (sk_reduce) sk_add(r, pnl * 32);
+        if (LNF) {
+          const float4* c4 = reinterpret_cast<const float4*>(p.ln_cs + nacc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 cs = __ldg(c4 + i);
+            r[4 * i] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i]), -ln_rm * cs.x));
+            r[4 * i + 1] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i + 1]), -ln_rm * cs.y));
+            r[4 * i + 2] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i + 2]), -ln_rm * cs.z));
+            r[4 * i + 3] = __float_as_uint(fmaf(ln_rstd, __uint_as_float(r[4 * i + 3]), -ln_rm * cs.w));
+          }
+        }
         float f[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -847,6 +891,17 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         }
         if (VAR == EV_BIAS_RES) mbar_wait(&res_bar[buf], (par >> buf) & 1);
         epi_f16_units<4, VAR == EV_BIAS_RES>(sbuf, lane, 0, f);
+        if ((VAR == EV_BIAS || VAR == EV_BIAS_RES) && p.rowstats_out != nullptr && row0 + lane < p.M) {
+          // f[] now holds this row's 32 final values (residual included): partial LayerNorm sums for the next GEMM
+          float rs = 0.f, rq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            rs += f[i];
+            rq = fmaf(f[i], f[i], rq);
+          }
+          p.rowstats_out[static_cast<size_t>((no0 + pnl * EPI_PANEL_COLS) >> 5) * p.rowstats_ld + row0 + lane] =
+              make_float2(rs, rq);
+        }
       }
 
       if (p.stats_out != nullptr) {
@@ -901,6 +956,13 @@ __device__ __forceinline__ void epilogue_warp_tma_dispatch(const GemmParams& p, 
       break;
     case EV_BIAS_ROWBIAS:
       epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_ROWBIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      break;
+    case EV_LN_BIAS:
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_LN_BIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      break;
+    case EV_LN_GEGLU:
+      if constexpr (BLOCK_N % 64 == 0)
+        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_LN_GEGLU>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_GEGLU:
       if constexpr (BLOCK_N % 64 == 0)

@@ -108,6 +108,8 @@ def gemm(
     tile_order: int = 0,
     stream_k: int = 0,
     stats: bool = False,
+    rowstats: bool = False,
+    ln=None,
 ) -> torch.Tensor:
     """out = act(alpha * a @ b.T + bias + rowbias) + residual     (a: [M,K], b: [N,K], 16-bit; fp32 accumulate).
 
@@ -148,6 +150,16 @@ def gemm(
         g.sk_workspace = _streamk_ws(a.device)
     if stats:
         out.gn_stats = _attach_stats(g, M, n_out, a.device)
+    if rowstats:
+        # per 32-column panel and row {sum, sumsq} of the output: the LayerNorm statistics of the NEXT (ln=...) GEMM
+        out.ln_stats = torch.empty((n_out // 32, M, 2), device=a.device, dtype=torch.float32)
+        g.rowstats_out = out.ln_stats.data_ptr()
+    if ln is not None:
+        # LayerNorm folded into this GEMM: ln = (row statistics of `a` from its producer, colsum(b), eps); `b` carries the
+        # LayerNorm scale and `bias` the shifted bias (see gillb200.h)
+        st, cs, eps = ln
+        assert st.shape == (K // 32, M, 2) and cs.dtype == torch.float32 and cs.numel() == N
+        g.ln_stats, g.ln_cs, g.ln_C, g.ln_eps = st.data_ptr(), cs.data_ptr(), K, eps
     ktot = K + (g.k2 if a2_mode == 1 else 0)
     with _P("gemm" if a2_mode != 2 else "gemm_split", 2.0 * M * N * ktot * (2 if a2_mode == 2 else 1),
             2.0 * (M * ktot + N * ktot) + out.element_size() * M * n_out, f"M{M} N{N} K{ktot} {act or ''}"):

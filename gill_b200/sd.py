@@ -17,6 +17,7 @@ B200-first layout decisions
   * CFG + PLMS is one fused elementwise kernel; the VAE epilogue writes uint8 NHWC on the device.
 """
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -107,6 +108,8 @@ class UNetB200:
         self._pack(sd)
         self._temb_table = None
         self._temb_steps = None
+        # transformer-block LayerNorms folded into their consuming GEMMs (False / GILLB200_FOLD_LN=0: separate LN kernels)
+        self.fold_ln = os.environ.get("GILLB200_FOLD_LN", "1") != "0"
 
     # ------------------------------------------------------------------------------------------------ packing
     def _put(self, k, v, dt=None):
@@ -166,6 +169,19 @@ class UNetB200:
         self._put(f"{t}.ff.geglu.bias", torch.stack([b[:half], b[half:]], 1).reshape(-1), f32)
         self._put(f"{t}.ff.out.weight", sd[f"{t}.ff.net.2.weight"])
         self._put(f"{t}.ff.out.bias", sd[f"{t}.ff.net.2.bias"], f32)
+        # LayerNorm folded into the consuming GEMM (norm1 -> qkv, norm2 -> cross-attention q, norm3 -> GEGLU):
+        #   LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (b + W beta),  W' = W diag(gamma)
+        def fold(wkey, bias, nkey):
+            W = self.w[wkey].float().cpu()                      # the packed (padded / interleaved) fp16 weight
+            gam, bet = sd[f"{t}.{nkey}.weight"].float(), sd[f"{t}.{nkey}.bias"].float()
+            Wf = (W * gam[None, :]).to(self.dt)
+            self._put(wkey + "_ln", Wf)
+            self._put(wkey + "_cs", Wf.float().sum(1), f32)     # column sums of what the tensor core multiplies
+            b0 = torch.zeros(W.shape[0]) if bias is None else self.w[bias].float().cpu()
+            self._put(wkey + "_lnb", b0 + W @ bet, f32)
+        fold(f"{t}.attn1.qkv", f"{t}.attn1.qkv_bias", "norm1")
+        fold(f"{t}.attn2.q", None, "norm2")
+        fold(f"{t}.ff.geglu.weight", f"{t}.ff.geglu.bias", "norm3")
         self._tf_meta = getattr(self, "_tf_meta", {})
         self._tf_meta[p] = (c, hd, hp)
 
@@ -309,6 +325,8 @@ class UNetB200:
         M, L = B * H * W, H * W
         t = p + ".transformer_blocks.0"
         n = ops.groupnorm(x, w[p + ".norm.weight"], w[p + ".norm.bias"], G, 1e-6)
+        if self.fold_ln:
+            return self._transformer_folded(x, n, p, ctx_kv)
         h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"])
         # self attention
         n1 = ops.layernorm(h, w[t + ".norm1.weight"], w[t + ".norm1.bias"], 1e-5)
@@ -333,6 +351,35 @@ class UNetB200:
         out = ops.gemm(h, w[p + ".proj_out.weight"], bias=w[p + ".proj_out.bias"], residual=x.view(M, C), stats=True)
         o4 = out.view(B, H, W, C)
         o4.gn_stats = out.gn_stats      # the next resnet's GroupNorm takes its statistics from this epilogue
+        return o4
+
+    def _transformer_folded(self, x, n, p, ctx_kv):
+        """Same block with the three LayerNorms folded into their consuming GEMMs: the producers of the residual stream
+        leave per-row partial sums (rowstats), the consumers correct `x W'^T` with (mean, rstd) in their epilogues -- no
+        LayerNorm kernel, no normalised copy of the stream."""
+        w, Hh = self.w, self.heads
+        B, H, W, C = x.shape
+        _, hd, hp = self._tf_meta[p]
+        M, L = B * H * W, H * W
+        t = p + ".transformer_blocks.0"
+        oc = hd if hp > hd else 0
+        h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"], rowstats=True)
+        qkv = ops.gemm(h, w[t + ".attn1.qkv_ln"], bias=w[t + ".attn1.qkv_lnb"],
+                       ln=(h.ln_stats, w[t + ".attn1.qkv_cs"], 1e-5)).view(B, L, 3 * Hh * hp)
+        a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
+                          hd ** -0.5, ones_col=oc)
+        h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h, rowstats=True)
+        q = ops.gemm(h, w[t + ".attn2.q_ln"], bias=w[t + ".attn2.q_lnb"],
+                     ln=(h.ln_stats, w[t + ".attn2.q_cs"], 1e-5)).view(B, L, Hh * hp)
+        kv = ctx_kv[p]
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc)
+        h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h, rowstats=True)
+        g = ops.gemm(h, w[t + ".ff.geglu.weight_ln"], bias=w[t + ".ff.geglu.weight_lnb"], act="geglu",
+                     ln=(h.ln_stats, w[t + ".ff.geglu.weight_cs"], 1e-5))
+        h = ops.gemm(g, w[t + ".ff.out.weight"], bias=w[t + ".ff.out.bias"], residual=h)
+        out = ops.gemm(h, w[p + ".proj_out.weight"], bias=w[p + ".proj_out.bias"], residual=x.view(M, C), stats=True)
+        o4 = out.view(B, H, W, C)
+        o4.gn_stats = out.gn_stats
         return o4
 
     def _conv_s2(self, x, p):

@@ -89,6 +89,18 @@ typedef struct gillb200_gemm_args {
    * the rounded 16-bit output values (consumed by gillb200_groupnorm_from_stats). Needs a 16-bit output, M % 32 == 0,
    * N % 32 == 0, 16-byte aligned rows and no GEGLU. */
   void* stats_out;
+  /* LayerNorm folded into the NEXT GEMM (UNet transformer blocks).
+   * rowstats_out (producer, optional): float [N/32, M, 2] = per 32-column panel and row {sum, sumsq} of the output; needs
+   *   the plain bias (+ residual) staged epilogue (fp16 output, N % 32 == 0).
+   * ln_stats / ln_cs (consumer, optional, both or none): ln_stats = the producer's rowstats_out of THIS GEMM's A operand
+   *   (ln_C = its column count), ln_cs[N] = column sums of the weights, which must already carry the LayerNorm scale
+   *   (W' = W diag(gamma)); bias must be b + W beta. The epilogue then computes
+   *   rstd * (A W'^T - mean * ln_cs) + bias  ==  LayerNorm(A) W^T + b.  act: none or GEGLU; no residual / rowbias. */
+  void* rowstats_out;
+  const void* ln_stats;
+  const float* ln_cs;
+  int ln_C;
+  float ln_eps;
   int conv_stride; /* conv3x3 only: 0/1 = stride 1; 2 = stride 2 (conv_H/conv_W stay the INPUT size, M = B*(H/2)*(W/2));
                     * the A tensor map then walks the input with TMA element strides, no im2col buffer */
 } gillb200_gemm_args;

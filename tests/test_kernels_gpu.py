@@ -462,3 +462,30 @@ def test_groupnorm_from_epilogue_statistics_equals_two_pass(ops, case):
     ref = F.group_norm(xc.permute(0, 3, 1, 2).float(), 32, w, b, 1e-5)
     ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
     assert rel(fast, ref) < 2e-3
+
+
+@pytest.mark.parametrize("C,N,geglu", [(320, 1536, False), (640, 512, False), (1280, 2560, True), (320, 2560, True)])
+def test_layernorm_folded_into_the_consuming_gemm(ops, C, N, geglu):
+    """Producer leaves per-row partial sums (rowstats); the consumer GEMM with ln=... computes LayerNorm(x) W^T + b from
+    the raw x: rstd * (x W'^T - mean * colsum(W')) + (b + W beta)."""
+    torch.manual_seed(40)
+    M = 1000                                                          # ragged last tile
+    a0 = torch.randn(M, 64, device=dev).half()
+    w0 = (torch.randn(C, 64, device=dev) * 0.3).half()
+    res = (torch.randn(M, C, device=dev) * 2 + 0.7).half()            # non-zero mean: exercises the mean * colsum term
+    x = ops.gemm(a0, w0, bias=torch.randn(C, device=dev), residual=res, rowstats=True)
+    ref_stats = torch.stack([x.float().view(M, C // 32, 32).sum(-1), (x.float() ** 2).view(M, C // 32, 32).sum(-1)], -1)
+    assert rel(x.ln_stats.permute(1, 0, 2), ref_stats) < 2e-3         # sums of the unrounded values vs the fp16 tensor
+    gam, bet = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    W = (torch.randn(N, C, device=dev) * 0.05).half()
+    b = torch.randn(N, device=dev)
+    Wf = (W.float() * gam[None]).half()
+    out = ops.gemm(x, Wf, bias=b + W.float() @ bet, act="geglu" if geglu else None,
+                   ln=(x.ln_stats, Wf.float().sum(1).contiguous(), 1e-5))
+    y = F.layer_norm(x.float(), (C,), gam, bet, 1e-5) @ W.float().T + b
+    ref = y[:, 0::2] * F.gelu(y[:, 1::2]) if geglu else y
+    assert out.shape == ref.shape and rel(out, ref) < 3e-3
+    # and equals the unfolded two-kernel path to fp16 noise
+    n = ops.layernorm(x, gam, bet, 1e-5)
+    two = ops.gemm(n, W, bias=b, act="geglu" if geglu else None)
+    assert rel(out, two) < 3e-3
