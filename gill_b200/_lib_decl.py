@@ -13,8 +13,9 @@ def declare(L):
         fn.restype = restype
 
     d("gillb200_topk_workspace_bytes", ci, cll, restype=cll)
-    d("gillb200_topk_scores", vp, cll, ci, cll, vp, ci, cll, ci, cll, vp, ci, vp, vp, vp, vp)
+    d("gillb200_topk_scores", vp, cll, ci, cll, vp, ci, cll, ci, cll, vp, ci, cll, vp, vp, vp, vp)
     d("gillb200_topk_merge", vp, vp, ci, ci, ci, ci, vp, vp, vp)
+    d("gillb200_topk_merge_strided", vp, cll, vp, cll, cll, ci, ci, ci, ci, vp, vp, vp)
     d("gillb200_attention", ctypes.POINTER(AttnArgs), vp)
     d("gillb200_layernorm", vp, cll, ci, vp, vp, cf, ci, ci, vp, cll, ci, vp, vp)
     d("gillb200_groupnorm_workspace_bytes", ci, ci, restype=cll)

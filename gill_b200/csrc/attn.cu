@@ -657,10 +657,9 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
 template <int HD_PAD>
 static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
   using C = Attn2Cfg<HD_PAD>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(attn2_kernel<HD_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
   GB_CUDA(launch_pdl(attn2_kernel<HD_PAD>, grid, dim3(128), C::SMEM_BYTES, stream, p));
@@ -671,11 +670,10 @@ static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
 template <int HD_PAD, int BLOCK_KV>
 static int launch_attn(const AttnParams& p, cudaStream_t stream) {
   using C = AttnCfg<HD_PAD, BLOCK_KV>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(attn_kernel<HD_PAD, BLOCK_KV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::SMEM_BYTES));
-    configured = true;
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
   GB_CUDA(launch_pdl(attn_kernel<HD_PAD, BLOCK_KV>, grid, dim3(256), C::SMEM_BYTES, stream, p));

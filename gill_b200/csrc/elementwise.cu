@@ -470,10 +470,9 @@ extern "C" int gillb200_attn_small_f32(const float* q, long long ldq, long long 
   GB_CHECK_ARG(hd == 128, "attn_small_f32: head dim must be 128 (got %d)", hd);
   GB_CHECK_ARG(Lk >= 1 && Lk <= 128 && Lq >= 1, "attn_small_f32: Lk must be in [1,128]");
   const size_t smem = (static_cast<size_t>(Lk) * (128 + 1) + static_cast<size_t>(Lk) * 128 + 8 * (Lk + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(attn_small_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
   }
   GB_CUDA(launch_pdl(attn_small_f32_kernel<128>, dim3(dim3(H, B)), dim3(256), smem, stream, q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
                                                                   out, ldo, o_bs, out_dtype, out_lo));

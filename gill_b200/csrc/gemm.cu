@@ -85,13 +85,12 @@ bool pdl_enabled() {
 }
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0 && (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0))
+    n[dev] = 148;
+  return n[dev];
 }
 
 // Shared-memory plan: [num_stages x stage][1 KB barriers][epilogue staging] (+1 KB alignment slack). The smem-staged
@@ -108,10 +107,9 @@ static int plan_smem(GemmParams& p, int stage_bytes, int max_stages) {
 template <int BN>
 static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   using C = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    configured = true;
   }
   const int smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
   GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (BN=%d)", BN);
@@ -133,10 +131,9 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
 template <int BN>
 static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
-    configured = true;
   }
   const int smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
   GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (pair, BN=%d)", BN);
@@ -293,7 +290,9 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     const char* e = getenv("GILLB200_STREAMK");  // "0": never stream-K in auto mode (A/B aid)
     env_sk = e ? atoi(e) : 1;
   }
-  if (a->sk_workspace && a->stream_k != 1 && (a->stream_k == 2 || env_sk) && a->tile_order != 2 && a->cta_pair != 2) {
+  // (stream-K partial/flag traffic assumes the previous GEMM of the stream has fully drained: never with PDL overlap)
+  if (a->sk_workspace && a->stream_k != 1 && (a->stream_k == 2 || env_sk) && a->tile_order != 2 && a->cta_pair != 2 &&
+      !pdl_enabled()) {
     if (a->stream_k == 2) {
       want_sk = true;
     } else if (a->conv3x3 && a->out_dtype != DT_F32 && p.num_k_blocks >= 16) {

@@ -38,6 +38,19 @@ int encode_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const u
 
 int num_sms();
 
+// cudaFuncSetAttribute (dynamic shared memory opt-in) is per device: a launcher configures its kernel once on every
+// device the process touches, not once per process.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 // Launch, optionally (GILLB200_PDL=1) with the programmatic-dependent-launch attribute: the kernel must call
 // gb::pdl_wait() before its first global-memory access. Captured into CUDA graphs as programmatic dependency edges.
 bool pdl_enabled();

@@ -12,6 +12,7 @@
 #include "gemm_sm100.cuh"
 #include "host_common.h"
 
+#include <cstdlib>
 #include <cstring>
 
 namespace gb {
@@ -23,7 +24,8 @@ struct TopkEpi {
   int Q;
   long long n_local;
   long long index_base;
-  const long long* exclude;
+  const long long* exclude;  // [Q or 1, n_exclude] global row ids (< 0: unused slot)
+  long long exclude_ld;      // elements between the lists of consecutive queries; 0: one list shared by every query
   int n_exclude;
   float* part_val;      // [splits, Qpad, KMAX]
   long long* part_idx;  // [splits, Qpad, KMAX]
@@ -143,8 +145,9 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
             if (s > tv[KMAX - 1] && nloc < e.n_local) {
               if (e.n_exclude > 0) {
                 const long long gidx = e.index_base + nloc;
+                const long long* ex = e.exclude + static_cast<long long>(qrow) * e.exclude_ld;
                 for (int x = 0; x < e.n_exclude; ++x)
-                  if (e.exclude[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
+                  if (ex[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
               }
               topk_insert(tv, ti, s, static_cast<int>(nloc));
             }
@@ -177,7 +180,8 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
 // One warp per query; K rounds of "best candidate strictly after the previous winner".
 __global__ void topk_merge_kernel(const float* __restrict__ cand_val, const long long* __restrict__ cand_idx, int R,
                                   long long q_stride /* elements between queries */,
-                                  long long r_stride /* elements between lists */, int kc, int Q, int K,
+                                  long long r_stride /* elements between lists (values) */,
+                                  long long r_stride_i /* elements between lists (indices) */, int kc, int Q, int K,
                                   float* __restrict__ out_val, long long* __restrict__ out_idx) {
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
@@ -190,9 +194,8 @@ __global__ void topk_merge_kernel(const float* __restrict__ cand_val, const long
     long long bi = 0x7fffffffffffffffLL;
     for (int t = lane; t < total; t += 32) {
       const int r = t / kc, j = t - r * kc;
-      const long long off = r * r_stride + q * q_stride + j;
-      const float v = cand_val[off];
-      const long long i = cand_idx[off];
+      const float v = cand_val[r * r_stride + q * q_stride + j];
+      const long long i = cand_idx[r * r_stride_i + q * q_stride + j];
       const bool after = (v < last_v) || (v == last_v && i > last_i);
       const bool better = (v > bv) || (v == bv && i < bi);
       if (after && better) {
@@ -215,6 +218,264 @@ __global__ void topk_merge_kernel(const float* __restrict__ cand_val, const long
     }
     last_v = bv;
     last_i = bi;
+  }
+}
+
+
+// ================================================================================================================
+// Small query batches (Q <= 4; the reference's own call shape is Q = 1, K = 3, gill/models.py:676-683).
+//
+// One pass over the bank, HBM-bound: N * D * 2 bytes against 2 * N * D * Q flops, so the 128-row tensor-core tile would
+// be 97-99 % padding and its per-tile hand-offs cap it at ~1/3 of the HBM rate (profiles/r01_topk_check.log). Here the
+// bank is streamed by plain coalesced 16-byte loads: a warp owns 8 consecutive rows per step, a lane owns 8 columns of
+// every 256-column chunk (512 contiguous bytes per row and warp-load), the queries sit in shared memory as fp32, and the
+// 8 x Q per-lane partial dot products are reduced with a transposing butterfly (8Q - 1 + log2(32 / 8Q) shuffles instead
+// of 5 per value). bf16 x bf16 products are exact in fp32; sums are fp32 like the tensor-core path.
+// Each warp keeps one sorted top-K list per query spread over its lanes (lane j = j-th best); rows arrive in increasing
+// order and insertion is strict '>', so ties keep the lowest row. Warp lists are merged per CTA in shared memory, CTA
+// lists by topk_merge_kernel (value desc, index asc).
+struct StreamParams {
+  const uint16_t* bank;
+  long long ldb, n_local;
+  const uint16_t* q;
+  long long ldq;
+  int D, Q, K;
+  long long index_base;
+  const long long* exclude;
+  long long exclude_ld;
+  int n_exclude;
+  int rows_per_cta;  // multiple of 8
+  float* part_val;      // [grid, QT, KMAX]
+  long long* part_idx;  // [grid, QT, KMAX]
+};
+
+constexpr int STREAM_THREADS = 512;
+constexpr int STREAM_WARPS = STREAM_THREADS / 32;
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+template <int QT, int NCH>
+__global__ void __launch_bounds__(STREAM_THREADS, 1) topk_stream_kernel(const StreamParams p) {
+  constexpr int NV = 8 * QT;         // values reduced per step: 8 rows x QT queries
+  constexpr int LPV = 32 / NV;       // lanes that end up holding the same value
+  constexpr int DP = NCH * 256;      // padded query length in shared memory
+  __shared__ __align__(16) float q_s[QT * DP];
+  __shared__ float m_val[STREAM_WARPS][QT][KMAX];
+  __shared__ int m_idx[STREAM_WARPS][QT][KMAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  for (int i = tid; i < QT * DP; i += STREAM_THREADS) {
+    const int qq = i / DP, d = i - qq * DP;
+    float v = 0.f;
+    if (qq < p.Q && d < p.D) v = __uint_as_float(static_cast<uint32_t>(p.q[qq * p.ldq + d]) << 16);
+    q_s[i] = v;
+  }
+  __syncthreads();
+
+  const long long cta_lo = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
+  const long long cta_hi = min(p.n_local, cta_lo + p.rows_per_cta);
+  const int n_steps = cta_hi > cta_lo ? static_cast<int>((cta_hi - cta_lo + 7) >> 3) : 0;
+
+  // per-warp top-K lists, one per query, spread over lanes 0..K-1
+  float lv[QT], thr[QT];
+  int li[QT];
+#pragma unroll
+  for (int qq = 0; qq < QT; ++qq) {
+    lv[qq] = -INFINITY;
+    li[qq] = 0x7fffffff;
+    thr[qq] = -INFINITY;
+  }
+  const int my_i = lane / LPV;   // value index this lane holds after the butterfly
+  const int my_r = my_i / QT, my_q = my_i % QT;
+  const bool rep = (lane % LPV) == 0 && my_q < p.Q;
+
+  // loads of (step, chunk): 8 rows x 16 bytes per lane; rows beyond the slice / columns beyond D read as zero
+  auto load_unit = [&](uint4 (&b)[8], int step, int c) {
+    const long long row0 = cta_lo + (static_cast<long long>(step) << 3);
+    const int col = c * 256 + lane * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      b[r] = make_uint4(0u, 0u, 0u, 0u);
+      if (row0 + r < cta_hi && col < p.D) b[r] = ldg_stream16(p.bank + (row0 + r) * p.ldb + col);
+    }
+  };
+
+  // Q <= 2: the next unit's 8 loads are in flight while this unit is reduced (double buffer); Q = 4 has no registers
+  // left for that (partial sums + query chunk = 64) and relies on the other 15 warps of the SM for overlap
+  constexpr bool DB = QT <= 2;
+  uint4 cur[8], nxt[DB ? 8 : 1];
+  int step = warp;
+  if (DB && step < n_steps) load_unit(cur, step, 0);
+  for (; step < n_steps; step += STREAM_WARPS) {
+    float acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if constexpr (DB) {  // next unit's loads go out before this unit's math
+        if (c + 1 < NCH) {
+          load_unit(nxt, step, c + 1);
+        } else if (step + STREAM_WARPS < n_steps) {
+          load_unit(nxt, step + STREAM_WARPS, 0);
+        }
+      } else {
+        load_unit(cur, step, c);
+      }
+      float qf[QT][8];
+#pragma unroll
+      for (int qq = 0; qq < QT; ++qq) {
+        const float4 a = *reinterpret_cast<const float4*>(&q_s[qq * DP + c * 256 + lane * 8]);
+        const float4 b = *reinterpret_cast<const float4*>(&q_s[qq * DP + c * 256 + lane * 8 + 4]);
+        qf[qq][0] = a.x, qf[qq][1] = a.y, qf[qq][2] = a.z, qf[qq][3] = a.w;
+        qf[qq][4] = b.x, qf[qq][5] = b.y, qf[qq][6] = b.z, qf[qq][7] = b.w;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t w[4] = {cur[r].x, cur[r].y, cur[r].z, cur[r].w};
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          x[2 * j] = __uint_as_float(w[j] << 16);
+          x[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        }
+#pragma unroll
+        for (int qq = 0; qq < QT; ++qq) {
+          float a = acc[r * QT + qq];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a = fmaf(x[j], qf[qq][j], a);
+          acc[r * QT + qq] = a;
+        }
+      }
+      if constexpr (DB) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) cur[r] = nxt[r];
+      }
+    }
+    // transposing butterfly: afterwards lanes [i*LPV, (i+1)*LPV) hold the full sum of value i = row*QT + query
+    {
+      int off = 16;
+#pragma unroll
+      for (int n = NV; n > 1; n >>= 1) {
+        const int half = n >> 1;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+          const float keep = up ? acc[j + half] : acc[j];
+          const float send = up ? acc[j] : acc[j + half];
+          acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
+      }
+#pragma unroll
+      for (int o = LPV >> 1; o > 0; o >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o);
+    }
+    const float s = acc[0];
+    const long long row0 = cta_lo + (static_cast<long long>(step) << 3);
+    float my_thr = thr[0];
+#pragma unroll
+    for (int qq = 1; qq < QT; ++qq)
+      if (my_q == qq) my_thr = thr[qq];
+    unsigned cand = __ballot_sync(0xffffffffu, rep && row0 + my_r < cta_hi && s > my_thr);
+    while (cand) {  // rare after the first few steps; everything below is warp-uniform
+      const int b = __ffs(cand) - 1;
+      cand &= cand - 1;
+      float sb = __shfl_sync(0xffffffffu, s, b);
+      const int ib = b / LPV, rb = ib / QT, qb = ib % QT;
+      const long long rowb = row0 + rb;
+      if (p.n_exclude > 0) {
+        const long long gidx = p.index_base + rowb;
+        const long long* ex = p.exclude + qb * p.exclude_ld;
+        for (int x = 0; x < p.n_exclude; ++x)
+          if (ex[x] == gidx) sb -= 1000.0f;  // gill/models.py:679-680
+      }
+#pragma unroll
+      for (int qq = 0; qq < QT; ++qq) {
+        if (qb == qq && sb > thr[qq]) {
+          // entries >= sb stay ahead (they have lower row ids); the rest shift down by one lane
+          const int pos = __popc(__ballot_sync(0xffffffffu, lane < p.K && lv[qq] >= sb));
+          const float up_v = __shfl_up_sync(0xffffffffu, lv[qq], 1);
+          const int up_i = __shfl_up_sync(0xffffffffu, li[qq], 1);
+          if (lane < p.K) {
+            if (lane > pos) {
+              lv[qq] = up_v;
+              li[qq] = up_i;
+            } else if (lane == pos) {
+              lv[qq] = sb;
+              li[qq] = static_cast<int>(rowb);
+            }
+          }
+          thr[qq] = __shfl_sync(0xffffffffu, lv[qq], p.K - 1);
+        }
+      }
+    }
+  }
+
+  // ---- CTA merge: warp lists -> shared memory -> warp qq merges query qq (value desc, row asc)
+#pragma unroll
+  for (int qq = 0; qq < QT; ++qq) {
+    if (lane < KMAX) {
+      m_val[warp][qq][lane] = lane < p.K ? lv[qq] : -INFINITY;
+      m_idx[warp][qq][lane] = lane < p.K ? li[qq] : 0x7fffffff;
+    }
+  }
+  __syncthreads();
+  if (warp < QT) {
+    const int qq = warp;
+    float last_v = INFINITY;
+    int last_i = -1;
+    for (int k = 0; k < p.K; ++k) {
+      float bv = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int t = lane; t < STREAM_WARPS * KMAX; t += 32) {
+        const float v = m_val[t / KMAX][qq][t % KMAX];
+        const int i = m_idx[t / KMAX][qq][t % KMAX];
+        const bool after = (v < last_v) || (v == last_v && i > last_i);
+        const bool better = (v > bv) || (v == bv && i < bi);
+        if (after && better) {
+          bv = v;
+          bi = i;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        const long long o = (static_cast<long long>(blockIdx.x) * QT + qq) * KMAX + k;
+        p.part_val[o] = bv;
+        p.part_idx[o] = bv == -INFINITY ? 0x7fffffffffffffffLL : p.index_base + bi;
+      }
+      last_v = bv;
+      last_i = bi;
+    }
+  }
+}
+
+template <int QT, int NCH>
+static int launch_topk_stream(const StreamParams& p, int grid, cudaStream_t stream) {
+  topk_stream_kernel<QT, NCH><<<grid, STREAM_THREADS, 0, stream>>>(p);
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+template <int QT>
+static int launch_topk_stream_q(const StreamParams& p, int grid, cudaStream_t stream) {
+  switch ((p.D + 255) / 256) {
+    case 1: return launch_topk_stream<QT, 1>(p, grid, stream);
+    case 2: return launch_topk_stream<QT, 2>(p, grid, stream);
+    case 3: return launch_topk_stream<QT, 3>(p, grid, stream);
+    default: return launch_topk_stream<QT, 4>(p, grid, stream);
   }
 }
 
@@ -244,8 +505,8 @@ extern "C" long long gillb200_topk_workspace_bytes(int Q, long long n_local) {
 
 extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, long long ld_bank, const void* q, int Q,
                                     long long ldq, int K, long long index_base, const long long* exclude_idx,
-                                    int n_exclude, void* workspace, float* out_val, long long* out_idx,
-                                    void* stream_) {
+                                    int n_exclude, long long exclude_ld, void* workspace, float* out_val,
+                                    long long* out_idx, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(bank && q && workspace && out_val && out_idx, "null pointer");
   GB_CHECK_ARG(K >= 1 && K <= KMAX, "K=%d out of range [1,%d]", K, KMAX);
@@ -253,6 +514,50 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
   GB_CHECK_ARG(n_local < (1LL << 31), "n_local must fit in int32");
   GB_CHECK_ARG(ld_bank % 8 == 0 && ldq % 8 == 0, "row strides must be multiples of 8 elements");
   GB_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "workspace must be 16-byte aligned");
+  GB_CHECK_ARG(exclude_ld == 0 || exclude_ld >= n_exclude, "exclude_ld must be 0 (shared list) or >= n_exclude");
+
+  static int env_stream = -1;
+  if (env_stream < 0) {
+    const char* ev = getenv("GILLB200_TOPK_STREAM");  // "0": always the tensor-core kernel (A/B aid)
+    env_stream = ev ? atoi(ev) : 1;
+  }
+  if (env_stream && Q <= 4 && d <= 1024 && d % 8 == 0 && reinterpret_cast<uintptr_t>(bank) % 16 == 0) {
+    // ---- bank-streaming path (HBM-bound)
+    StreamParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.bank = static_cast<const uint16_t*>(bank);
+    sp.ldb = ld_bank;
+    sp.n_local = n_local;
+    sp.q = static_cast<const uint16_t*>(q);
+    sp.ldq = ldq;
+    sp.D = d;
+    sp.Q = Q;
+    sp.K = K;
+    sp.index_base = index_base;
+    sp.exclude = exclude_idx;
+    sp.exclude_ld = exclude_ld;
+    sp.n_exclude = exclude_idx ? n_exclude : 0;
+    const int QT = Q == 1 ? 1 : Q == 2 ? 2 : 4;
+    int grid = num_sms();
+    long long per = (n_local + grid - 1) / grid;
+    per = (per + 7) / 8 * 8;
+    grid = static_cast<int>((n_local + per - 1) / per);
+    sp.rows_per_cta = static_cast<int>(per);
+    sp.part_idx = reinterpret_cast<long long*>(workspace);
+    sp.part_val = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 1LL * grid * QT * KMAX * sizeof(long long));
+    int r = QT == 1 ? launch_topk_stream_q<1>(sp, grid, stream)
+            : QT == 2 ? launch_topk_stream_q<2>(sp, grid, stream)
+                      : launch_topk_stream_q<4>(sp, grid, stream);
+    if (r) return r;
+    const int wpb = 4;
+    topk_merge_kernel<<<(Q + wpb - 1) / wpb, wpb * 32, 0, stream>>>(sp.part_val, sp.part_idx, grid, KMAX,
+                                                                   static_cast<long long>(QT) * KMAX,
+                                                                   static_cast<long long>(QT) * KMAX, K, Q, K, out_val,
+                                                                   out_idx);
+    GB_COUNT_LAUNCH(1);
+    GB_CUDA(cudaGetLastError());
+    return 0;
+  }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -287,6 +592,7 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
   e.n_local = n_local;
   e.index_base = index_base;
   e.exclude = exclude_idx;
+  e.exclude_ld = exclude_ld;
   e.n_exclude = exclude_idx ? n_exclude : 0;
   e.q_pad = num_m * BLOCK_M;
   e.tiles_per_split = tps;
@@ -296,17 +602,17 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
   e.part_val = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + part_elems * sizeof(long long));
 
   using C = GemmCfg<TOPK_BN>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(topk_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   topk_scores_kernel<<<num_m * splits, TOPK_THREADS, C::SMEM_BYTES, stream>>>(p, e);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   const int warps_per_block = 4;
   topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      e.part_val, e.part_idx, splits * 2, KMAX, static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx);
+      e.part_val, e.part_idx, splits * 2, KMAX, static_cast<long long>(e.q_pad) * KMAX,
+      static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -319,7 +625,23 @@ extern "C" int gillb200_topk_merge(const float* cand_val, const long long* cand_
   GB_CHECK_ARG(R >= 1 && Q >= 1 && K >= 1 && K <= R * Kc, "bad merge shape R=%d Q=%d Kc=%d K=%d", R, Q, Kc, K);
   const int warps_per_block = 4;
   topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      cand_val, cand_idx, R, Kc, static_cast<long long>(Q) * Kc, Kc, Q, K, out_val, out_idx);
+      cand_val, cand_idx, R, Kc, static_cast<long long>(Q) * Kc, static_cast<long long>(Q) * Kc, Kc, Q, K, out_val,
+      out_idx);
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gillb200_topk_merge_strided(const float* cand_val, long long r_stride_val, const long long* cand_idx,
+                                           long long r_stride_idx, long long q_stride, int R, int Q, int Kc, int K,
+                                           float* out_val, long long* out_idx, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(cand_val && cand_idx && out_val && out_idx, "null pointer");
+  GB_CHECK_ARG(R >= 1 && Q >= 1 && K >= 1 && K <= R * Kc && q_stride >= Kc, "bad merge shape R=%d Q=%d Kc=%d K=%d", R, Q,
+               Kc, K);
+  const int warps_per_block = 4;
+  topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
+      cand_val, cand_idx, R, q_stride, r_stride_val, r_stride_idx, Kc, Q, K, out_val, out_idx);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;

@@ -90,14 +90,25 @@ class _InputEmbeddings:
 class _LinearB200(nn.Linear):
     """nn.Linear parameters, forward on the tcgen05 GEMM (split-precision activations, fp32 accumulate)."""
 
+    def _packed(self):
+        """bf16 weight / fp32 bias copies, rebuilt only when the parameters change (load_state_dict, .to(), .bfloat16())."""
+        key = (self.weight.data_ptr(), self.weight._version, self.weight.dtype,
+               None if self.bias is None else (self.bias.data_ptr(), self.bias._version))
+        if getattr(self, "_pk_key", None) != key:
+            self._pk = (self.weight.detach().to(torch.bfloat16).contiguous(),
+                        self.bias.detach().float().contiguous() if self.bias is not None else None)
+            self._pk_key = key
+        return self._pk
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise RuntimeError("gill_b200 linears run on CUDA (sm_100a) only; there is no CPU fallback")
         shp = x.shape
         x2 = x.reshape(-1, shp[-1]).contiguous()
         hi = torch.empty(x2.shape, device=x.device, dtype=torch.bfloat16)
         lo = torch.empty_like(hi)
         ops.cast_add(x2, None, torch.bfloat16, out=hi, out_lo=lo)
-        w = self.weight.detach().to(torch.bfloat16).contiguous()
-        b = self.bias.detach().float().contiguous() if self.bias is not None else None
+        w, b = self._packed()
         o = ops.gemm(hi, w, a2=lo, a2_mode=2, bias=b, out_dtype=torch.float32)
         return o.view(*shp[:-1], -1).to(x.dtype)
 
@@ -210,11 +221,13 @@ class GILLModel(nn.Module):
             can_spec = speculative and embeddings.shape[0] == 1 and self.retrieval_token_idx[0] != -1 \
                 and self.retrieval_token_idx == self.gen_token_idx
             img_embs = self.input_embeddings(img_ids[None, :]) if can_spec else None
+            n_img = len(self.retrieval_token_idx)  # tokens appended on an [IMG0] hit (models.py:518-520); != num_tokens
+                                                   # under the default GILLArgs (retrieval_token_idx=[0])
             cached = None  # (hidden_states over T+8, logits at position T+7) carried over from a speculative hit
             kv, hs_all, n_new = None, None, embeddings.shape[1]
             if use_cache:
                 can_spec = False
-                kv = self.lm.new_cache(embeddings.shape[0], embeddings.shape[1] + max_len * max(1, self.num_tokens))
+                kv = self.lm.new_cache(embeddings.shape[0], embeddings.shape[1] + max_len * max(1, n_img))
             for i in range(max_len):
                 T = embeddings.shape[1]
                 if kv is not None:
@@ -227,7 +240,7 @@ class GILLModel(nn.Module):
                     spec_hs = None
                 elif can_spec:
                     full = torch.cat([embeddings, img_embs.to(embeddings.dtype)], dim=1)
-                    hs_full, lg2 = self.lm.forward(full, logit_positions=[T - 1, T + self.num_tokens - 1])
+                    hs_full, lg2 = self.lm.forward(full, logit_positions=[T - 1, T + n_img - 1])
                     hs, logits = hs_full[:, :T], lg2[:, 0]
                     spec_hs = (hs_full, lg2[:, 1])
                 else:
@@ -496,6 +509,9 @@ class GILL(nn.Module):
         and optionally 'ret' = (values, indices)."""
         m = self.model
         B, P, D = input_embs.shape
+        if len(m.retrieval_token_idx) != m.num_tokens:                                         # models.py:661
+            raise ValueError(f"emit_images_batch needs all {m.num_tokens} [IMG] token ids in retrieval_token_idx, "
+                             f"got {m.retrieval_token_idx}")
         img_ids = torch.tensor(m.retrieval_token_idx, dtype=torch.int64, device=m.lm.dev)
         img_embs = m.input_embeddings(img_ids[None, :])                                        # (1, 8, D)
         full = torch.cat([input_embs.to(m.lm.dev, m.lm.dt), img_embs.expand(B, -1, -1).to(m.lm.dt)], dim=1)
@@ -531,6 +547,9 @@ def load_gill(model_dir: str, load_ret_embs: bool = True, decision_model_fn: str
               device: str = "cuda") -> GILL:
     """gill/models.py:810-902. Reads model_args.json, pretrained_ckpt.pth.tar (keys `module.model.*`) and the
     cc3m*.npy pickles exactly like the reference. The frozen third-party models are injected (see module docstring)."""
+    if lm is None:
+        raise ValueError("load_gill needs `lm=` (an OPTB200 holding the OPT weights): pretrained OPT cannot be fetched "
+                         "offline, see the module docstring")
     model_args_path = os.path.join(model_dir, "model_args.json")
     model_ckpt_path = os.path.join(model_dir, "pretrained_ckpt.pth.tar")
     embs_paths = [s for s in glob.glob(os.path.join(model_dir, "cc3m*.npy"))]
@@ -571,9 +590,8 @@ def load_gill(model_dir: str, load_ret_embs: bool = True, decision_model_fn: str
         model_kwargs["retrieval_token_idx"].append(ret_token_idx[0])
     model_kwargs["gen_token_idx"] = model_kwargs["retrieval_token_idx"]                        # models.py:862
     args = namedtuple("args", model_kwargs)(**model_kwargs)
+    # like the reference (models.py:866-873): a named decision model that is missing is an error, not a silent skip
     decision_model_path = os.path.join(model_dir, decision_model_fn) if decision_model_fn is not None else None
-    if decision_model_path is not None and not os.path.exists(decision_model_path):
-        decision_model_path = None
 
     model = GILL(tokenizer, args, path_array=path_array, emb_matrix=emb_matrix, load_sd=sd_pipe is not None,
                  num_gen_images=1, decision_model_path=decision_model_path, lm=lm, sd_pipe=sd_pipe,
@@ -586,7 +604,14 @@ def load_gill(model_dir: str, load_ret_embs: bool = True, decision_model_fn: str
     state_dict = {k.replace("module.", ""): v for k, v in checkpoint["state_dict"].items()}
     img_token_embeddings = state_dict["model.input_embeddings.weight"].cpu().detach()
     del state_dict["model.input_embeddings.weight"]
-    model.load_state_dict(state_dict, strict=False)
+    # the reference loads with strict=False (models.py:887) because the checkpoint holds the trained parameters only;
+    # here every checkpoint key must land somewhere (no silent key-name drift)
+    res = model.load_state_dict(state_dict, strict=False)
+    if res.unexpected_keys:
+        raise RuntimeError(f"pretrained_ckpt.pth.tar has keys this model does not know: {res.unexpected_keys[:8]}")
+    missing = [k for k in res.missing_keys if not k.startswith("decision_model.")]
+    if missing:
+        raise RuntimeError(f"pretrained_ckpt.pth.tar lacks trained parameters: {missing[:8]}")
     with torch.no_grad():                                                                      # models.py:890-893
         if "share_ret_gen" in model_kwargs:
             assert model_kwargs["share_ret_gen"], "Model loading only supports share_ret_gen=True for now."

@@ -66,17 +66,44 @@ def _chk2d(t: torch.Tensor, name: str):
 
 
 _sk_ws = {}
+_capture_streams = {}
+
+
+def ensure_streamk_ws(device: torch.device, stream: Optional[torch.cuda.Stream] = None) -> int:
+    """Allocate (eagerly, zeroed once: the kernel's arrival flags re-arm themselves) the stream-K scratch of
+    (device, stream). One buffer per stream because two GEMMs running concurrently must not share it."""
+    device = torch.device(device)
+    stream = stream or torch.cuda.current_stream(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    ws = _sk_ws.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            # a buffer allocated during capture would live in that graph's private pool and dangle once the graph is
+            # freed while later captures keep using it
+            raise _lib.GillB200Error("stream-K workspace requested for the first time inside a CUDA-graph capture; "
+                                     "capture through gill_b200.ops.graph_capture() (it allocates the workspace first)")
+        with torch.cuda.stream(stream):
+            ws = torch.zeros(lib().gillb200_gemm_streamk_workspace_bytes(), device=device, dtype=torch.uint8)
+        stream.synchronize()
+        _sk_ws[key] = ws
+    return ws.data_ptr()
 
 
 def _streamk_ws(device: torch.device) -> int:
-    """Per-(device, stream) stream-K scratch (zeroed once: the kernel's arrival flags re-arm themselves). One buffer per
-    stream because two GEMMs running concurrently must not share it."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _sk_ws.get(key)
-    if ws is None:
-        ws = torch.zeros(lib().gillb200_gemm_streamk_workspace_bytes(), device=device, dtype=torch.uint8)
-        _sk_ws[key] = ws
-    return ws.data_ptr()
+    return ensure_streamk_ws(device, torch.cuda.current_stream(device))
+
+
+def graph_capture(graph: "torch.cuda.CUDAGraph", device=None):
+    """`torch.cuda.graph(graph)` on a long-lived per-device capture stream whose stream-K workspace exists BEFORE the
+    capture starts (eager allocation, outside every graph's private memory pool)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _capture_streams.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _capture_streams[idx] = st
+    ensure_streamk_ws(device, st)
+    return torch.cuda.graph(graph, stream=st)
 
 
 def _attach_stats(g: GemmArgs, M: int, n_out: int, device) -> torch.Tensor:
@@ -235,9 +262,10 @@ def conv3x3(
 
 
 def topk_scores(bank: torch.Tensor, q: torch.Tensor, k: int, *, index_base: int = 0,
-                exclude_idx: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None):
-    """Fused (bank @ q.T) + top-k. bank [N,D] bf16, q [Q,D] bf16 -> (values [Q,k] fp32, global indices [Q,k] int64).
-    Ties resolve to the lowest row index. exclude_idx: int64 device tensor of global rows to down-weight by 1000."""
+                exclude_idx: Optional[torch.Tensor] = None, workspace: Optional[torch.Tensor] = None, out=None):
+    """Fused (bank @ q.T) + top-k. bank [N,D] bf16, q [Q,D] bf16 (row stride free) -> (values [Q,k] fp32, global
+    indices [Q,k] int64). Ties resolve to the lowest row index. exclude_idx: int64 device tensor of global rows to
+    down-weight by 1000 -- [n] / [1,n] (shared by all queries) or [Q,n] (one list per query; entries < 0 are unused)."""
     _chk2d(bank, "bank")
     _chk2d(q, "q")
     assert bank.dtype == torch.bfloat16 and q.dtype == torch.bfloat16 and bank.shape[1] == q.shape[1]
@@ -245,14 +273,23 @@ def topk_scores(bank: torch.Tensor, q: torch.Tensor, k: int, *, index_base: int 
     need = lib().gillb200_topk_workspace_bytes(Q, N)
     if workspace is None or workspace.numel() < need:
         workspace = torch.empty(need, device=bank.device, dtype=torch.uint8)
-    vals = torch.empty((Q, k), device=bank.device, dtype=torch.float32)
-    idx = torch.empty((Q, k), device=bank.device, dtype=torch.int64)
-    n_ex = 0 if exclude_idx is None else exclude_idx.numel()
-    if n_ex:
-        assert exclude_idx.dtype == torch.int64 and exclude_idx.is_cuda and exclude_idx.is_contiguous()
-    with _P("topk_scores", 2.0 * N * bank.shape[1] * Q, 2.0 * N * bank.shape[1]):
+    if out is None:
+        vals = torch.empty((Q, k), device=bank.device, dtype=torch.float32)
+        idx = torch.empty((Q, k), device=bank.device, dtype=torch.int64)
+    else:
+        vals, idx = out
+        assert vals.dtype == torch.float32 and idx.dtype == torch.int64 and vals.is_contiguous() and idx.is_contiguous()
+        assert tuple(vals.shape) == (Q, k) and tuple(idx.shape) == (Q, k)
+    n_ex, ex_ld = 0, 0
+    if exclude_idx is not None and exclude_idx.numel() > 0:
+        ex = exclude_idx if exclude_idx.dim() == 2 else exclude_idx.view(1, -1)
+        assert ex.dtype == torch.int64 and ex.is_cuda and ex.stride(1) == 1 and ex.shape[0] in (1, Q)
+        n_ex = ex.shape[1]
+        ex_ld = ex.stride(0) if ex.shape[0] == Q and Q > 1 else 0
+        exclude_idx = ex
+    with _P("topk_scores", 2.0 * N * bank.shape[1] * Q, 2.0 * N * bank.shape[1], f"N{N} D{bank.shape[1]} Q{Q} K{k}"):
         check(lib().gillb200_topk_scores(bank.data_ptr(), N, bank.shape[1], bank.stride(0), q.data_ptr(), Q,
-                                         q.stride(0), k, index_base, _ptr(exclude_idx) if n_ex else None, n_ex,
+                                         q.stride(0), k, index_base, _ptr(exclude_idx) if n_ex else None, n_ex, ex_ld,
                                          workspace.data_ptr(), vals.data_ptr(), idx.data_ptr(), _stream()),
               "gillb200_topk_scores")
     return vals, idx
@@ -271,9 +308,28 @@ def topk_merge(cand_val: torch.Tensor, cand_idx: torch.Tensor, k: int):
     return vals, idx
 
 
+def topk_merge_packed(recv: torch.Tensor, R: int, list_bytes: int, idx_offset_bytes: int, q_first: int, Q: int, Kc: int,
+                      k: int, out=None):
+    """Merge straight out of a packed exchange buffer (ShardedBank): `recv` holds R lists of `list_bytes` bytes, each
+    [fp32 values [Qall,Kc] | padding | int64 indices [Qall,Kc] at idx_offset_bytes]; merges queries q_first..q_first+Q."""
+    assert recv.dtype == torch.uint8 and recv.is_contiguous() and list_bytes % 8 == 0 and idx_offset_bytes % 8 == 0
+    if out is None:
+        vals = torch.empty((Q, k), device=recv.device, dtype=torch.float32)
+        idx = torch.empty((Q, k), device=recv.device, dtype=torch.int64)
+    else:
+        vals, idx = out
+    base = recv.data_ptr()
+    with _P("topk_merge"):
+        check(lib().gillb200_topk_merge_strided(base + q_first * Kc * 4, list_bytes // 4,
+                                                base + idx_offset_bytes + q_first * Kc * 8, list_bytes // 8, Kc, R, Q, Kc,
+                                                k, vals.data_ptr(), idx.data_ptr(), _stream()),
+              "gillb200_topk_merge_strided")
+    return vals, idx
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_pad: int, scale: float, *,
               out: Optional[torch.Tensor] = None, causal: bool = False, causal_offset: int = 0,
-              kv_lens: Optional[torch.Tensor] = None, ones_col: int = 0) -> torch.Tensor:
+              kv_lens: Optional[torch.Tensor] = None, ones_col: int = 0, head_dim: int = 0) -> torch.Tensor:
     """q [B,Lq,>=H*hd_pad], k/v [B,Lk,>=H*hd_pad] (views into fused QKV buffers allowed; last dim contiguous).
     Returns out [B,Lq,H*hd_pad]. Pad columns of each head must be zero in q, k, v -- except that v may carry 1.0 in
     pad column `ones_col` (> 0) of every head, which moves the softmax row sum onto the tensor core."""
@@ -291,8 +347,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
     a.B, a.H, a.Lq, a.Lk, a.hd_pad = B, heads, Lq, Lk, hd_pad
     a.causal, a.causal_offset = int(causal), causal_offset
     a.dtype, a.scale, a.ones_col = _DT[q.dtype], scale, ones_col
-    with _P("attention", 4.0 * B * heads * Lq * Lk * hd_pad, 2.0 * B * heads * hd_pad * (2 * Lq + 2 * Lk),
-            f"B{B} H{heads} Lq{Lq} Lk{Lk} hp{hd_pad}"):
+    # profile records count ALGORITHMIC work: the true head dim (head_dim, when the caller states it), not the padding
+    hd = head_dim or hd_pad
+    with _P("attention", 4.0 * B * heads * Lq * Lk * hd * (0.5 if causal and Lq == Lk else 1.0),
+            2.0 * B * heads * hd * (2 * Lq + 2 * Lk), f"B{B} H{heads} Lq{Lq} Lk{Lk} hd{hd} hp{hd_pad}"):
         check(lib().gillb200_attention(ctypes.byref(a), _stream()), "gillb200_attention")
     return out
 

@@ -30,8 +30,9 @@ class OPTB200:
         """sd: OPTForCausalLM-named state dict (`model.decoder.*`); weights are stored bf16, biases / norms fp32."""
         self.D, self.L, self.H, self.F = hidden, layers, heads, ffn
         self.hd = hidden // heads
-        if self.hd != 128:
-            raise ValueError(f"OPTB200 supports head_dim 128 (OPT-6.7B family), got {self.hd}")
+        if self.hd not in (64, 128):
+            raise ValueError(f"OPTB200 supports head_dim 64 (OPT-125M, BASELINE configs[0]) and 128 (OPT-6.7B family), "
+                             f"got {self.hd}")
         self.dev, self.dt = torch.device(device), dtype
         f32 = torch.float32
         p = "model.decoder."

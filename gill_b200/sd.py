@@ -339,13 +339,13 @@ class UNetB200:
         oc = hd if hp > hd else 0
         qkv = ops.gemm(n1, w[t + ".attn1.qkv"], bias=w[t + ".attn1.qkv_bias"]).view(B, L, 3 * Hh * hp)
         a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
-                          hd ** -0.5, ones_col=oc)
+                          hd ** -0.5, ones_col=oc, head_dim=hd)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h)
         # cross attention against the precomputed K/V of the conditioning
         n2 = ops.layernorm(h, w[t + ".norm2.weight"], w[t + ".norm2.bias"], 1e-5)
         q = ops.gemm(n2, w[t + ".attn2.q"]).view(B, L, Hh * hp)
         kv = ctx_kv[p]
-        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc)
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc, head_dim=hd)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h)
         # GEGLU feed-forward
         n3 = ops.layernorm(h, w[t + ".norm3.weight"], w[t + ".norm3.bias"], 1e-5)
@@ -370,12 +370,12 @@ class UNetB200:
         qkv = ops.gemm(h, w[t + ".attn1.qkv_ln"], bias=w[t + ".attn1.qkv_lnb"],
                        ln=(h.ln_stats, w[t + ".attn1.qkv_cs"], 1e-5)).view(B, L, 3 * Hh * hp)
         a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
-                          hd ** -0.5, ones_col=oc)
+                          hd ** -0.5, ones_col=oc, head_dim=hd)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h, rowstats=True)
         q = ops.gemm(h, w[t + ".attn2.q_ln"], bias=w[t + ".attn2.q_lnb"],
                      ln=(h.ln_stats, w[t + ".attn2.q_cs"], 1e-5)).view(B, L, Hh * hp)
         kv = ctx_kv[p]
-        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc)
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc, head_dim=hd)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h, rowstats=True)
         g = ops.gemm(h, w[t + ".ff.geglu.weight_ln"], bias=w[t + ".ff.geglu.weight_lnb"], act="geglu",
                      ln=(h.ln_stats, w[t + ".ff.geglu.weight_cs"], 1e-5))
@@ -579,7 +579,7 @@ class StableDiffusionB200:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = lib().gillb200_launch_count()
-            with torch.cuda.graph(g):
+            with ops.graph_capture(g, self.device):
                 st["eps"] = self.unet.forward(pair, None, st["ctx_kv"])
             st["launches_per_eval"] = lib().gillb200_launch_count() - n0
             st["graph"] = g

@@ -140,3 +140,35 @@ def build_gill(device="cuda", opt="opt-6.7b", tiny_sd=False, with_sd=True, seed=
     gill = gill.eval().to(device)
     kind = load_gill_trained_weights(gill, device)
     return gill, kind
+
+
+# ---- synthetic retrieval banks: identical on every machine / GPU count ------------------------
+BANK_CHUNKS = 8
+
+
+def synthetic_bank_chunk(c: int, rows: int, d: int, exact: bool = False, device="cpu") -> torch.Tensor:
+    """Chunk c of the synthetic bank: seed 7000+c, randn -> row-normalise -> x14.24 -> bf16 (tier B), or values
+    randint(-4,5)/8 (tier A: exactly representable, order-independent fp32 sums). `device` selects the generator too:
+    CPU chunks are what the oracle tests use, CUDA chunks (a different but equally deterministic stream) fill the
+    3M-row benchmark bank quickly; a given (c, rows, d, device type) always yields the same rows, whatever the GPU count."""
+    g = torch.Generator(device=device).manual_seed(7000 + c)
+    if exact:
+        return (torch.randint(-4, 5, (rows, d), generator=g, device=device).float() / 8).bfloat16()
+    m = torch.randn(rows, d, generator=g, device=device)
+    m = m / m.norm(dim=1, keepdim=True)
+    return (m * 14.24).bfloat16()
+
+
+def synthetic_queries(q: int, d: int, exact: bool = False, seed: int = 8) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    if exact:
+        return (torch.randint(-4, 5, (q, d), generator=g).float() / 8).bfloat16()
+    m = torch.randn(q, d, generator=g)
+    return (m / m.norm(dim=1, keepdim=True)).bfloat16()
+
+
+def synthetic_bank_shard(n_total: int, d: int, world: int, rank: int, exact: bool = False, device="cuda") -> torch.Tensor:
+    """Rows [rank*n/world, (rank+1)*n/world) of the 8-chunk synthetic bank (world must divide 8, n_total % 8 == 0)."""
+    assert BANK_CHUNKS % world == 0 and n_total % BANK_CHUNKS == 0
+    per, rows = BANK_CHUNKS // world, n_total // BANK_CHUNKS
+    return torch.cat([synthetic_bank_chunk(c, rows, d, exact, device) for c in range(rank * per, (rank + 1) * per)], 0)

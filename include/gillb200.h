@@ -117,15 +117,25 @@ int gillb200_gemm(const gillb200_gemm_args* args, void* stream);
  *   out = top-K per query, value descending, ties -> lowest global index; out_idx = index_base + local row.
  *
  * bank: [n_local, d] bf16 (already normalised and scaled as in models.py:895-900), q: [Q, d] bf16, K <= 16.
+ * exclude_idx: [Q or 1, n_exclude] int64 global row ids on the device (entries < 0 are unused slots); exclude_ld = elements
+ *   between the lists of consecutive queries, 0 = one list shared by all queries (the reference keeps one `seen_image_idx`
+ *   list per conversation, models.py:679; batched callers pass one list per query).
  * `workspace` must hold gillb200_topk_workspace_bytes(Q, n_local) bytes of device memory.
- * gillb200_topk_merge merges R candidate lists [R, Q, Kc] (e.g. one per GPU after the NCCL all-gather).
+ * Q <= 4 (the reference's call shape is Q = 1, K = 3) takes a bank-streaming kernel bound by HBM; larger batches the
+ * tcgen05 kernel bound by the tensor cores.
+ * gillb200_topk_merge merges R candidate lists [R, Q, Kc] (e.g. one per GPU after the NCCL all-gather);
+ * gillb200_topk_merge_strided does the same over lists that sit inside a packed exchange buffer: list r's values start at
+ * cand_val + r * r_stride_val, its indices at cand_idx + r * r_stride_idx, query q at + q * q_stride (all in elements).
  * ------------------------------------------------------------------------------------------------------------- */
 long long gillb200_topk_workspace_bytes(int Q, long long n_local);
 int gillb200_topk_scores(const void* bank, long long n_local, int d, long long ld_bank, const void* q, int Q,
                          long long ldq, int K, long long index_base, const long long* exclude_idx, int n_exclude,
-                         void* workspace, float* out_val, long long* out_idx, void* stream);
+                         long long exclude_ld, void* workspace, float* out_val, long long* out_idx, void* stream);
 int gillb200_topk_merge(const float* cand_val, const long long* cand_idx, int R, int Q, int Kc, int K, float* out_val,
                         long long* out_idx, void* stream);
+int gillb200_topk_merge_strided(const float* cand_val, long long r_stride_val, const long long* cand_idx,
+                                long long r_stride_idx, long long q_stride, int R, int Q, int Kc, int K, float* out_val,
+                                long long* out_idx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused multi-head attention  out = softmax(scale * Q K^T [+ causal / length mask]) V   (flash style, tcgen05).

@@ -10,6 +10,9 @@ Fixtures (all inputs are seeded; every file records how it was made):
   retrieval_tierA.npz   the reference expression `emb_matrix @ ret_emb.T; scores[seen] -= 1000; topk(3)` (fp32, CPU)
   opt_tiny.npz          transformers OPTForCausalLM (config-built, seeded) hidden_states[-1] / logits
   generate_tiny.npz     reference `GILLModel.generate` (patched to a config-built tiny OPT) ids / hidden / logits
+  opt_wide.npz          transformers OPTForCausalLM at the BENCHMARKED width (hidden 4096, 32 heads, ffn 16384; 2 layers),
+                        B=8, T=81: the 8 [IMG]-position hidden states + strided last-real-position logits
+  opt_125m.npz          the same at the OPT-125M shape (hidden 768, 12 heads of 64, ffn 3072; 2 layers), BASELINE configs[0]
 """
 import os
 import sys
@@ -105,6 +108,40 @@ def golden_opt():
     return hc, sd, cfg
 
 
+def wide_inputs(cfg, B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, T, cfg["hidden"], generator=g) * 0.05).bfloat16().float()
+
+
+@torch.no_grad()
+def golden_opt_shapes():
+    """OPT at the benchmarked width and at the OPT-125M head size: what the hot path consumes -- hidden
+    states of the 8 trailing [IMG] positions and the logits of the last prompt position (every 16th vocabulary entry
+    plus the last 16, which hold the [IMG] ids), from transformers' own OPTForCausalLM."""
+    from transformers import OPTConfig, OPTForCausalLM
+
+    for name, base, seed, B, T in (("opt_wide.npz", "opt-6.7b", 5, 8, 81), ("opt_125m.npz", "opt-125m", 6, 2, 33)):
+        cfg = dict(oopt.opt_config(base), layers=2)
+        sd = {k: v.bfloat16().float() for k, v in oopt.init_opt(cfg, seed=seed).items()}
+        hc = OPTConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"],
+                       num_attention_heads=cfg["heads"], ffn_dim=cfg["ffn"], max_position_embeddings=cfg["max_pos"],
+                       word_embed_proj_dim=cfg["hidden"], do_layer_norm_before=True, activation_function="relu")
+        m = OPTForCausalLM(hc).eval()
+        m.load_state_dict({**sd, "lm_head.weight": sd["model.decoder.embed_tokens.weight"]}, strict=True)
+        x = wide_inputs(cfg, B, T, seed + 100)
+        o = m(inputs_embeds=x, use_cache=False, output_hidden_states=True)
+        hs, lg = o.hidden_states[-1], o.logits[:, T - 9]
+        o_hs, o_lg = oopt.opt_forward(sd, cfg, x)
+        assert torch.allclose(o_hs, hs, atol=2e-4, rtol=1e-4), (name, (o_hs - hs).abs().max())
+        assert torch.allclose(o_lg[:, T - 9], lg, atol=2e-4, rtol=1e-4), name
+        sel = torch.cat([torch.arange(0, cfg["vocab"] - 16, 16), torch.arange(cfg["vocab"] - 16, cfg["vocab"])])
+        save(name, hidden_img=hs[:, T - 8:].half(), logits_sel=lg[:, sel], sel=sel.numpy(),
+             hidden_rms=np.float32(hs.pow(2).mean().sqrt().item()),
+             note=f"transformers OPTForCausalLM({base} shape, 2 layers), weights=init_opt(seed {seed}).bfloat16(), "
+                  f"x=randn({B},{T},{cfg['hidden']},seed {seed + 100})*0.05 bf16; hidden_img = hidden_states[-1][:, -8:] (fp16), "
+                  f"logits_sel = logits[:, T-9, sel]")
+
+
 @torch.no_grad()
 def golden_generate(hc, sd, cfg):
     """The reference's own GILLModel.generate with OPT/CLIP patched to config-built models."""
@@ -159,3 +196,4 @@ if __name__ == "__main__":
     golden_retrieval()
     hc, sd, cfg = golden_opt()
     golden_generate(hc, sd, cfg)
+    golden_opt_shapes()

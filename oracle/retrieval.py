@@ -67,25 +67,5 @@ def merge_topk(vals: torch.Tensor, idx: torch.Tensor, k: int) -> Tuple[torch.Ten
     return torch.gather(v, 1, o2)[:, :k].contiguous(), torch.gather(i, 1, o2)[:, :k].contiguous()
 
 
-# ---- synthetic banks: identical on every machine / GPU count -------------------------------
-
-BANK_CHUNKS = 8
-
-
-def synthetic_bank_chunk(c: int, rows: int, d: int, exact: bool = False) -> torch.Tensor:
-    """Chunk c of the synthetic bank: seed 7000+c, randn -> row-normalise -> x14.24 -> bf16 (tier B), or values
-    randint(-4,5)/8 (tier A: exactly representable, order-independent fp32 sums)."""
-    g = torch.Generator().manual_seed(7000 + c)
-    if exact:
-        return (torch.randint(-4, 5, (rows, d), generator=g).float() / 8).bfloat16()
-    m = torch.randn(rows, d, generator=g)
-    m = m / m.norm(dim=1, keepdim=True)
-    return (m * 14.24).bfloat16()
-
-
-def synthetic_queries(q: int, d: int, exact: bool = False, seed: int = 8) -> torch.Tensor:
-    g = torch.Generator().manual_seed(seed)
-    if exact:
-        return (torch.randint(-4, 5, (q, d), generator=g).float() / 8).bfloat16()
-    m = torch.randn(q, d, generator=g)
-    return (m / m.norm(dim=1, keepdim=True)).bfloat16()
+# ---- synthetic banks: one definition, shared with bench.py's product arm through harness/ ----
+from harness.synthetic import BANK_CHUNKS, synthetic_bank_chunk, synthetic_queries  # noqa: E402,F401

@@ -77,10 +77,36 @@ def _worker(rank, world, port, q_out):
     bank = orc.synthetic_bank_chunk(0, N, D, exact=True)
     lo, hi = shard_rows(N, world, rank)
     q_all = orc.synthetic_queries(world * Ql, D, exact=True)
-    sb = ShardedBank(bank[lo:hi], N, local_topk=lambda b, q, k, ex, base: orc.retrieval_topk(b, q, k, ex, base),
-                     merge=orc.merge_topk)
-    v, i = sb.search(q_all[rank * Ql:(rank + 1) * Ql], K, exclude_idx=[0, 500, 1000])
-    rv, ri = orc.retrieval_topk(bank, q_all[rank * Ql:(rank + 1) * Ql], K, exclude_idx=[0, 500, 1000])
+
+    def local_topk(b, q, k, ex, base):
+        # per-query seen lists [Q, E] (-1 = unused slot), as the CUDA kernel takes them
+        vs, is_ = [], []
+        for j in range(q.shape[0]):
+            seen = [int(e) for e in ex[j].tolist() if e >= 0] if ex is not None else None
+            v, i = orc.retrieval_topk(b, q[j:j + 1].contiguous(), k, seen, base)
+            vs.append(v)
+            is_.append(i)
+        return torch.cat(vs), torch.cat(is_)
+
+    sb = ShardedBank(bank[lo:hi], N, local_topk=local_topk, merge=orc.merge_topk)
+    # every rank has its OWN seen lists (one per query): remote shards must filter with the owner's list
+    mine = q_all[rank * Ql:(rank + 1) * Ql]
+    first = orc.retrieval_topk(bank, mine, K)[1]
+    seen = [[int(first[j, 0]), int(first[j, 2])] if (j + rank) % 2 == 0 else [int(first[j, 1])] for j in range(Ql)]
+    v, i = sb.search(mine, K, exclude_idx=seen)
+    rv = torch.empty(Ql, K)
+    ri = torch.empty(Ql, K, dtype=torch.int64)
+    for j in range(Ql):
+        rv[j], ri[j] = (t[0] for t in orc.retrieval_topk(bank, mine[j:j + 1], K, exclude_idx=seen[j]))
+    ok = bool(torch.equal(v, rv) and torch.equal(i, ri))
+    # a shared list and no list at all go through the same exchange
+    v2, i2 = sb.search(mine, K, exclude_idx=[0, 500, 1000])
+    rv2, ri2 = orc.retrieval_topk(bank, mine, K, exclude_idx=[0, 500, 1000])
+    ok = ok and bool(torch.equal(v2, rv2) and torch.equal(i2, ri2))
+    v3, i3 = sb.search(mine, K)
+    rv3, ri3 = orc.retrieval_topk(bank, mine, K)
+    ok = ok and bool(torch.equal(v3, rv3) and torch.equal(i3, ri3))
+    v, i, rv, ri = v3, i3, rv3, ri3
     q_out.put((rank, bool(torch.equal(v, rv) and torch.equal(i, ri))))
     dist.destroy_process_group()
 

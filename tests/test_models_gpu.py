@@ -96,6 +96,30 @@ def test_opt_forward_matches_transformers_fixture(golden):
     assert torch.equal(out.logits[:, -1, :], lg) and torch.equal(out.hidden_states[-1], hs)
 
 
+@pytest.mark.parametrize("name", ["opt_wide.npz", "opt_125m.npz"])
+def test_opt_forward_at_the_benchmarked_width_matches_oracle_and_transformers(golden, name):
+    """The shape bench.py runs (hidden 4096, 32 heads of 128, ffn 16384, B=8, T=81 = 73 prompt + 8 [IMG] tokens; 2 layers)
+    and the OPT-125M head size (12 heads of 64): hidden states of every position against the CPU oracle, and the
+    [IMG]-position hidden states / last-prompt-position logits against the transformers-generated fixture."""
+    from gill_b200.opt import OPTB200
+    from oracle import opt as oopt
+
+    g = golden(name)
+    cfg, sd, x, T = oopt.shape_case(name)
+    lm = OPTB200(sd, cfg["hidden"], cfg["layers"], cfg["heads"], cfg["ffn"], device=dev)
+    hs, lg = lm.forward(x.to(dev).bfloat16(), logit_positions=[T - 9])
+    ref_hs, ref_lg = oopt.opt_forward(sd, cfg, x)
+    # bf16 operands and bf16 hidden-state output, as the reference runs OPT: 1.5e-2 relative
+    assert rel(hs, ref_hs) < 1.5e-2 and rel(lg[:, 0], ref_lg[:, T - 9]) < 1.5e-2
+    assert rel(hs[:, T - 8:], g["hidden_img"].astype(np.float32)) < 1.5e-2
+    assert rel(lg[:, 0][:, torch.as_tensor(g["sel"]).to(dev)], g["logits_sel"]) < 1.5e-2
+    # KV-cached continuation over the 8 [IMG] tokens is bit-identical to the one-shot prefill
+    kv = lm.new_cache(x.shape[0], T)
+    lm.forward(x[:, :T - 8].to(dev).bfloat16(), need_logits=False, cache=kv)
+    hs2, _ = lm.forward(x[:, T - 8:].to(dev).bfloat16(), need_logits=False, cache=kv)
+    assert torch.equal(hs2, hs[:, T - 8:])
+
+
 class _Tok:
     cls_token_id, pad_token_id, bos_token_id = 512 - 9, 2, 2
 
@@ -134,6 +158,24 @@ def test_generate_matches_reference_generate_fixture(golden, speculative):
     torch.manual_seed(0)
     ids, _, _ = gm.generate(emb.to(dev), max_len=3, temperature=0.7, top_p=0.9)
     assert ids.shape[0] == 1 and ids.shape[1] >= 3
+
+
+def test_generate_with_default_gill_args():
+    """under the default GILLArgs (retrieval_token_idx=[0], num_tokens=8) the speculative forward appends ONE
+    token, so the look-ahead logits sit at T, not T + 7. Speculative and plain decoding must agree and not index past
+    the sequence."""
+    from gill_b200 import models
+
+    lm, cfg, _ = tiny_opt()
+    a = models.GILLArgs()
+    gm = models.GILLModel(_Tok(), a, lm=lm, visual_hidden_size=64)
+    ge = torch.Generator().manual_seed(12)
+    emb = (torch.randn(1, 7, cfg["hidden"], generator=ge) * 0.05).bfloat16().to(dev)
+    for kw in (dict(max_len=3), dict(max_len=3, gen_scale_factor=1e5, ret_scale_factor=1e5)):
+        i0, e0, l0 = gm.generate(emb, speculative=False, **kw)
+        i1, e1, l1 = gm.generate(emb, speculative=True, **kw)
+        assert torch.equal(i0, i1) and len(e0) == len(e1)
+        assert all(a_.shape == b_.shape for a_, b_ in zip(e0, e1)) and rel(e1[-1], e0[-1]) < 2e-2
 
 
 def test_generate_with_kv_cache_is_bit_identical(golden):
@@ -345,7 +387,104 @@ def test_full_unet_single_eval_matches_oracle():
     assert rel(eps2.permute(0, 3, 1, 2), ref) < 5e-3 and rel(eps, eps2) < 3e-3
 
 
+def test_full_unet_b16_eval_matches_oracle():
+    """The batch the bench runs (B=16 = 8 prompts x CFG pair; picks the CTA-pair / stream-K / wide-tile dispatch the B=2
+    test never reaches). Samples are independent, so the CPU oracle evaluates three of them."""
+    from gill_b200 import sd as psd
+    from oracle import sd15 as osd
+
+    usd = {k: v.half().float() for k, v in osd.init_unet(0).items()}
+    unet = psd.UNetB200(usd, device=dev)
+    table = psd.plms_table(50)
+    unet.prepare_timesteps([t for t, _, _, _ in table])
+    g = torch.Generator().manual_seed(15)
+    lat = torch.randn(16, 4, 64, 64, generator=g).half().float()
+    ctx = torch.randn(16, 77, 768, generator=g).half().float()
+    kv = unet.precompute_ctx(ctx.to(dev))
+    x = lat.permute(0, 2, 3, 1).contiguous().to(dev).half()
+    eps = unet.forward(x, 7, kv).permute(0, 3, 1, 2)
+    pick = [0, 9, 15]
+    ref = osd.unet_forward(usd, lat[pick], table[7][0], ctx[pick])
+    for j, s_ in enumerate(pick):
+        assert rel(eps[s_], ref[j]) < 5e-3, s_
+    # deterministic across calls (stream-K partials are reduced in CTA order)
+    assert torch.equal(unet.forward(x, 7, kv).permute(0, 3, 1, 2), eps)
+
+
+def test_full_vae_decode_u8_matches_oracle():
+    """The real decoder (49.5 M parameters, 64x64 latents -> 512x512 uint8), against the CPU fp32 oracle."""
+    from gill_b200 import sd as psd
+    from oracle import sd15 as osd
+
+    vsd = {k: v.half().float() for k, v in osd.init_vae_decoder(1).items()}
+    vae = psd.VAEDecoderB200(vsd, device=dev)
+    g = torch.Generator().manual_seed(16)
+    z = torch.randn(2, 4, 64, 64, generator=g) * 0.18215 * 4
+    u8 = vae.decode_u8(z.permute(0, 2, 3, 1).contiguous().to(dev))
+    ref = osd.to_uint8_nhwc(osd.vae_decode(vsd, z[:1]))
+    assert u8.shape == (2, 512, 512, 3) and u8.dtype == torch.uint8
+    d = (u8[:1].cpu().int() - ref.int()).abs()
+    assert d.max() <= 2 and d.float().mean() < 0.2                                  # pixel tolerance: <= 2/255
+    assert int(u8.max()) > int(u8.min())                                             # not a constant image
+
+
 # ------------------------------------------------------------------------------------------------ GILL surface
+def test_load_gill_real_checkpoint_and_decision_head(tmp_path):
+    """The reference's public factory (gill/models.py:810-902) on the SHIPPED model directory: model_args.json,
+    pretrained_ckpt.pth.tar (strict key coverage), decision_model.pth.tar, a cc3m*.npy pickle; then the retrieval +
+    decision branch of generate_for_images_and_texts (models.py:671-701) runs with the real decision MLP."""
+    import os
+    import pickle
+
+    from gill_b200 import models, retrieval
+    from gill_b200.opt import OPTB200
+    from harness import synthetic
+
+    if not synthetic.real_checkpoint_available():
+        pytest.skip("shipped checkpoint not present")
+    for fn in ("model_args.json", "pretrained_ckpt.pth.tar", "decision_model.pth.tar"):
+        os.symlink(os.path.join(synthetic.CKPT_DIR, fn), tmp_path / fn)
+    g = torch.Generator().manual_seed(31)
+    n = 2000
+    emb = torch.randn(n, 256, generator=g)
+    with open(tmp_path / "cc3m_embeddings_0.npy", "wb") as f:                        # models.py:813-839 pickle format
+        pickle.dump({"paths": [f"http://127.0.0.1:9/{i}.jpg" for i in range(n)],
+                     "embeddings": [emb[i].numpy() for i in range(n)]}, f)
+    tok = synthetic.SyntheticTokenizer()
+    with pytest.raises(ValueError):
+        models.load_gill(str(tmp_path), tokenizer=tok)                               # no OPT injected: fail up front
+    lm = OPTB200.random_init(4096, 2, 32, 16384, vocab=len(tok), seed=0, device=dev)
+    sd_pipe = synthetic.build_sd(dev, tiny=True)[0]
+    gill = models.load_gill(str(tmp_path), tokenizer=tok, lm=lm, sd_pipe=sd_pipe)
+    ck = torch.load(os.path.join(synthetic.CKPT_DIR, "pretrained_ckpt.pth.tar"), map_location="cpu")["state_dict"]
+    # [IMG] rows copied into the OPT table (models.py:890-893), trained heads loaded
+    assert torch.equal(lm.embed[-8:].cpu(), ck["module.model.input_embeddings.weight"].to(lm.embed.dtype))
+    assert gill.model.retrieval_token_idx == list(range(50266, 50274)) == gill.model.gen_token_idx
+    w = gill.model.gen_text_hidden_fcs[0].fc.weight
+    assert torch.equal(w.detach().cpu().float(), ck["module.model.gen_text_hidden_fcs.0.fc.weight"].float())
+    assert gill.emb_matrix.shape == (n, 256) and gill.emb_matrix.dtype == torch.bfloat16 and len(gill.path_array) == n
+    expect = retrieval.prepare_bank(emb.numpy(), ck["module.model.logit_scale"].to(dev))
+    assert torch.equal(gill.emb_matrix, expect)
+    # decision head: Linear(4096 -> 2) of the shipped decision_model.pth.tar against torch's own nn.Linear in fp32
+    dm = torch.load(os.path.join(synthetic.CKPT_DIR, "decision_model.pth.tar"), map_location="cpu")["state_dict"]
+    x = torch.randn(5, 4096, generator=g)
+    got = gill.decision_model(x.to(dev)).float().cpu()
+    ref = torch.nn.functional.linear(x, dm["1.weight"].bfloat16().float(), dm["1.bias"].bfloat16().float())
+    assert rel(got, ref) < 1e-3                                                      # model.bfloat16(): weights are bf16
+    # the whole branch inside the surface: retrieval (fetches fail offline), decision label + probabilities, generation
+    out = gill.generate_for_images_and_texts(["a photo of a cat"], num_words=2, gen_scale_factor=1e5,
+                                             num_inference_steps=2)
+    dec = out[1]["decision"]
+    assert dec[0] in ("gen", "ret") and len(dec[1]) == 2 and abs(sum(dec[1]) - 1.0) < 1e-2
+    assert out[1]["ret"] == [] and len(out[1]["gen"]) == 1
+    # a named decision model that does not exist is an error, as in the reference
+    with pytest.raises(FileNotFoundError):
+        models.load_gill(str(tmp_path), decision_model_fn="nope.pth.tar", tokenizer=tok, lm=lm, sd_pipe=sd_pipe)
+    # and without one the default decision is reported (models.py:704 applies only without a bank; with a bank: None)
+    g2 = models.load_gill(str(tmp_path), load_ret_embs=False, decision_model_fn=None, tokenizer=tok, lm=lm, sd_pipe=sd_pipe)
+    assert g2.emb_matrix is None and g2.decision_model is None
+
+
 @pytest.fixture(scope="module")
 def gill_small():
     from harness import synthetic

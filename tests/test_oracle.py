@@ -84,6 +84,17 @@ def test_opt_oracle_matches_transformers(golden):
     assert rel(hs, g["hidden"]) < 2e-6 and rel(lg[:, -1], g["last_logits"]) < 2e-6
 
 
+@pytest.mark.parametrize("name", ["opt_125m.npz", "opt_wide.npz"])
+def test_opt_oracle_matches_transformers_at_the_benchmarked_shapes(golden, name):
+    """the OPT oracle pinned by transformers' OPTForCausalLM at hidden 4096 / 32 heads / ffn 16384 (the
+    benchmarked width, 2 layers, B=8, T=81) and at the OPT-125M head size (BASELINE configs[0])."""
+    g = golden(name)
+    cfg, sd, x, T = oopt.shape_case(name)
+    hs, lg = oopt.opt_forward(sd, cfg, x)
+    assert rel(hs[:, T - 8:], g["hidden_img"].astype(np.float32)) < 1e-3          # fixture stored as fp16
+    assert rel(lg[:, T - 9][:, torch.as_tensor(g["sel"])], g["logits_sel"]) < 1e-4
+
+
 def test_generate_oracle_matches_reference_generate(golden):
     g = golden("generate_tiny.npz")
     cfg = oopt.opt_config("opt-tiny")

@@ -103,3 +103,60 @@ def test_full_size_bank_properties(mods):
     # idempotent / deterministic
     v2, i2 = retrieval.retrieval_topk(bank, q, K)
     assert torch.equal(v, v2) and torch.equal(i, i2)
+
+
+@pytest.mark.parametrize("case", [(3, 256, 1, 3), (9001, 256, 2, 16), (50000, 768, 4, 5), (20011, 1024, 3, 16),
+                                  (4099, 264, 4, 16), (1_000_003, 256, 1, 16)])
+def test_streaming_small_batch_path_bit_exact(mods, case):
+    """Q <= 4 takes the bank-streaming kernel (the reference's call shape, models.py:676-683): bit-exact against the
+    oracle on exactly representable data, and identical to what the tensor-core kernel returns for the same queries
+    (run as part of a larger batch, which takes the tcgen05 path)."""
+    ops, retrieval, orc = mods
+    N, D, Q, K = case
+    K = min(K, N)
+    bank = orc.synthetic_bank_chunk(5, N, D, exact=True)
+    q = orc.synthetic_queries(Q + 4, D, exact=True)
+    bd, qd = bank.to(dev), q.to(dev)
+    v, i = retrieval.retrieval_topk(bd, qd[:Q], K, index_base=77)
+    rv, ri = orc.topk_lowest_index(orc.scores_fp32(bank, q[:Q]), K, 77)
+    assert torch.equal(i.cpu(), ri) and torch.equal(v.cpu(), rv)
+    if N >= 16:
+        v8, i8 = retrieval.retrieval_topk(bd, qd, K, index_base=77)          # Q + 4 >= 5 queries: tensor-core kernel
+        assert torch.equal(v8[:Q], v) and torch.equal(i8[:Q], i)
+
+
+def test_per_query_seen_lists(mods):
+    """Batched prompts keep one seen list each (gill/models.py:679 keeps `seen_image_idx` per conversation): both kernels
+    apply query j's list to query j only."""
+    ops, retrieval, orc = mods
+    N, D, K = 30000, 256, 3
+    bank = orc.synthetic_bank_chunk(6, N, D, exact=True)
+    for Q in (3, 40):
+        q = orc.synthetic_queries(Q, D, exact=True)
+        first = orc.retrieval_topk(bank, q, K)[1]
+        seen = [[int(first[j, 0])] if j % 2 else [int(first[j, 1]), int(first[j, 0]), 12345] for j in range(Q)]
+        v, i = retrieval.retrieval_topk(bank.to(dev), q.to(dev), K, exclude_idx=seen)
+        for j in range(Q):
+            rv, ri = orc.retrieval_topk(bank, q[j:j + 1], K, exclude_idx=seen[j])
+            assert torch.equal(v[j].cpu(), rv[0]) and torch.equal(i[j].cpu(), ri[0]), (Q, j)
+    with pytest.raises(ValueError):
+        retrieval.retrieval_topk(bank.to(dev), q.to(dev), K, exclude_idx=[[1], [2]])     # 2 lists for 40 queries
+
+
+def test_streaming_path_full_size_properties(mods):
+    """3M x 256, Q = 1, K = 3 (the reference's real shape): the query is a bank row => it finds itself; values are the true
+    scores; deterministic."""
+    ops, retrieval, orc = mods
+    N, D = 3_000_000, 256
+    g = torch.Generator(device=dev).manual_seed(2)
+    bank = torch.randn(N, D, generator=g, device=dev).bfloat16()
+    for row in (0, 1_234_567, N - 1):
+        q = bank[row:row + 1].clone()
+        v, i = retrieval.retrieval_topk(bank, q, 3, exclude_idx=[5, 6])
+        assert i[0, 0].item() == row and (v[0, :-1] >= v[0, 1:]).all()
+        chk = (bank[i[0]].float() * q.float()).sum(-1)
+        assert torch.allclose(chk, v[0], rtol=1e-5, atol=1e-3)
+        v2, i2 = retrieval.retrieval_topk(bank, q, 3, exclude_idx=[5, 6])
+        assert torch.equal(v, v2) and torch.equal(i, i2)
+        ve, ie = retrieval.retrieval_topk(bank, q, 3, exclude_idx=[row])          # the seen row drops out (-1000)
+        assert ie[0, 0].item() != row
