@@ -107,4 +107,5 @@ class AttnArgs(ctypes.Structure):
         ("dtype", _c_int),
         ("scale", _c_float),
         ("ones_col", _c_int),
+        ("head_stride", _c_int),
     ]

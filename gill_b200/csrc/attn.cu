@@ -31,6 +31,9 @@ struct alignas(64) AttnParams {
   int causal, causal_offset;  // key j visible to query i iff j <= i + causal_offset
   int out_dtype;
   int in_dtype;
+  int hd_cols;       // columns per head in q/k/v/out (head pitch, multiple of 16, <= HD_PAD): head h starts at column
+                     // h * hd_cols; Q.K^T runs hd_cols / 16 K-steps and P.V produces hd_cols output columns. TMA boxes stay
+                     // HD_PAD wide (the tail belongs to the next head / is zero filled and is never multiplied)
   int ones_col;      // >= 0: column (inside the head padding) where V holds 1.0, so O[:, ones_col] IS the softmax
                      // denominator (computed by the tensor core from the same rounded P as the numerator); -1: none
   float scale_log2;  // softmax scale * log2(e)
@@ -170,7 +173,8 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
-  const int col0 = head * HD_PAD;
+  const int col0 = head * p.hd_cols;
+  const int ksteps = p.hd_cols >> 4;
 
   if (warp == 0) {
     if (lane_id() == 0) {
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
       // ---------------- MMA issuer
       const bool bf16 = p.in_dtype == DT_BF16;
       const uint32_t idesc_s = make_idesc_f16(128, BLOCK_KV, bf16, false);
-      const uint32_t idesc_o = make_idesc_f16(128, HD_PAD, bf16, true);  // B = V, MN-major
+      const uint32_t idesc_o = make_idesc_f16(128, p.hd_cols, bf16, true);  // B = V, MN-major
       const uint32_t sq = smem_u32(smem + C::OFF_Q);
       const uint32_t sp = smem_u32(smem + C::OFF_P);
       auto issue_s = [&](int j) {
@@ -213,10 +217,12 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
         const uint32_t sk = smem_u32(smem + C::OFF_K + ks * C::KV_BYTES);
 #pragma unroll
         for (int k = 0; k < HD_PAD / 16; ++k) {
-          const int c = k >> 2, kk = k & 3;
-          const uint64_t da = make_smem_desc_sw128(sq + c * (128 * 128) + kk * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sk + c * (BLOCK_KV * 128) + kk * 32, 16, 1024);
-          umma_f16(tmem_base + C::TMEM_S0 + s * BLOCK_KV, da, db, idesc_s, k != 0 ? 1u : 0u);
+          if (k < ksteps) {
+            const int c = k >> 2, kk = k & 3;
+            const uint64_t da = make_smem_desc_sw128(sq + c * (128 * 128) + kk * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(sk + c * (BLOCK_KV * 128) + kk * 32, 16, 1024);
+            umma_f16(tmem_base + C::TMEM_S0 + s * BLOCK_KV, da, db, idesc_s, k != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&bars->s_full[s]);
         umma_commit(&bars->k_empty[ks]);
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
       auto rescale_o = [&](float alpha) {
         const uint32_t to = tmem_base + C::TMEM_O + lane_off;
 #pragma unroll 1
-        for (int c = 0; c < HD_PAD; c += 16) {
+        for (int c = 0; c < p.hd_cols; c += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(to + c, v);
           tmem_wait_ld();
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(256, AttnCfg<HD_PAD, BLOCK_KV>::CTAS_PER_SM) a
     uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
                      static_cast<long long>(qrow) * p.ldo + col0;
 #pragma unroll 1
-    for (int c = 0; c < HD_PAD; c += 16) {
+    for (int c = 0; c < p.hd_cols; c += 16) {
       uint32_t v[16];
       tmem_ld_32x32b_x16(to + c, v);
       tmem_wait_ld();
@@ -449,7 +455,12 @@ struct Attn2Bars {
   uint32_t tmem_ptr;
 };
 
-template <int HD_PAD>
+// PT (P through tensor memory): the softmax threads write the packed 16-bit P tile back into the upper half of the S
+// columns with tcgen05.st and P.V reads its A operand from there (tcgen05.mma with a TMEM A operand) -- no st.shared of P
+// (ncu r01: 7.2 M shared-memory bank conflicts per launch from those stores), no generic->async proxy fence, no P buffer.
+// The MMAs of one thread execute in issue order, so S_{j+1} = Q.K_{j+1}^T (issued after P.V_j) overwrites the S columns,
+// P included, only after P.V_j has consumed them.
+template <int HD_PAD, bool PT>
 __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kernel(const __grid_constant__ AttnParams p) {
   using C = Attn2Cfg<HD_PAD>;
   constexpr int BKV = C::BKV;
@@ -487,10 +498,11 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
-  const int col0 = head * HD_PAD;
+  const int col0 = head * p.hd_cols;
+  const int ksteps = p.hd_cols >> 4;
   const bool bf16 = p.in_dtype == DT_BF16;
   const uint32_t idesc_s = make_idesc_f16(128, BKV, bf16, false);
-  const uint32_t idesc_o = make_idesc_f16(128, HD_PAD, bf16, true);  // B = V, MN-major
+  const uint32_t idesc_o = make_idesc_f16(128, p.hd_cols, bf16, true);  // B = V, MN-major
   const uint32_t sq = smem_u32(smem + C::OFF_Q), sk = smem_u32(smem + C::OFF_K), sv = smem_u32(smem + C::OFF_V),
                  spa = smem_u32(smem + C::OFF_P);
 
@@ -506,16 +518,22 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
   auto mma_s = [&]() {
 #pragma unroll
     for (int k = 0; k < HD_PAD / 16; ++k) {
-      const int c = k >> 2, kk = k & 3;
-      umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + c * (128 * 128) + kk * 32, 16, 1024),
-               make_smem_desc_sw128(sk + c * (BKV * 128) + kk * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+      if (k < ksteps) {
+        const int c = k >> 2, kk = k & 3;
+        umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + c * (128 * 128) + kk * 32, 16, 1024),
+                 make_smem_desc_sw128(sk + c * (BKV * 128) + kk * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+      }
     }
   };
   auto mma_pv = [&](int j) {
 #pragma unroll
-    for (int k = 0; k < BKV / 16; ++k)
-      umma_f16(tmem_base + C::TMEM_O, make_smem_desc_sw128(spa + k * 32, 16, 1024),
-               make_smem_desc_sw128(sv + k * (16 * 128), BKV * 128, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
+    for (int k = 0; k < BKV / 16; ++k) {
+      const uint64_t db = make_smem_desc_sw128(sv + k * (16 * 128), BKV * 128, 1024);
+      if (PT)  // A = P in TMEM: packed pairs at S columns [BKV/2, BKV), 8 columns per 16-key step
+        umma_f16_ts(tmem_base + C::TMEM_O, tmem_base + C::TMEM_S + BKV / 2 + k * 8, db, idesc_o, (j | k) != 0 ? 1u : 0u);
+      else
+        umma_f16(tmem_base + C::TMEM_O, make_smem_desc_sw128(spa + k * 32, 16, 1024), db, idesc_o, (j | k) != 0 ? 1u : 0u);
+    }
   };
 
   if (tid == 0) {
@@ -575,7 +593,7 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
     if (__any_sync(0xffffffffu, need)) {  // O is quiescent: P.V_{j-1} retired before S_j
       l *= alpha;
 #pragma unroll 1
-      for (int c = 0; c < HD_PAD; c += 16) {
+      for (int c = 0; c < p.hd_cols; c += 16) {
         uint32_t v[16];
         tmem_ld_32x32b_x16(to + c, v);
         tmem_wait_ld();
@@ -602,13 +620,20 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
                     : attn_exp32<true, true, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
       }
       l += part;
+      if (PT) {
+        tmem_st_32x32b_x16(ts + BKV / 2 + 16 * h, pk);  // this row's 32 keys -> 16 packed columns
+      } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int phys = (4 * h + u) ^ (r & 7);
-        *reinterpret_cast<uint4*>(prow + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        for (int u = 0; u < 4; ++u) {
+          const int phys = (4 * h + u) ^ (r & 7);
+          *reinterpret_cast<uint4*>(prow + phys * 16) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        }
       }
     }
-    fence_proxy_async_smem();
+    if (PT)
+      tmem_wait_st();
+    else
+      fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
@@ -637,16 +662,15 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
   uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
                    static_cast<long long>(qrow) * p.ldo + col0;
 #pragma unroll 1
-  for (int c = 0; c < HD_PAD; c += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32b_x32(to + c, v);
+  for (int c = 0; c < p.hd_cols; c += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(to + c, v);
     tmem_wait_ld();
     if (qrow < p.Lq) {
-      float f[32];
+      float f[16];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * inv;
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
       store16(orow + c, f, 16, p.out_dtype);
-      store16(orow + c + 16, f + 16, 16, p.out_dtype);
     }
   }
   tc_fence_before();
@@ -654,15 +678,15 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int HD_PAD>
+template <int HD_PAD, bool PT>
 static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
   using C = Attn2Cfg<HD_PAD>;
   static PerDeviceOnce configured;
   if (configured.need()) {
-    GB_CUDA(cudaFuncSetAttribute(attn2_kernel<HD_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    GB_CUDA(cudaFuncSetAttribute(attn2_kernel<HD_PAD, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  GB_CUDA(launch_pdl(attn2_kernel<HD_PAD>, grid, dim3(128), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl(attn2_kernel<HD_PAD, PT>, grid, dim3(128), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -692,6 +716,9 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
                a->hd_pad);
   GB_CHECK_ARG(a->dtype == DT_BF16 || a->dtype == DT_F16, "attention operands must be bf16 or fp16");
   GB_CHECK_ARG(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "bad attention shape");
+  const int hd_cols = a->head_stride > 0 ? a->head_stride : a->hd_pad;
+  GB_CHECK_ARG(hd_cols % 16 == 0 && hd_cols >= 16 && hd_cols <= a->hd_pad,
+               "head_stride must be a multiple of 16 in [16, hd_pad] (got %d, hd_pad %d)", hd_cols, a->hd_pad);
   GB_CHECK_ARG(a->ldq % 8 == 0 && a->ldk % 8 == 0 && a->ldv % 8 == 0 && a->ldo % 8 == 0, "row strides %% 8");
   GB_CHECK_ARG(a->q_bstride % 8 == 0 && a->k_bstride % 8 == 0 && a->v_bstride % 8 == 0, "batch strides %% 8");
   const bool bf16 = a->dtype == DT_BF16;
@@ -700,11 +727,14 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
     const char* e = getenv("GILLB200_ATTN");  // A/B aid. "1": warp-specialised attn_kernel for every head size;
     impl = e ? atoi(e) : 0;                   //          "2": 4-warp attn2 for every head size
   }
-  const bool use_attn2 = impl == 2 || (impl != 1 && a->hd_pad == 64);
+  // measured on B200 (profiles/r02_attn_variants.log, 16x8 heads): the 4-warp attn2 form wins for 64- and 128-wide tiles
+  // (hd 80 self-attention 120 vs 132 us, its 77-key cross-attention 33.5 vs 43.9 us); the 192-wide tile and the causal
+  // bf16 OPT prefill keep the warp-specialised kernel (23.3 vs 26.1 us at 16x16)
+  const bool use_attn2 = impl == 2 || (impl != 1 && (a->hd_pad == 64 || (a->hd_pad == 128 && !a->causal)));
   const int bkv = (!use_attn2 && a->hd_pad == 128) ? 128 : 64;  // K/V TMA box rows = the kernel's KV tile
   AttnParams p;
   memset(&p, 0, sizeof(p));
-  const uint64_t cols = (uint64_t)a->H * a->hd_pad;
+  const uint64_t cols = (uint64_t)a->H * hd_cols;  // boxes that reach past the last head are zero filled by TMA
   {
     const uint64_t dims[3] = {cols, (uint64_t)a->Lq, (uint64_t)a->B};
     const uint64_t str[2] = {(uint64_t)a->ldq * 2, (uint64_t)a->q_bstride * 2};
@@ -735,11 +765,22 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   p.out_dtype = a->dtype;
   p.in_dtype = a->dtype;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.ones_col = (a->ones_col > 0 && a->ones_col < a->hd_pad) ? a->ones_col : -1;
+  p.hd_cols = hd_cols;
+  p.ones_col = (a->ones_col > 0 && a->ones_col < hd_cols) ? a->ones_col : -1;
   if (use_attn2) {
-    if (a->hd_pad == 64) return launch_attn2<64>(p, stream);
-    if (a->hd_pad == 128) return launch_attn2<128>(p, stream);
-    return launch_attn2<192>(p, stream);
+    static int ptmem = -1;
+    if (ptmem < 0) {
+      const char* e = getenv("GILLB200_ATTN_PTMEM");  // "0": P through shared memory (A/B aid)
+      ptmem = e ? atoi(e) : 1;
+    }
+    if (ptmem) {
+      if (a->hd_pad == 64) return launch_attn2<64, true>(p, stream);
+      if (a->hd_pad == 128) return launch_attn2<128, true>(p, stream);
+      return launch_attn2<192, true>(p, stream);
+    }
+    if (a->hd_pad == 64) return launch_attn2<64, false>(p, stream);
+    if (a->hd_pad == 128) return launch_attn2<128, false>(p, stream);
+    return launch_attn2<192, false>(p, stream);
   }
   if (a->hd_pad == 64) return launch_attn<64, 64>(p, stream);
   if (a->hd_pad == 128) return launch_attn<128, 128>(p, stream);

@@ -111,6 +111,10 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
       tv[j] = -INFINITY;
       ti[j] = 0x7fffffff;
     }
+    // this query's seen list (exchange buffers carry all-unused lists for most queries: skip the scan for those)
+    const long long* my_ex = e.exclude + static_cast<long long>(min(qrow, e.Q - 1)) * e.exclude_ld;
+    bool has_ex = false;
+    for (int x = 0; x < e.n_exclude; ++x) has_ex |= my_ex[x] >= 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int n_blk = n_lo; n_blk < n_hi; ++n_blk) {
@@ -143,11 +147,10 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
             tmem_wait_ld();
             const long long nloc = n0 + c + j;
             if (s > tv[KMAX - 1] && nloc < e.n_local) {
-              if (e.n_exclude > 0) {
+              if (has_ex) {
                 const long long gidx = e.index_base + nloc;
-                const long long* ex = e.exclude + static_cast<long long>(qrow) * e.exclude_ld;
                 for (int x = 0; x < e.n_exclude; ++x)
-                  if (ex[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
+                  if (my_ex[x] == gidx) s -= 1000.0f;  // gill/models.py:679-680
               }
               topk_insert(tv, ti, s, static_cast<int>(nloc));
             }

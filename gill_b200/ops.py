@@ -329,16 +329,17 @@ def topk_merge_packed(recv: torch.Tensor, R: int, list_bytes: int, idx_offset_by
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_pad: int, scale: float, *,
               out: Optional[torch.Tensor] = None, causal: bool = False, causal_offset: int = 0,
-              kv_lens: Optional[torch.Tensor] = None, ones_col: int = 0, head_dim: int = 0) -> torch.Tensor:
-    """q [B,Lq,>=H*hd_pad], k/v [B,Lk,>=H*hd_pad] (views into fused QKV buffers allowed; last dim contiguous).
-    Returns out [B,Lq,H*hd_pad]. Pad columns of each head must be zero in q, k, v -- except that v may carry 1.0 in
+              kv_lens: Optional[torch.Tensor] = None, ones_col: int = 0, head_dim: int = 0,
+              head_stride: int = 0) -> torch.Tensor:
+    """q [B,Lq,>=H*stride], k/v [B,Lk,>=H*stride] (views into fused QKV buffers allowed; last dim contiguous), stride =
+    head_stride or hd_pad (column pitch of the heads; hd_pad selects the kernel tile width). Returns out [B,Lq,H*stride]. Pad columns of each head must be zero in q, k, v -- except that v may carry 1.0 in
     pad column `ones_col` (> 0) of every head, which moves the softmax row sum onto the tensor core."""
     B, Lq, _ = q.shape
     Lk = k.shape[1]
     for t in (q, k, v):
         assert t.stride(2) == 1 and t.dtype == q.dtype
     if out is None:
-        out = torch.empty((B, Lq, heads * hd_pad), device=q.device, dtype=q.dtype)
+        out = torch.empty((B, Lq, heads * (head_stride or hd_pad)), device=q.device, dtype=q.dtype)
     a = _lib.AttnArgs()
     a.q, a.k, a.v, a.out = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
     a.ldq, a.ldk, a.ldv, a.ldo = q.stride(1), k.stride(1), v.stride(1), out.stride(1)
@@ -346,7 +347,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hd_
     a.kv_lens = _ptr(kv_lens)
     a.B, a.H, a.Lq, a.Lk, a.hd_pad = B, heads, Lq, Lk, hd_pad
     a.causal, a.causal_offset = int(causal), causal_offset
-    a.dtype, a.scale, a.ones_col = _DT[q.dtype], scale, ones_col
+    a.dtype, a.scale, a.ones_col, a.head_stride = _DT[q.dtype], scale, ones_col, head_stride
     # profile records count ALGORITHMIC work: the true head dim (head_dim, when the caller states it), not the padding
     hd = head_dim or hd_pad
     with _P("attention", 4.0 * B * heads * Lq * Lk * hd * (0.5 if causal and Lq == Lk else 1.0),

@@ -43,13 +43,12 @@ def exclude_tensor(exclude_idx: Exclude, n_queries: int, device, width: Optional
     if len(rows) not in (0, 1, n_queries):
         raise ValueError(f"exclude_idx holds {len(rows)} lists for {n_queries} queries (expected 1 or {n_queries})")
     n = max([len(r) for r in rows], default=0)
+    if n == 0:
+        return None                      # nothing seen yet: no list at all (the exchange then sends all -1 slots)
     if width is not None:
         if n > width:
             raise ValueError(f"{n} excluded rows exceed the exchange's max_exclude={width}")
         n = width
-    if n == 0:
-        return None
-    rows = rows or [[]]
     return torch.tensor([r + [-1] * (n - len(r)) for r in rows], dtype=torch.int64, device=device)
 
 

@@ -8,8 +8,9 @@ B200-first layout decisions
   * activations are NHWC fp16 (the reference runs SD in fp16): a [B,H,W,C] tensor IS the [B*H*W, C] token matrix, so
     conv <-> transformer transitions are views, 1x1 convs are plain GEMMs and 3x3 convs are implicit GEMMs whose taps
     are TMA box shifts (no im2col buffer);
-  * attention heads are stored padded to 64/128/192 columns (zero weight rows), so every TMA box is a full 128-byte
-    swizzled row; the padding is folded into the projection weights at load time;
+  * attention heads are stored at a pitch of 48/96/176 columns (head dims 40/80/160; zero weight rows, folded into the
+    projection weights at load time); the attention kernels still fetch full 128-byte swizzled rows per TMA box and
+    simply run fewer K-steps / a narrower P.V;
   * GEGLU value/gate rows are interleaved so the gate is applied in the GEMM epilogue;
   * everything that does not depend on the latent is hoisted out of the 51-step loop: the time-embedding MLP and all
     22 resnet time projections (a [51, sum_c] table built once), the 16 cross-attention K/V pairs (once per prompt),
@@ -38,6 +39,16 @@ def _hd_pad(hd: int) -> int:
         if hd <= p:
             return p
     raise ValueError(f"head dim {hd} > 192 not supported by the fused attention kernel")
+
+
+def _hd_pitch(hd: int) -> int:
+    """Column pitch of one head in the q/k/v/out projections. Head dims that fill a 64-column tile exactly keep it;
+    the others (SD-1.5: 40 / 80 / 160) get the next multiple of 16 ABOVE hd, i.e. 48 / 96 / 176: at least one spare
+    column per head (V's ones column: the softmax denominator comes out of the P.V product) while the projections, the
+    attention K-steps and the P.V width shrink by 25 / 25 / 8 % against padding every head to 64 / 128 / 192."""
+    if os.environ.get("GILLB200_HEAD_PITCH", "1") == "0":        # A/B aid: round-1 layout (pitch == tile width)
+        return _hd_pad(hd)
+    return hd if hd % 64 == 0 else (hd // 16 + 1) * 16
 
 
 def _conv_w(w: torch.Tensor, dt) -> torch.Tensor:
@@ -137,7 +148,7 @@ class UNetB200:
         f32 = torch.float32
         H = self.heads
         hd = c // H
-        hp = _hd_pad(hd)
+        hp = _hd_pitch(hd)          # column pitch of a head in every packed projection below
         for n in ("norm",):
             self._put(f"{p}.{n}.weight", sd[f"{p}.{n}.weight"], f32)
             self._put(f"{p}.{n}.bias", sd[f"{p}.{n}.bias"], f32)
@@ -186,7 +197,7 @@ class UNetB200:
         fold(f"{t}.attn2.q", None, "norm2")
         fold(f"{t}.ff.geglu.weight", f"{t}.ff.geglu.bias", "norm3")
         self._tf_meta = getattr(self, "_tf_meta", {})
-        self._tf_meta[p] = (c, hd, hp)
+        self._tf_meta[p] = (c, hd, _hd_pad(hp), hp)
 
     def _pack(self, sd):
         cfg, f32 = self.cfg, torch.float32
@@ -324,7 +335,7 @@ class UNetB200:
     def _transformer(self, x, p, ctx_kv):
         w, G, Hh = self.w, self.G, self.heads
         B, H, W, C = x.shape
-        _, hd, hp = self._tf_meta[p]
+        _, hd, tile, hp = self._tf_meta[p]      # hp = head pitch (columns per head), tile = kernel tile width
         M, L = B * H * W, H * W
         t = p + ".transformer_blocks.0"
         n = ops.groupnorm(x, w[p + ".norm.weight"], w[p + ".norm.bias"], G, 1e-6)
@@ -338,14 +349,15 @@ class UNetB200:
         # measured slower on B200)
         oc = hd if hp > hd else 0
         qkv = ops.gemm(n1, w[t + ".attn1.qkv"], bias=w[t + ".attn1.qkv_bias"]).view(B, L, 3 * Hh * hp)
-        a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
-                          hd ** -0.5, ones_col=oc, head_dim=hd)
+        a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, tile,
+                          hd ** -0.5, ones_col=oc, head_dim=hd, head_stride=hp)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h)
         # cross attention against the precomputed K/V of the conditioning
         n2 = ops.layernorm(h, w[t + ".norm2.weight"], w[t + ".norm2.bias"], 1e-5)
         q = ops.gemm(n2, w[t + ".attn2.q"]).view(B, L, Hh * hp)
         kv = ctx_kv[p]
-        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc, head_dim=hd)
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, tile, hd ** -0.5, ones_col=oc, head_dim=hd,
+                          head_stride=hp)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h)
         # GEGLU feed-forward
         n3 = ops.layernorm(h, w[t + ".norm3.weight"], w[t + ".norm3.bias"], 1e-5)
@@ -362,20 +374,21 @@ class UNetB200:
         LayerNorm kernel, no normalised copy of the stream."""
         w, Hh = self.w, self.heads
         B, H, W, C = x.shape
-        _, hd, hp = self._tf_meta[p]
+        _, hd, tile, hp = self._tf_meta[p]
         M, L = B * H * W, H * W
         t = p + ".transformer_blocks.0"
         oc = hd if hp > hd else 0
         h = ops.gemm(n.view(M, C), w[p + ".proj_in.weight"], bias=w[p + ".proj_in.bias"], rowstats=True)
         qkv = ops.gemm(h, w[t + ".attn1.qkv_ln"], bias=w[t + ".attn1.qkv_lnb"],
                        ln=(h.ln_stats, w[t + ".attn1.qkv_cs"], 1e-5)).view(B, L, 3 * Hh * hp)
-        a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, hp,
-                          hd ** -0.5, ones_col=oc, head_dim=hd)
+        a = ops.attention(qkv[:, :, : Hh * hp], qkv[:, :, Hh * hp : 2 * Hh * hp], qkv[:, :, 2 * Hh * hp :], Hh, tile,
+                          hd ** -0.5, ones_col=oc, head_dim=hd, head_stride=hp)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn1.out.weight"], bias=w[t + ".attn1.out.bias"], residual=h, rowstats=True)
         q = ops.gemm(h, w[t + ".attn2.q_ln"], bias=w[t + ".attn2.q_lnb"],
                      ln=(h.ln_stats, w[t + ".attn2.q_cs"], 1e-5)).view(B, L, Hh * hp)
         kv = ctx_kv[p]
-        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, hp, hd ** -0.5, ones_col=oc, head_dim=hd)
+        a = ops.attention(q, kv[:, :, : Hh * hp], kv[:, :, Hh * hp :], Hh, tile, hd ** -0.5, ones_col=oc, head_dim=hd,
+                          head_stride=hp)
         h = ops.gemm(a.view(M, Hh * hp), w[t + ".attn2.out.weight"], bias=w[t + ".attn2.out.bias"], residual=h, rowstats=True)
         g = ops.gemm(h, w[t + ".ff.geglu.weight_ln"], bias=w[t + ".ff.geglu.weight_lnb"], act="geglu",
                      ln=(h.ln_stats, w[t + ".ff.geglu.weight_cs"], 1e-5))

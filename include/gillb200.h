@@ -142,7 +142,7 @@ int gillb200_topk_merge_strided(const float* cand_val, long long r_stride_val, c
  *
  * Replaces diffusers' Attention (UNet self/cross attention, gill/custom_sd.py:633-638) and OPTAttention
  * (gill/models.py:465). q: [B, Lq, *], k/v: [B, Lk, *], out: [B, Lq, *]; head h occupies columns
- * [h*hd_pad, (h+1)*hd_pad) of each row, hd_pad in {64, 128, 192}; columns beyond the true head dim must be zero in
+ * [h*hd_pad, (h+1)*hd_pad) of each row (or a tighter pitch, see head_stride), hd_pad in {64, 128, 192}; columns beyond the true head dim must be zero in
  * q, k and v (except v's optional ones column, see ones_col) (the projection weights are zero-padded at load time). Strides are in elements.
  * causal: key j is visible to query i iff j <= i + causal_offset. kv_lens: optional per-batch key count (device).
  * ------------------------------------------------------------------------------------------------------------- */
@@ -158,8 +158,11 @@ typedef struct gillb200_attn_args {
   int causal, causal_offset;
   int dtype;
   float scale;
-  int ones_col; /* 0 = unused. > 0: v[..., h*hd_pad + ones_col] == 1.0 for every key (a spare padding column), which
+  int ones_col; /* 0 = unused. > 0: v[..., h*stride + ones_col] == 1.0 for every key (a spare padding column), which
                  * lets the kernel take the softmax denominator from the P.V product (fp16 only) */
+  int head_stride; /* 0 = hd_pad. Otherwise the column pitch of the heads in q/k/v/out (multiple of 16, <= hd_pad): head h
+                    * occupies columns [h*head_stride, (h+1)*head_stride); hd_pad only selects the kernel's tile width.
+                    * SD-1.5's head dims 40 / 80 / 160 are stored at pitch 48 / 96 / 176 instead of 64 / 128 / 192. */
 } gillb200_attn_args;
 
 int gillb200_attention(const gillb200_attn_args* args, void* stream);

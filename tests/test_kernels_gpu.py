@@ -319,6 +319,39 @@ def test_fused_attention(ops, case):
         assert (got1.view(B, Lq, H, hp)[..., hd].float() - 1).abs().max() < 2e-3
 
 
+PITCH_CASES = [  # B, H, Lq, Lk, hd, pitch, tile, dtype, causal     (SD-1.5 head dims 40 / 80 / 160 at pitch 48 / 96 / 176)
+    (2, 8, 1024, 1024, 40, 48, 64, torch.float16, False), (2, 8, 384, 77, 40, 48, 64, torch.float16, False),
+    (2, 8, 512, 512, 80, 96, 128, torch.float16, False), (2, 8, 300, 77, 80, 96, 128, torch.float16, False),
+    (2, 8, 256, 256, 160, 176, 192, torch.float16, False), (1, 8, 64, 77, 160, 176, 192, torch.float16, False),
+    (2, 3, 200, 200, 32, 48, 64, torch.bfloat16, True), (2, 8, 2048, 2048, 40, 48, 64, torch.float16, False),
+]
+
+
+@pytest.mark.parametrize("case", PITCH_CASES)
+def test_fused_attention_head_pitch(ops, case):
+    """Heads stored at a column pitch below the kernel's tile width (head_stride): fewer K-steps, narrower P.V, the TMA
+    boxes read into the neighbouring head / past the last head (zero filled) without ever multiplying those columns.
+    q/k/v are views into one fused buffer, like the UNet's qkv projection output."""
+    B, H, Lq, Lk, hd, pt, tile, dt, causal = case
+    torch.manual_seed(12)
+    L = max(Lq, Lk)
+    buf = torch.zeros(B, L, 3, H, pt, device=dev)
+    buf[..., :hd] = torch.randn(B, L, 3, H, hd, device=dev)
+    use_ones = dt == torch.float16
+    if use_ones:
+        buf[:, :, 2, :, hd] = 1.0
+    buf = buf.view(B, L, 3 * H * pt).to(dt)
+    q, k, v = buf[:, :Lq, : H * pt], buf[:, :Lk, H * pt: 2 * H * pt], buf[:, :Lk, 2 * H * pt:]
+    got = ops.attention(q, k, v, H, tile, hd ** -0.5, causal=causal, ones_col=hd if use_ones else 0, head_stride=pt)
+    ref = attn_ref(q, k, v, H, pt, hd ** -0.5, causal)
+    assert got.shape == (B, Lq, H * pt)
+    tol = 1e-2 if dt == torch.bfloat16 else 3e-3
+    assert torch.isfinite(got.float()).all() and rel(got, ref) < tol
+    if use_ones:
+        assert (got.view(B, Lq, H, pt)[..., hd].float() - 1).abs().max() < 2e-3
+    assert got.view(B, Lq, H, pt)[..., hd + 1:].abs().max() == 0            # padding columns stay exactly zero
+
+
 @pytest.mark.parametrize("hd,hp,dt", [(40, 64, torch.float16), (80, 128, torch.float16), (128, 128, torch.bfloat16)])
 def test_fused_attention_growing_max(ops, hd, hp, dt):
     """Key norms grow along the sequence, so the running row max rises by far more than the lazy-rescale threshold
