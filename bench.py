@@ -248,6 +248,47 @@ def retrieval_section(dev, rank, world, pk, timed):
     return obj
 
 
+def config5_section(gill, dev, rank, world, timed):
+    """BASELINE configs[4]: the full generate_for_images_and_texts surface, batched -- per rank 4 conversations (2 CLIP-
+    encoded images + ~64 text tokens each, unequal lengths) -> ragged OPT prefill -> retrieval top-3 over the 3M x 256 bank
+    (row-sharded across the ranks, one candidate exchange) -> decision -> GILLMapper -> 4 images per prompt (SD in chunks
+    of 8, 50-step PLMS) -> CLIP ViT-L/14 re-rank on the device. images/s = all ranks' images / max-over-ranks time."""
+    from gill_b200 import retrieval
+    from harness import synthetic
+
+    m = gill.model
+    n_prompts, n_gen = 4, 4
+    t0 = time.time()
+    old = (m.visual_model, gill.emb_matrix, gill.num_gen_images)
+    m.visual_model = synthetic.build_clip_tower(dev)
+    shard = synthetic.synthetic_bank_shard(BANK_N, 256, world, rank, device=dev)
+    sb = retrieval.ShardedBank(shard, BANK_N)
+    prompts = synthetic.config5_prompts(n_prompts, 100 + 1000 * rank)
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+    setup_s = time.time() - t0
+
+    def step():
+        out = gill.generate_for_images_and_texts_batch(prompts, num_gen_images=n_gen, generator=gen, bank=sb)
+        return torch.stack([o[1]["gen"][0][0] for o in out]).cpu()          # best image of each prompt reaches the host
+
+    try:
+        ms, launches = timed(step, 2, 1)
+        info = gill.last_batch_info
+        ok = bool(all(info["forced_ok"]))
+        lens = info["prompt_lens"]
+    finally:
+        m.visual_model, gill.emb_matrix, gill.num_gen_images = old
+        del shard, sb
+        torch.cuda.empty_cache()
+    imgs = world * n_prompts * n_gen
+    return {"metric": "images/sec, full generate_for_images_and_texts surface (BASELINE configs[4])",
+            "value": round(imgs / (ms / 1e3), 4), "unit": "images/s", "ms_per_step": round(ms, 1), "gpu_launches": int(launches),
+            "config": {"prompts_per_gpu": n_prompts, "images_per_prompt": n_gen, "global_images_per_step": imgs,
+                       "prompt_lens_rank0": lens, "bank": f"{BANK_N}x256 bf16 sharded {world}-way, top-3 + per-prompt seen lists",
+                       "rerank": "CLIP ViT-L/14-shaped tower (24 layers, seeded init) on 224x224 PIL-exact device resize",
+                       "forced_emission_ok": ok, "setup_s": round(setup_s, 1)}}
+
+
 _TRAFFIC = None
 
 
@@ -438,6 +479,16 @@ def run_ours(args):
     # ---- retrieval: 3M x 768 bank row-sharded over the ranks, Q=1024, K=16 (BASELINE configs[2])
     retrieval_obj = retrieval_section(dev, rank, world, pk, timed)
 
+    # ---- BASELINE configs[4]: the batched full surface (every rank takes part: the bank exchange is a collective)
+    config5 = None
+    if os.environ.get("GILLB200_BENCH_C5", "1") != "0":
+        try:
+            config5 = config5_section(gill, dev, rank, world, timed)
+        except Exception as e:
+            config5 = {"unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+            if world > 1:
+                raise
+
     # ---- GILLMapper-only forward, B=256 (BASELINE configs[1]); one captured CUDA graph replayed per step
     mapper_obj = None
     if rank == 0:
@@ -514,7 +565,7 @@ def run_ours(args):
         "clocks": clocks,
         "achieved_tflops_whole_step": round(flop_per_batch / (ms_dev / 1e3), 1),
         "roofline": roof, "rooflines_by_family": rooflines, "stages_ms": stages, "unet_eval_breakdown": breakdown,
-        "cpu_baseline": cpu, "hf_eager_gpu": hf_gpu, "retrieval": retrieval_obj,
+        "cpu_baseline": cpu, "hf_eager_gpu": hf_gpu, "retrieval": retrieval_obj, "config5_full_surface": config5,
         "mapper": mapper_obj,
     }
     print(json.dumps(line))

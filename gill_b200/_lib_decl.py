@@ -33,3 +33,5 @@ def declare(L):
     d("gillb200_launch_count", restype=cll)
     d("gillb200_channel_mix", vp, ci, vp, vp, ci, cll, vp, ci, vp)
     d("gillb200_clip_preprocess_u8", vp, ci, ci, ci, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), vp, ci, vp, vp)
+    d("gillb200_clip_preprocess_u8_crop", vp, ci, ci, ci, ci, ci, ci, ci, ci, ctypes.POINTER(cf), ctypes.POINTER(cf), vp, ci,
+      vp, vp)

@@ -16,7 +16,7 @@ the overlapping files.
 import json
 import os
 import pickle
-from typing import List, Optional, Sequence, Tuple
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -108,3 +108,48 @@ def load_bank_shard(bank_dir: str, rank: int, world: int, device="cuda") -> Tupl
 def load_paths(bank_dir: str) -> List[str]:
     with open(os.path.join(bank_dir, "paths.txt")) as f:
         return [ln.rstrip("\n") for ln in f]
+
+
+def build_bank(model, images: Iterable, paths: Sequence[str], out_dir: str, shards: int = 1, batch: int = 64) -> None:
+    """The bank BUILDER (scripts/extract_img_embs.py:16-43): image -> HF feature extractor -> CLIP ViT-L/14 ->
+    `visual_fc` (`get_visual_embs(mode="retrieval")`) -> one 256-d embedding per image, then the load-time preparation of
+    gill/models.py:895-900 (cast, row-normalise, x exp(logit_scale)) and the flat sharded layout of this module.
+
+    `model` is a gill_b200.models.GILL with a CLIP tower; `images` yields PIL images or uint8 HWC arrays / tensors in the
+    order of `paths`. Everything after the JPEG decode runs on the device, `batch` images of equal size at a time
+    (the reference pushes one image at a time through the host-side feature extractor)."""
+    import numpy as np
+
+    from . import ops, retrieval
+
+    m = model.model
+    if m.visual_model is None:
+        raise ValueError("build_bank needs a CLIP vision tower (GILL(..., visual_model=CLIPVisionB200(...)))")
+    dev, dt = m.lm.dev, m.lm.dt
+    embs: List[torch.Tensor] = []
+    pend: List[torch.Tensor] = []
+
+    def flush():
+        if not pend:
+            return
+        u8 = torch.stack(pend).to(dev).contiguous()
+        px = ops.clip_preprocess_u8(u8, 224, out_dtype=dt, mode="feature_extractor")      # scripts/extract_img_embs.py:37
+        embs.append(m.get_visual_embs(px, mode="retrieval")[:, 0, :].float().cpu())       # :39-40
+        pend.clear()
+
+    n = 0
+    for img in images:
+        a = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.asarray(
+            img.convert("RGB") if hasattr(img, "convert") else img).copy())
+        if a.dtype != torch.uint8 or a.dim() != 3 or a.shape[-1] != 3:
+            raise ValueError(f"image {n}: expected uint8 [H,W,3], got {a.dtype} {tuple(a.shape)}")
+        if pend and (a.shape != pend[0].shape or len(pend) == batch):
+            flush()
+        pend.append(a)
+        n += 1
+    flush()
+    if n != len(paths):
+        raise ValueError(f"{n} images for {len(paths)} paths")
+    emb = torch.cat(embs, 0)
+    bank = retrieval.prepare_bank(emb.numpy(), m.logit_scale.detach())
+    save_prepared_bank(bank.cpu(), list(paths), out_dir, shards=shards)

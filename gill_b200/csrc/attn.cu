@@ -678,6 +678,210 @@ __global__ void __launch_bounds__(128, Attn2Cfg<HD_PAD>::CTAS_PER_SM) attn2_kern
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ================================================================================================================
+// attn3: attn2 (64-wide tile, P through tensor memory) with the issue work moved to a FIFTH warp.
+//
+// In attn2 thread 0 is both a softmax row and the CTA's TMA / MMA issuer: after every tile it alone waits for V and K,
+// builds descriptors and issues 7-8 tcgen05.mma + a commit while warps 1-3 already sleep on the S barrier -- so warp 0
+// reaches every CTA barrier last and the whole CTA runs at the pace of its most loaded warp. Here warps 0-3 only do
+// softmax (thread = query row) and hand P over with one mbarrier arrive per warp (no CTA-wide bar.sync); warp 4 waits
+// for that barrier with V / K already checked and issues P.V_j, Q.K_{j+1}^T and the commit immediately.
+struct Attn3Bars {
+  uint64_t q_full, k_full, v_full, s_full, p_full;
+  uint32_t tmem_ptr;
+};
+
+__global__ void __launch_bounds__(160, 4) attn3_kernel(const __grid_constant__ AttnParams p) {
+  using C = Attn2Cfg<64>;
+  constexpr int BKV = C::BKV;
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Attn3Bars* bars = reinterpret_cast<Attn3Bars*>(smem + C::OFF_BAR);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int kv_len = p.kv_lens ? p.kv_lens[b] : p.Lk;
+  int n_tiles = (kv_len + BKV - 1) / BKV;
+  if (p.causal) {
+    const int last_visible = min(kv_len - 1, q0 + 127 + p.causal_offset);
+    n_tiles = min(n_tiles, last_visible / BKV + 1);
+  }
+  if (n_tiles < 1) n_tiles = 1;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tma_q);
+    tma_prefetch_desc(&p.tma_k);
+    tma_prefetch_desc(&p.tma_v);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->k_full, 1);
+    mbar_init(&bars->v_full, 1);
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->p_full, 4);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(&bars->tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+  const int col0 = head * p.hd_cols;
+  const int ksteps = p.hd_cols >> 4;
+  const bool bf16 = p.in_dtype == DT_BF16;
+
+  if (warp == 4) {
+    // ---------------- issuer warp: TMA loads + every tcgen05.mma of the CTA (one lane)
+    if (lane_id() == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, BKV, bf16, false);
+      const uint32_t idesc_o = make_idesc_f16(128, p.hd_cols, bf16, true);  // B = V, MN-major
+      const uint32_t sq = smem_u32(smem + C::OFF_Q), sk = smem_u32(smem + C::OFF_K), sv = smem_u32(smem + C::OFF_V);
+      auto load_kv = [&](int j, bool is_v) {
+        uint64_t* bar = is_v ? &bars->v_full : &bars->k_full;
+        mbar_arrive_expect_tx(bar, C::KV_BYTES);
+        tma_load_3d(smem + (is_v ? C::OFF_V : C::OFF_K), is_v ? &p.tma_v : &p.tma_k, bar, col0, j * BKV, b);
+      };
+      auto mma_s = [&]() {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < ksteps)
+            umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + k * 32, 16, 1024),
+                     make_smem_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+      };
+      mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
+      tma_load_3d(smem + C::OFF_Q, &p.tma_q, &bars->q_full, col0, q0, b);
+      load_kv(0, false);
+      load_kv(0, true);
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->k_full, 0);
+      tc_fence_after();
+      mma_s();
+      umma_commit(&bars->s_full);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&bars->s_full, j & 1);             // S_j (and P.V_{j-1}) retired: K and V buffers are free
+        if (j + 1 < n_tiles) load_kv(j + 1, false);
+        if (j > 0) load_kv(j, true);
+        mbar_wait(&bars->v_full, j & 1);
+        if (j + 1 < n_tiles) mbar_wait(&bars->k_full, (j + 1) & 1);
+        mbar_wait(&bars->p_full, j & 1);             // all four softmax warps have stored P_j
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_f16_ts(tmem_base + C::TMEM_O, tmem_base + C::TMEM_S + BKV / 2 + k * 8,
+                      make_smem_desc_sw128(sv + k * (16 * 128), BKV * 128, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
+        if (j + 1 < n_tiles) mma_s();
+        umma_commit(&bars->s_full);  // completion #(j+1): S_{j+1} ready, or (last tile) O final
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row
+    const int r = tid;
+    const int qrow = q0 + r;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t ts = tmem_base + C::TMEM_S + lane_off;
+    const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+    float m_used = 0.f, l = 0.f;
+    const bool use_ones = p.ones_col >= 0;
+    const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&bars->s_full, j & 1);
+      tc_fence_after();
+      const int kv0 = j * BKV;
+      const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
+      const bool no_mask = __all_sync(0xffffffffu, lim >= BKV - 1);
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(ts, s0);
+      tmem_ld_32x32b_x32(ts + 32, s1);
+      tmem_wait_ld();
+      float mx = no_mask ? fmaxf(attn_max32<false>(s0, 0, lim), attn_max32<false>(s1, 32, lim))
+                         : fmaxf(attn_max32<true>(s0, 0, lim), attn_max32<true>(s1, 32, lim));
+      mx *= p.scale_log2;
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mx == -INFINITY ? 0.f : mx;
+      } else if (mx > m_used + 8.f) {
+        alpha = fast_exp2(m_used - mx);
+        m_used = mx;
+        need = true;
+      }
+      if (__any_sync(0xffffffffu, need)) {  // O is quiescent: P.V_{j-1} retired before S_j
+        l *= alpha;
+#pragma unroll 1
+        for (int c = 0; c < p.hd_cols; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(to + c, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32b_x16(to + c, v);
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t(&sh)[32] = h == 0 ? s0 : s1;
+        uint32_t pk[16];
+        float part;
+        if (no_mask) {
+          if (use_ones) part = bf16 ? attn_exp32<false, false, true>(sh, 32 * h, lim, p.scale_log2, m_used, pk)
+                                    : attn_exp32<false, false, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
+          else part = bf16 ? attn_exp32<false, true, true>(sh, 32 * h, lim, p.scale_log2, m_used, pk)
+                           : attn_exp32<false, true, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
+        } else {
+          part = bf16 ? attn_exp32<true, true, true>(sh, 32 * h, lim, p.scale_log2, m_used, pk)
+                      : attn_exp32<true, true, false>(sh, 32 * h, lim, p.scale_log2, m_used, pk);
+        }
+        l += part;
+        tmem_st_32x32b_x16(ts + BKV / 2 + 16 * h, pk);  // this row's 32 keys -> 16 packed columns (upper half of S)
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&bars->p_full);
+    }
+    // ---- epilogue: O / l
+    mbar_wait(&bars->s_full, n_tiles & 1);
+    tc_fence_after();
+    if (use_ones) {
+      l = __uint_as_float(tmem_ld_32x32b_x1(to + p.ones_col));
+      tmem_wait_ld();
+    }
+    const float inv = 1.f / l;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
+                     static_cast<long long>(qrow) * p.ldo + col0;
+#pragma unroll 1
+    for (int c = 0; c < p.hd_cols; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(to + c, v);
+      tmem_wait_ld();
+      if (qrow < p.Lq) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+        store16(orow + c, f, 16, p.out_dtype);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+static int launch_attn3(const AttnParams& p, cudaStream_t stream) {
+  using C = Attn2Cfg<64>;
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    GB_CUDA(cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  }
+  dim3 grid((p.Lq + 127) / 128, p.H, p.B);
+  GB_CUDA(launch_pdl(attn3_kernel, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_COUNT_LAUNCH(1);
+  return 0;
+}
+
 template <int HD_PAD, bool PT>
 static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
   using C = Attn2Cfg<HD_PAD>;
@@ -773,6 +977,14 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
       const char* e = getenv("GILLB200_ATTN_PTMEM");  // "0": P through shared memory (A/B aid)
       ptmem = e ? atoi(e) : 1;
     }
+    static int issuer = -1;
+    if (issuer < 0) {
+      // dedicated issuer warp (attn3) for the 64-wide tile: measured 726 vs 766 us (16x8x4096^2, hd 40) and 51.6 vs 54.2 us
+      // for the 77-key cross-attention; "0" falls back to attn2 (A/B aid)
+      const char* e = getenv("GILLB200_ATTN_ISSUER");
+      issuer = e ? atoi(e) : 1;
+    }
+    if (issuer && a->hd_pad == 64) return launch_attn3(p, stream);
     if (ptmem) {
       if (a->hd_pad == 64) return launch_attn2<64, true>(p, stream);
       if (a->hd_pad == 128) return launch_attn2<128, true>(p, stream);

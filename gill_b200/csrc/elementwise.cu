@@ -343,7 +343,11 @@ __device__ __forceinline__ int pil_clip8(int v) {
   return v < 0 ? 0 : v > 255 ? 255 : v;
 }
 
-__global__ void clip_preprocess_u8_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int S, float m0, float m1,
+// The image is resized to RH x RW and the S x S window at (top, left) of the resized image is produced: RH = RW = S,
+// top = left = 0 is `img.resize((S, S))`; RH / RW = shortest edge S, centred window = the HF CLIP feature extractor
+// (resize shortest edge + centre crop, gill/utils.py:117-119 -> gill/models.py:608).
+__global__ void clip_preprocess_u8_kernel(const uint8_t* __restrict__ img, int B, int H, int W, int RH, int RW, int top,
+                                          int left, int S, float m0, float m1,
                                           float m2, float s0, float s1, float s2, void* __restrict__ out, int out_dtype,
                                           uint8_t* __restrict__ resized /* optional [B,S,S,3] */) {
   pdl_wait();
@@ -352,8 +356,8 @@ __global__ void clip_preprocess_u8_kernel(const uint8_t* __restrict__ img, int B
   if (t >= 1LL * B * S * S) return;
   const int ox = static_cast<int>(t % S), oy = static_cast<int>((t / S) % S), b = static_cast<int>(t / (1LL * S * S));
   int kx[RESIZE_KS], ky[RESIZE_KS], x0, nx, y0, ny;
-  pil_coeffs(W, S, ox, &x0, &nx, kx);
-  pil_coeffs(H, S, oy, &y0, &ny, ky);
+  pil_coeffs(W, RW, ox + left, &x0, &nx, kx);
+  pil_coeffs(H, RH, oy + top, &y0, &ny, ky);
   const uint8_t* base = img + static_cast<long long>(b) * H * W * 3;
   int acc[3] = {1 << 21, 1 << 21, 1 << 21};
   for (int j = 0; j < ny; ++j) {
@@ -491,16 +495,25 @@ extern "C" int gillb200_channel_mix(const float* x, int cin, const float* w, con
   return 0;
 }
 
+extern "C" int gillb200_clip_preprocess_u8_crop(const void* img, int B, int H, int W, int RH, int RW, int top, int left,
+                                                int S, const float* mean3, const float* std3, void* out, int out_dtype,
+                                                void* resized_u8, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(img && out && mean3 && std3 && B > 0 && H > 0 && W > 0 && S > 0, "clip_preprocess_u8: bad args");
+  GB_CHECK_ARG(RH >= S && RW >= S && top >= 0 && left >= 0 && top + S <= RH && left + S <= RW,
+               "clip_preprocess_u8: the %d x %d window at (%d, %d) leaves the %d x %d resized image", S, S, top, left, RH, RW);
+  GB_CHECK_ARG(H <= 5 * RH && W <= 5 * RW, "clip_preprocess_u8: down-scaling factor above 5 (H=%d W=%d -> %d x %d)", H, W, RH,
+               RW);
+  GB_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "clip_preprocess_u8: bad out dtype");
+  GB_CUDA(launch_pdl(clip_preprocess_u8_kernel, dim3(grid_for(1LL * B * S * S, 128)), dim3(128), 0, stream,
+                     reinterpret_cast<const uint8_t*>(img), B, H, W, RH, RW, top, left, S, mean3[0], mean3[1], mean3[2],
+                     std3[0], std3[1], std3[2], out, out_dtype, reinterpret_cast<uint8_t*>(resized_u8)));
+  GB_COUNT_LAUNCH(1);
+  return 0;
+}
+
 extern "C" int gillb200_clip_preprocess_u8(const void* img, int B, int H, int W, int S, const float* mean3,
                                            const float* std3, void* out, int out_dtype, void* resized_u8,
                                            void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GB_CHECK_ARG(img && out && mean3 && std3 && B > 0 && H > 0 && W > 0 && S > 0, "clip_preprocess_u8: bad args");
-  GB_CHECK_ARG(H <= 5 * S && W <= 5 * S, "clip_preprocess_u8: down-scaling factor above 5 (H=%d W=%d S=%d)", H, W, S);
-  GB_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "clip_preprocess_u8: bad out dtype");
-  GB_CUDA(launch_pdl(clip_preprocess_u8_kernel, dim3(grid_for(1LL * B * S * S, 128)), dim3(128), 0, stream,
-                     reinterpret_cast<const uint8_t*>(img), B, H, W, S, mean3[0], mean3[1], mean3[2], std3[0], std3[1],
-                     std3[2], out, out_dtype, reinterpret_cast<uint8_t*>(resized_u8)));
-  GB_COUNT_LAUNCH(1);
-  return 0;
+  return gillb200_clip_preprocess_u8_crop(img, B, H, W, S, S, 0, 0, S, mean3, std3, out, out_dtype, resized_u8, stream_);
 }

@@ -150,6 +150,16 @@ static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
 // profiles/r01_shape_sweep.log): time ~ waves x (k_blocks x BN / eff(BN) + epilogue(BN)), where eff() is the measured
 // MMA-issue / smem-fill efficiency of a 128 x BN tile relative to BN = 256 (MMA-only ceilings: 1868 TF/s at BN=256,
 // ~1300 at BN=160/128). Padding waste is implicit in the tile count.
+// plain GEMMs: minimum K depth (in 64-wide blocks) from which the wide pair tile is picked automatically; tuning aid
+static int wide_min_kb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GILLB200_WIDE_GEMM_KB");
+    v = e ? atoi(e) : 1 << 20;  // default: convs only (see the measurements next to the selection)
+  }
+  return v;
+}
+
 static int pick_block_n(int M, int N, int k_blocks) {
   const int cands[5] = {256, 160, 128, 64, 32};
   const double eff[5] = {1.0, 0.70, 0.70, 0.50, 0.30};
@@ -312,11 +322,33 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     const long long tiles2 = 1LL * ((a->M + 255) / 256) * ((a->N + bn - 1) / bn);
     pair = tiles2 >= (num_sms() / 2) * 3 / 4 && p.num_k_blocks >= (bn == 256 ? 10 : 32);
   }
-  if (pair) GB_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256, "cta_pair needs block_n in {64,128,160,256}");
+  // Wide pair tile (256 x 320, two N = 160 MMAs per K-step, see Gemm2Cfg) for N % 320 == 0. Measured on B200
+  // (tools/gpu_conv_bench.py, profiles/r02_conv_wide.log, B = 16): 64x64 C320->320 142 -> 110 us, 32x32 C640->640 134 -> 107,
+  // 16x16 C1280->1280 122 (stream-K) -> 101, 16x16 C2560->1280 258 -> 179; all UNet convs of an evaluation 5.97 -> 4.06 ms.
+  // It needs enough 256 x 320 tiles for the 74 SM pairs: below ~48 (8x8 level, 16x16 C640) stream-K stays.
+  {
+    static int env_wide = -1;
+    if (env_wide < 0) {
+      const char* e = getenv("GILLB200_WIDE");  // "0": never pick the wide tile in auto mode (A/B aid)
+      env_wide = e ? atoi(e) : 1;
+    }
+    const long long tiles_w = 1LL * ((a->M + 255) / 256) * (a->N / 320);
+    const bool can_wide = a->N % 320 == 0 && a->act != ACT_GEGLU && a->cta_pair != 1 && a->stream_k != 2;
+    const bool auto_wide = a->block_n == 0 && env_wide && p.num_k_blocks >= (a->conv3x3 ? 20 : wide_min_kb()) &&
+                           tiles_w >= (num_sms() / 2) * 2 / 3;
+    if (can_wide && (a->block_n == 320 || auto_wide)) {
+      bn = 320;
+      pair = true;
+      want_sk = false;
+    }
+    GB_CHECK_ARG(bn != 320 || pair, "block_n 320 exists only as the CTA-pair wide tile (N %% 320 == 0, no GEGLU, no stream-K)");
+  }
+  if (pair) GB_CHECK_ARG(bn == 64 || bn == 128 || bn == 160 || bn == 256 || bn == 320, "cta_pair needs block_n in {64,128,160,256,320}");
   {
     const uint64_t dims[2] = {(uint64_t)kb_total_cols, (uint64_t)a->N};
     const uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-    const uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? bn / 2 : bn)};
+    // a CTA of a pair loads half of each MMA's B rows per box (the wide tile issues two MMAs of N = 160: 80-row boxes)
+    const uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? (bn == 320 ? bn / 4 : bn / 2) : bn)};
     int r = encode_tmap_16bit(&p.tma_b, a->b, 2, dims, strides, box, bf16);
     if (r) return r;
   }
@@ -458,6 +490,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
       case 64: return launch_gemm2<64>(p, stream);
       case 128: return launch_gemm2<128>(p, stream);
       case 160: return launch_gemm2<160>(p, stream);
+      case 320: return launch_gemm2<320>(p, stream);
       default: return launch_gemm2<256>(p, stream);
     }
   }

@@ -19,18 +19,71 @@ namespace gb {
 
 template <int BLOCK_N>
 struct Gemm2Cfg {
+  // BLOCK_N <= 256: one tcgen05.mma of N = BLOCK_N per K-step, two TMEM accumulator stages.
+  // BLOCK_N == 320 ("wide" tile, for the N = 320 / 640 / 1280 implicit convs): two MMAs of N = 160 per K-step into ONE
+  //   320-column accumulator stage. Operand fill per MMA clock drops from 81 B (256 x 160 tiles: every A tile fetched once per
+  //   N tile) to 56 B per SM, against an L2 -> SM ceiling of ~43 B per SM clock with all 148 SMs pulling (ncu r01: the
+  //   256 x 160 conv moved 1.23 GB L2 -> SM per launch, tensor pipe 44 %). The epilogue no longer overlaps the next tile's
+  //   main loop -- ~1.7 k of ~29 k clocks per tile at K = 2880.
+  static constexpr int NMMA = BLOCK_N > 256 ? 2 : 1;
+  static constexpr int MMA_N = BLOCK_N / NMMA;
+  static constexpr int NACC = BLOCK_N > 256 ? 1 : 2;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows
-  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half of the B tile
+  static constexpr int B_SUB = (MMA_N / 2) * BLOCK_K * 2;        // this CTA's half of one MMA's B rows
+  static constexpr int B_BYTES = NMMA * B_SUB;                   // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAGES_RAW = (SMEM_BUDGET - BAR_BYTES - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr int ACC_STRIDE = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : 256;
-  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 64 && BLOCK_N <= 256, "invalid 2-CTA UMMA N");
-  static_assert(B_BYTES % 1024 == 0, "B half stage must keep 1024-B alignment");
+  static constexpr int ACC_STRIDE = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : BLOCK_N <= 256 ? 256 : 512;
+  static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
+  static_assert(MMA_N % 32 == 0 && MMA_N >= 64 && MMA_N <= 256 && TMEM_COLS <= 512, "invalid 2-CTA UMMA N");
+  static_assert(B_SUB % 1024 == 0, "B sub-tiles must keep 1024-B alignment");
 };
+
+// Tile schedule of one CTA pair. Whole rounds hand pair p the tiles p, p + P, p + 2P, ...; when the tiles left for the
+// last, partial round of a wide (two-MMA) kernel number at most P / 2, each of them is split into its two N halves so
+// that twice as many pairs stay busy (64x64 UNet convs: 256 tiles on 74 pairs = 3 rounds + 34 tiles -> 68 half tiles).
+// `code` = tile * 3 + (0: whole tile, 1 / 2: first / second N half).
+struct PairSched {
+  int kb_per_tile;  // (name shared with SegIter: the staged epilogue reads it)
+  int pair, num_pairs, num_tiles, whole_rounds, rem;
+  bool split;
+  int i;
+  __device__ __forceinline__ bool next(Seg& sg) {
+    sg.kb0 = 0;
+    sg.kb1 = kb_per_tile;
+    if (i < whole_rounds) {
+      sg.tile = (pair + i * num_pairs) * 3;
+      ++i;
+      return true;
+    }
+    if (i > whole_rounds) return false;
+    ++i;
+    const int base = whole_rounds * num_pairs;
+    if (split) {
+      if (pair >= 2 * rem) return false;
+      sg.tile = (base + (pair >> 1)) * 3 + 1 + (pair & 1);
+      return true;
+    }
+    if (pair >= rem) return false;
+    sg.tile = (base + pair) * 3;
+    return true;
+  }
+};
+__device__ __forceinline__ PairSched make_pair_sched(int kb_per_tile, int pair, int num_pairs, int num_tiles, bool wide) {
+  PairSched s;
+  s.kb_per_tile = kb_per_tile;
+  s.pair = pair;
+  s.num_pairs = num_pairs;
+  s.num_tiles = num_tiles;
+  s.whole_rounds = num_tiles / num_pairs;
+  s.rem = num_tiles - s.whole_rounds * num_pairs;
+  s.split = wide && s.rem > 0 && 2 * s.rem <= num_pairs;
+  s.i = 0;
+  return s;
+}
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
@@ -49,6 +102,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = num_m2 * num_n;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const PairSched sched0 = make_pair_sched(p.num_k_blocks, pair, num_pairs, num_tiles, C::NMMA == 2);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tma_a);
@@ -86,9 +140,13 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       // ---------------- TMA producer (both CTAs); warp-uniform loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      PairSched sched = sched0;
+      Seg sg;
+      while (sched.next(sg)) {
+        const int tile = sg.tile / 3, part = sg.tile % 3;  // part 0: whole tile; 1 / 2: one N half of a wide tile
         const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
-        const int n0 = (tile / num_m2) * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2);
+        const int n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0) + static_cast<int>(rank) * (C::MMA_N / 2);
+        const int nmma = part == 0 ? C::NMMA : 1;
         int cb0 = 0, cy0 = 0, cx0 = 0;
         if (p.a_mode == A_CONV3X3) {
           const int per_img = p.conv_W * p.conv_H;
@@ -102,7 +160,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           uint8_t* sb = sa + C::A_BYTES;
           const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
           if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * C::STAGE_BYTES);
+            if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * (C::A_BYTES + nmma * C::B_SUB));
             if (kb >= p.kb_split) {
               tma2_load_2d(sa, &p.tma_a2, full_leader, (kb - p.kb_split) * BLOCK_K, m0);
             } else if (p.a_mode == A_CONV3X3) {
@@ -114,7 +172,9 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             } else {
               tma2_load_2d(sa, &p.tma_a, full_leader, kb * BLOCK_K, m0);
             }
-            tma2_load_2d(sb, &p.tma_b, full_leader, (kb % p.b_kb_wrap) * BLOCK_K, n0);
+            const int bcol = (kb % p.b_kb_wrap) * BLOCK_K;
+            tma2_load_2d(sb, &p.tma_b, full_leader, bcol, n0);
+            if (C::NMMA == 2 && nmma == 2) tma2_load_2d(sb + C::B_SUB, &p.tma_b, full_leader, bcol, n0 + C::MMA_N);
           }
           __syncwarp();
           if (++stage == p.num_stages) {
@@ -127,19 +187,23 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   } else if (warp == 1) {
     if (leader) {
       // ---------------- MMA issuer (leader CTA only; one thread drives both SMs' tensor cores)
-      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
+      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, C::MMA_N, p.in_dtype == DT_BF16, false);
       // incremental descriptors + look-ahead probe of the next stage's barrier: see gemm_mma()
       const uint32_t s0 = smem_u32(smem_tiles);
       const uint64_t da0 = make_smem_desc_sw128(s0, 16, 1024);
       const uint64_t db0 = make_smem_desc_sw128(s0 + C::A_BYTES, 16, 1024);
       constexpr uint64_t DESC_STEP = C::STAGE_BYTES >> 4;
+      constexpr uint64_t SUB_STEP = C::B_SUB >> 4;
       uint64_t da = da0, db = db0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       bool ready = false;
-      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      PairSched sched = sched0;
+      Seg sg;
+      while (sched.next(sg)) {
+        const int nmma = sg.tile % 3 == 0 ? C::NMMA : 1;
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
@@ -152,8 +216,11 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           ready = mbar_test_wait(&bars->full[nstage], nphase);
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
               umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (C::NMMA == 2 && nmma == 2)
+                umma2_f16(tmem_d + C::MMA_N, da + 2 * k, db + SUB_STEP + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
             umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
           }
           __syncwarp();
@@ -164,7 +231,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         }
         if (elect_one()) umma2_commit_mcast(&bars->tmem_full[acc], 0b11);  // accumulators ready in both CTAs
         __syncwarp();
-        if (++acc == 2) {
+        if (++acc == C::NACC) {
           acc = 0;
           acc_phase ^= 1;
         }
@@ -174,11 +241,13 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     // ---------------- epilogue (both CTAs, own 128 accumulator rows)
     if (p.epi_tma) {
       if (warp - 4 < p.epi_warps) {
-        epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE>(
-            p, bars, epi_stage, tmem_base, SegIter{p.num_k_blocks, pair, num_pairs, num_tiles, 0, 0},
-            [&](int tile, int* row_base, int* n0) {
+        epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE, C::NACC>(
+            p, bars, epi_stage, tmem_base, sched0,
+            [&](int code, int* row_base, int* n0, int* ncols) {
+              const int tile = code / 3, part = code % 3;
               *row_base = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
-              *n0 = (tile / num_m2) * BLOCK_N;
+              *n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0);
+              if (part != 0) *ncols = C::MMA_N;
             },
             [&](int acc) {
               tc_fence_before();
@@ -190,14 +259,17 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     const int ewarp = warp & 3;
     const int cgrp = (warp - 4) >> 2;
     constexpr int NGRP = GEMM_EPI_WARPS / 4;
-    constexpr int NCH = BLOCK_N / 16;
-    const int ch_begin = cgrp * (NCH / NGRP) + min(cgrp, NCH % NGRP);
-    const int ch_end = ch_begin + NCH / NGRP + (cgrp < NCH % NGRP ? 1 : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+    PairSched sched = sched0;
+    Seg sg;
+    while (sched.next(sg)) {
+      const int tile = sg.tile / 3, part = sg.tile % 3;
+      const int nch = (part == 0 ? BLOCK_N : C::MMA_N) / 16;
+      const int ch_begin = cgrp * (nch / NGRP) + min(cgrp, nch % NGRP);
+      const int ch_end = ch_begin + nch / NGRP + (cgrp < nch % NGRP ? 1 : 0);
       const int row = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M + ewarp * 32 + lane_id();
-      const int n0 = (tile / num_m2) * BLOCK_N;
+      const int n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0);
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * C::ACC_STRIDE + (static_cast<uint32_t>(ewarp * 32) << 16);
@@ -217,7 +289,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
-      if (++acc == 2) {
+      if (++acc == C::NACC) {
         acc = 0;
         acc_phase ^= 1;
       }

@@ -652,9 +652,9 @@ static_assert(sizeof(GemmSmemBars) <= 1024, "barrier block");
 //   release_fn(acc): arrive on the tile's tmem_empty barrier (local, or the pair leader's for cta_group::2).
 // Per panel: [lane 0: make sure the staging buffer is free, prefetch the next residual panel] -> bias loads in flight
 // -> tcgen05.ld -> math -> swizzled st.shared -> fence.proxy.async -> [lane 0: TMA store].
-template <int BLOCK_N, int ACC_STRIDE, int VAR, typename TileFn, typename Release>
+template <int BLOCK_N, int ACC_STRIDE, int VAR, int NACC, typename Iter, typename TileFn, typename Release>
 __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemBars* bars, uint8_t* epi_stage,
-                                                  uint32_t tmem_base, SegIter it, TileFn tile_fn, Release release_fn) {
+                                                  uint32_t tmem_base, Iter it, TileFn tile_fn, Release release_fn) {
   const int warp = threadIdx.x >> 5;
   const int ew = warp - 4, quad = warp & 3;
   const int cgrp = ew >> 2, ngrp = p.epi_warps >> 2;
@@ -664,10 +664,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
   const bool geglu = VAR == EV_GENERIC ? p.act == ACT_GEGLU : GEGLU;
   const bool has_res = VAR == EV_GENERIC ? p.residual != nullptr : VAR == EV_BIAS_RES;
   const int acc_per_panel = geglu ? 2 * EPI_PANEL_COLS : EPI_PANEL_COLS;
-  const int np = (BLOCK_N + acc_per_panel - 1) / acc_per_panel;
   const int n_out_total = geglu ? p.N / 2 : p.N;
-  const int pb0 = cgrp * (np / ngrp) + min(cgrp, np % ngrp);
-  const int pe0 = pb0 + np / ngrp + (cgrp < np % ngrp ? 1 : 0);
   const uint32_t nbuf = static_cast<uint32_t>(p.epi_nbuf);
   const uint32_t panel_bytes = static_cast<uint32_t>(p.epi_buf_bytes);
   uint8_t* stage = epi_stage + ew * nbuf * panel_bytes;
@@ -680,8 +677,11 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
   Seg sg;
   while (it.next(sg)) {
     const int tile = sg.tile;
-    int row_base, n0;
-    tile_fn(tile, &row_base, &n0);
+    int row_base, n0, ncols = BLOCK_N;  // ncols: accumulator columns this tile really holds (a split tail tile: fewer)
+    tile_fn(tile, &row_base, &n0, &ncols);
+    const int np = (ncols + acc_per_panel - 1) / acc_per_panel;
+    const int pb0 = cgrp * (np / ngrp) + min(cgrp, np % ngrp);
+    const int pe0 = pb0 + np / ngrp + (cgrp < np % ngrp ? 1 : 0);
     const int row0 = row_base + quad * 32;
     // stream-K: a tile cut by a CTA boundary. The owner of k-block 0 finishes it; everyone else parks partials.
     const bool sk_partial = sg.kb0 > 0;
@@ -752,7 +752,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         int* flag = p.sk_flags + static_cast<size_t>(blockIdx.x) * GEMM_EPI_WARPS + ew;
         asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
       }
-      if (++acc == 2) {
+      if (++acc == NACC) {
         acc = 0;
         acc_phase ^= 1;
       }
@@ -934,7 +934,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       if (lane == 0)
         for (int c = sk_first; c <= sk_last; ++c) p.sk_flags[static_cast<size_t>(c) * GEMM_EPI_WARPS + ew] = 0;
     }
-    if (++acc == 2) {
+    if (++acc == NACC) {
       acc = 0;
       acc_phase ^= 1;
     }
@@ -943,33 +943,33 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
 }
 
 // Runtime -> compile-time variant dispatch (once per warp, outside the tile loop).
-template <int BLOCK_N, int ACC_STRIDE, typename TileFn, typename Release>
+template <int BLOCK_N, int ACC_STRIDE, int NACC = 2, typename Iter, typename TileFn, typename Release>
 __device__ __forceinline__ void epilogue_warp_tma_dispatch(const GemmParams& p, GemmSmemBars* bars, uint8_t* epi_stage,
-                                                           uint32_t tmem_base, SegIter it, TileFn tile_fn,
+                                                           uint32_t tmem_base, Iter it, TileFn tile_fn,
                                                            Release release_fn) {
   switch (p.epi_variant) {
     case EV_BIAS:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_BIAS_RES:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_RES>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_RES, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_BIAS_ROWBIAS:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_ROWBIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_BIAS_ROWBIAS, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_LN_BIAS:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_LN_BIAS>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_LN_BIAS, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_LN_GEGLU:
       if constexpr (BLOCK_N % 64 == 0)
-        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_LN_GEGLU>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_LN_GEGLU, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     case EV_GEGLU:
       if constexpr (BLOCK_N % 64 == 0)
-        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GEGLU>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+        epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GEGLU, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
       break;
     default:
-      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GENERIC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
+      epilogue_warp_tma<BLOCK_N, ACC_STRIDE, EV_GENERIC, NACC>(p, bars, epi_stage, tmem_base, it, tile_fn, release_fn);
   }
 }
 
@@ -1034,7 +1034,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     } else if (warp - 4 < p.epi_warps) {
       epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE>(
           p, bars, epi_stage, tmem_base, seg_it,
-          [&](int tile, int* row_base, int* n0) {
+          [&](int tile, int* row_base, int* n0, int*) {
             const TileCoord tc = tile_coord(tile, order);
             *row_base = tc.m_blk * BLOCK_M;
             *n0 = tc.n_blk * BLOCK_N;

@@ -332,11 +332,17 @@ class GILL(nn.Module):
         add_bos = True
         for p in prompts:
             if Image is not None and isinstance(p, Image.Image):
-                if m.feature_extractor is None:
-                    raise NotImplementedError("PIL prompts need a feature_extractor + CLIP visual_model "
-                                              "(SURVEY.md §8f-1); pass CLIP-encoded tensors instead")
-                pixel_values = m.feature_extractor(p.convert("RGB"), return_tensors="pt").pixel_values[0, ...]
-                pixel_values = pixel_values.to(device=dev, dtype=dt)[None, ...]
+                if m.visual_model is None:
+                    raise NotImplementedError("PIL prompts need a CLIP visual_model (gill_b200.clip.CLIPVisionB200, "
+                                              "SURVEY.md §8f-1); pass CLIP-encoded tensors instead")
+                if m.feature_extractor is not None:                               # models.py:608 (host, PIL/numpy)
+                    pixel_values = m.feature_extractor(p.convert("RGB"), return_tensors="pt").pixel_values[0, ...]
+                    pixel_values = pixel_values.to(device=dev, dtype=dt)[None, ...]
+                else:
+                    # the same pre-processing on the device: PIL-exact 8-bit bicubic resize of the shortest edge to 224,
+                    # centre crop, rescale, normalise (gill/utils.py:117-119)
+                    u8 = torch.from_numpy(np.asarray(p.convert("RGB")).copy()).to(dev)[None].contiguous()
+                    pixel_values = ops.clip_preprocess_u8(u8, 224, out_dtype=dt, mode="feature_extractor")
                 input_embs.append(m.get_visual_embs(pixel_values, mode="captioning").to(dt))
             elif isinstance(p, torch.Tensor):
                 t = p.to(dev)
@@ -537,9 +543,158 @@ class GILL(nn.Module):
             out["images"] = torch.cat(imgs, 0) if output_type == "uint8" else sum(imgs, [])
         return out
 
+    # -------------------------------------------------------------------------------------------- batched surface
+    @torch.no_grad()
+    def generate_for_images_and_texts_batch(
+            self, prompt_lists: List[List], num_gen_images: Optional[int] = None, max_num_rets: int = 3,
+            generator=None, latents: Optional[torch.Tensor] = None, guidance_scale: float = 7.5,
+            num_inference_steps: int = 50, always_add_bos: bool = False, bank=None, seen: Optional[List[List[int]]] = None,
+            fetch_images: bool = False, output_type: str = "uint8"):
+        """B independent conversations through the forced-emission path of `generate_for_images_and_texts`
+        (`num_words=2, gen_scale_factor=1e5`, evals/generate_vist_images.py:72-73), each the per-sample equivalent of the
+        reference's strictly batch-1 call (models.py:582-762) -- BASELINE configs[4]:
+
+          * prompts of UNEQUAL length are right-padded to one [B, P_max + 8, D] prefill: OPT is causal, so the 8 [IMG]
+            embeddings placed directly after each prompt's last token see exactly that prompt and nothing of the padding
+            (per-sample [IMG] offsets; positions are left-aligned, so the learned position embeddings match too);
+          * retrieval for all prompts at once, each with its own seen list (`seen`), through `bank` (a ShardedBank:
+            row-sharded across the ranks, one candidate exchange) or `self.emb_matrix`;
+          * decision head, GILLMapper, `num_gen_images` Stable-Diffusion samples per prompt in chunks of 8
+            (models.py:726), then the CLIP re-rank of models.py:733-751 on the device when a vision tower is present.
+
+        Returns one `[caption + ' [IMG0]...[IMG7]', {'gen': [(image, score)...], 'ret': [...], 'decision': ...}]` pair per
+        prompt list; images are uint8 HWC tensors (output_type='uint8') or PIL images ('pil'); 'ret' holds
+        (row index, 'ret', score) triples, or fetched images when fetch_images=True."""
+        m = self.model
+        dev, dt = m.lm.dev, m.lm.dt
+        G = self.num_gen_images if num_gen_images is None else num_gen_images
+        if len(m.retrieval_token_idx) != m.num_tokens:
+            raise ValueError(f"needs all {m.num_tokens} [IMG] token ids in retrieval_token_idx, got {m.retrieval_token_idx}")
+        B = len(prompt_lists)
+        embs = [self._encode_prompts(pl, always_add_bos)[0][0] for pl in prompt_lists]            # [P_i, D] each
+        lens = [int(e.shape[0]) for e in embs]
+        n_img = m.num_tokens
+        T = max(lens) + n_img
+        img_ids = torch.tensor(m.retrieval_token_idx, dtype=torch.int64, device=dev)
+        img_embs = m.input_embeddings(img_ids[None, :])                                          # (1, 8, D)
+        full = torch.zeros((B, T, m.lm.D), device=dev, dtype=dt)
+        for i, e in enumerate(embs):
+            full[i, :lens[i]] = e.to(dt)
+            full[i, lens[i]:lens[i] + n_img] = img_embs[0].to(dt)
+        hs, _ = m.lm.forward(full, need_logits=False)
+        rows = torch.arange(B, device=dev)
+        lens_t = torch.tensor(lens, device=dev)
+        logits = m.lm.logits_of(hs[rows, lens_t - 1]).float()                                     # last prompt position
+        m._postprocess_logits(logits, 0, 0, 1.0, 1e5, -float("Inf"))                              # models.py:475-489
+        forced_ok = (logits.argmax(dim=-1) == m.retrieval_token_idx[0]).tolist()
+        gather = (lens_t[:, None] + torch.arange(n_img, device=dev)[None, :])                     # per-sample [IMG] offsets
+        raw_emb = hs[rows[:, None], gather].float().contiguous()                                   # (B, 8, D) models.py:662
+        gen_prefix = "".join([f"[IMG{i}]" for i in range(n_img)])
+        outs = [{"gen": [], "ret": [], "decision": None} for _ in range(B)]
+        # ---- retrieval (models.py:671-693) for all prompts in one kernel launch / one exchange
+        ret_q = None
+        have_bank = bank is not None or self.emb_matrix is not None
+        if have_bank:
+            ret_emb = m.ret_text_hidden_fcs[0](raw_emb, None)[:, 0, :]
+            ret_q = ops.l2norm_rows(ret_emb.float().contiguous(), torch.bfloat16)
+            seen_l = seen if seen is not None else [[] for _ in range(B)]
+            ex = seen_l if any(len(x) for x in seen_l) else None
+            if bank is not None:
+                vals, idx = bank.search(ret_q, 3, exclude_idx=ex)
+            else:
+                vals, idx = retrieval.retrieval_topk(self.emb_matrix, ret_q, 3, exclude_idx=ex)
+            vals, idx = vals.cpu().tolist(), idx.cpu().tolist()
+            for i in range(B):
+                for rank_i, img_idx in enumerate(idx[i][:max(1, max_num_rets)]):
+                    if fetch_images:
+                        try:
+                            outs[i]["ret"].append((get_image_from_url(self.path_array[img_idx]), "ret", vals[i][rank_i]))
+                        except Exception:
+                            pass
+                    else:
+                        outs[i]["ret"].append((img_idx, "ret", vals[i][rank_i]))
+            if self.decision_model is not None:                                                   # models.py:696-701
+                dl = self.decision_model(raw_emb[:, 0, :].float())
+                probs = dl.softmax(dim=-1).cpu().float().tolist()
+                arg = dl.argmax(dim=-1).tolist()
+                for i in range(B):
+                    outs[i]["decision"] = [self.idx2dec[arg[i]], probs[i]]
+        else:
+            for i in range(B):
+                outs[i]["decision"] = ["gen", [0, 1]]                                             # models.py:704
+        # ---- GILLMapper + Stable Diffusion (models.py:707-731)
+        gen_emb = m.gen_text_hidden_fcs[0](raw_emb, img_embs.float())                             # (B, 77, 768)
+        result_imgs = None
+        if self.load_sd:
+            rep = gen_emb.repeat_interleave(G, dim=0)                                             # models.py:721, per prompt
+            chunks = []
+            for c0 in range(0, B * G, 8):                                                         # gen_max_bs = 8
+                lat = None if latents is None else latents[c0:c0 + 8]
+                chunks.append(self.sd_pipe(prompt_embeds=rep[c0:c0 + 8], generator=generator, latents=lat,
+                                           guidance_scale=guidance_scale, num_inference_steps=num_inference_steps,
+                                           output_type="uint8").images)
+            result_imgs = torch.cat(chunks, 0)                                                    # (B*G, H, W, 3) uint8
+            scores = None
+            if have_bank and m.visual_model is not None:                                          # models.py:733-751
+                px = ops.clip_preprocess_u8(result_imgs.contiguous(), 224, out_dtype=dt)
+                ve = m.get_visual_embs(px, mode="retrieval")[:, 0, :].float()
+                ve = ve / ve.norm(dim=-1, keepdim=True)
+                scores = (ve.view(B, G, -1).to(torch.bfloat16).float() * ret_q.float()[:, None, :]).sum(-1)   # (B, G)
+            for i in range(B):
+                imgs_i = result_imgs[i * G:(i + 1) * G]
+                if output_type == "pil":
+                    imgs_i = [Image.fromarray(a) for a in imgs_i.cpu().numpy()]
+                if scores is not None:
+                    order = torch.argsort(-scores[i]).tolist() if G > 1 else [0]
+                    sc = scores[i].tolist()
+                    outs[i]["gen"] = [(imgs_i[j], sc[j]) for j in order]
+                else:
+                    outs[i]["gen"] = [(imgs_i[0], 0)]                                             # models.py:753
+        else:
+            for i in range(B):
+                outs[i]["gen"] = [gen_emb[i:i + 1]]                                               # models.py:755
+        ret = []
+        for i in range(B):
+            ret.append([f" {gen_prefix}", outs[i]])
+        self.last_batch_info = {"forced_ok": forced_ok, "prompt_lens": lens, "gen_emb": gen_emb, "images": result_imgs,
+                                "ret_q": ret_q, "raw_emb": raw_emb}
+        return ret
+
+    @torch.no_grad()
     def get_log_likelihood_scores(self, prompts: List):
-        raise NotImplementedError("get_log_likelihood_scores (gill/models.py:764-807) needs full-vocabulary logits at "
-                                  "every position; it is not on the image-emission hot path")
+        """gill/models.py:764-807: log likelihood of an interleaved prompt = minus the mean next-token cross entropy over
+        the text positions (image positions carry label -100; <bos> only on the first string). The reference gets it
+        from `lm(..., labels=input_ids).loss`; here: OPT forward -> tied lm_head on every position -> row softmax kernel."""
+        m = self.model
+        dev, dt = m.lm.dev, m.lm.dt
+        input_embs, input_ids = [], []
+        add_bos = True
+        for p in prompts:
+            if (Image is not None and isinstance(p, Image.Image)) or isinstance(p, torch.Tensor):
+                e, _ = self._encode_prompts([p], always_add_bos=False)
+                input_embs.append(e)
+                input_ids.append(torch.full(e.shape[:2], -100, dtype=torch.int64, device=dev))
+            elif type(p) == str:
+                text_ids = m.tokenizer(p, add_special_tokens=True, return_tensors="pt").input_ids.to(dev)
+                if not add_bos:
+                    text_ids = text_ids[:, 1:]                                           # models.py:792-797
+                else:
+                    add_bos = False
+                input_embs.append(m.input_embeddings(text_ids))
+                input_ids.append(text_ids)
+            else:
+                raise ValueError(f"Input prompts should be either PIL.Image.Image or str types, got {type(p)} instead.")
+        embs = torch.cat([e.to(dt) for e in input_embs], dim=1)
+        ids = torch.cat(input_ids, dim=1)
+        hs, _ = m.lm.forward(embs, need_logits=False)
+        logits = m.lm.logits_of(hs[0, :-1])                                              # position t predicts token t+1
+        labels = ids[0, 1:]
+        keep = labels != -100
+        if not bool(keep.any()):
+            return float("nan")                                                          # mean over zero tokens, as torch does
+        probs = ops.softmax_rows(logits, 1.0, torch.float32)
+        tok = probs[torch.arange(labels.numel(), device=dev), labels.clamp_min(0)]
+        return float(tok[keep].log().mean().item())
 
 
 def load_gill(model_dir: str, load_ret_embs: bool = True, decision_model_fn: str = "decision_model.pth.tar", *,

@@ -486,19 +486,41 @@ CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # openai/clip-vit-large-patch1
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
+def hf_clip_geometry(H: int, W: int, size: int = 224):
+    """(RH, RW, top, left) of the HF CLIP feature extractor (transformers 4.30.2 CLIPImageProcessor with the
+    openai/clip-vit-large-patch14 config): shortest edge -> `size` keeping the aspect (long edge = int(size * long / short)),
+    then the centred size x size crop (top = (RH - size) // 2, left = (RW - size) // 2)."""
+    if H <= W:
+        RH, RW = size, int(size * W / H)
+    else:
+        RH, RW = int(size * H / W), size
+    return RH, RW, (RH - size) // 2, (RW - size) // 2
+
+
 def clip_preprocess_u8(img_u8: torch.Tensor, size: int = 224, out_dtype: torch.dtype = torch.bfloat16,
-                       mean=CLIP_MEAN, std=CLIP_STD, return_resized: bool = False):
-    """uint8 NHWC [B,H,W,3] on the device -> CLIP pixel_values NCHW [B,3,size,size]: PIL-exact bicubic resize
-    (`img.resize((224, 224))`, gill/models.py:735) + rescale + normalise (HF feature extractor, gill/utils.py:117-119)."""
+                       mean=CLIP_MEAN, std=CLIP_STD, return_resized: bool = False, mode: str = "square"):
+    """uint8 NHWC [B,H,W,3] on the device -> CLIP pixel_values NCHW [B,3,size,size]: PIL-exact 8-bit bicubic resample +
+    rescale + normalise.
+      mode="square"       : `img.resize((size, size))` then the feature extractor on the already square image -- the
+                            re-rank of generated images (gill/models.py:733-737);
+      mode="feature_extractor": resize shortest edge to `size`, centre crop -- what the HF feature extractor does to image
+                            PROMPTS and bank images (gill/utils.py:117-119, models.py:608, scripts/extract_img_embs.py:37)."""
     assert img_u8.dtype == torch.uint8 and img_u8.is_cuda and img_u8.is_contiguous() and img_u8.shape[-1] == 3
     B, H, W, _ = img_u8.shape
+    if mode == "square":
+        RH, RW, top, left = size, size, 0, 0
+    elif mode == "feature_extractor":
+        RH, RW, top, left = hf_clip_geometry(H, W, size)
+    else:
+        raise ValueError(f"mode must be 'square' or 'feature_extractor', got {mode!r}")
     out = torch.empty((B, 3, size, size), device=img_u8.device, dtype=out_dtype)
     rz = torch.empty((B, size, size, 3), device=img_u8.device, dtype=torch.uint8) if return_resized else None
     m3 = (ctypes.c_float * 3)(*mean)
     s3 = (ctypes.c_float * 3)(*std)
     with _P("clip_preprocess_u8"):
-        check(lib().gillb200_clip_preprocess_u8(img_u8.data_ptr(), B, H, W, size, m3, s3, out.data_ptr(), _DT[out_dtype],
-                                                _ptr(rz), _stream()), "gillb200_clip_preprocess_u8")
+        check(lib().gillb200_clip_preprocess_u8_crop(img_u8.data_ptr(), B, H, W, RH, RW, top, left, size, m3, s3,
+                                                     out.data_ptr(), _DT[out_dtype], _ptr(rz), _stream()),
+              "gillb200_clip_preprocess_u8_crop")
     return (out, rz) if return_resized else out
 
 

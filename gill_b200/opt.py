@@ -129,6 +129,11 @@ class OPTB200:
             logits = ops.gemm(last, self.embed, out_dtype=torch.float32)          # tied lm_head, last position only
         return hs, logits
 
+    @torch.no_grad()
+    def logits_of(self, hidden_rows: torch.Tensor) -> torch.Tensor:
+        """Tied lm_head on selected post-final-LayerNorm hidden states [n, D] -> fp32 logits [n, V]."""
+        return ops.gemm(hidden_rows.to(self.dev, self.dt).contiguous(), self.embed, out_dtype=torch.float32)
+
     def __call__(self, inputs_embeds=None, use_cache=False, output_hidden_states=True, **kw):
         """HF-shaped result for the reference's call site: `.logits[:, -1, :]` and `.hidden_states[-1]` are valid."""
         if inputs_embeds is None:

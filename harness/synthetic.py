@@ -172,3 +172,28 @@ def synthetic_bank_shard(n_total: int, d: int, world: int, rank: int, exact: boo
     assert BANK_CHUNKS % world == 0 and n_total % BANK_CHUNKS == 0
     per, rows = BANK_CHUNKS // world, n_total // BANK_CHUNKS
     return torch.cat([synthetic_bank_chunk(c, rows, d, exact, device) for c in range(rank * per, (rank + 1) * per)], 0)
+
+
+def build_clip_tower(device="cuda", layers: int = 24, seed: int = 4):
+    """CLIP ViT-L/14-shaped vision tower (seeded random init; the real weights cannot be downloaded offline) on the B200
+    kernels, for the re-rank step (gill/models.py:733-751) and raw-pixel prompts."""
+    from gill_b200.clip import CLIPVisionB200
+    from oracle import clip as oclip
+
+    cfg = dict(oclip.CLIP_L14, layers=layers)
+    return CLIPVisionB200(oclip.init_clip(cfg, seed=seed), cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"],
+                          cfg["patch"], cfg["image"], device=device)
+
+
+def config5_prompts(n: int, seed: int):
+    """BASELINE configs[4] prompts: 2 CLIP-encoded images (pooled 1024-d features) + ~64 text tokens each, of UNEQUAL
+    length (56..72 tokens) so that the batched prefill really is ragged."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for i in range(n):
+        f1, f2 = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
+        n1 = 24 + int(torch.randint(0, 9, (1,), generator=g))
+        n2 = 32 + int(torch.randint(0, 9, (1,), generator=g))
+        w = lambda k, o: " ".join(f"w{seed}x{i}y{o + j}" for j in range(k))
+        out.append([f1, w(n1, 0), f2, w(n2, 100)])
+    return out

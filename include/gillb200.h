@@ -77,7 +77,7 @@ typedef struct gillb200_gemm_args {
   int res_dtype;
   int act;   /* GEGLU: B rows interleaved (value, gate) pairs; N_out = N/2 */
   float alpha;
-  int block_n; /* 0 = auto; else one of 32, 64, 128, 160, 256 */
+  int block_n; /* 0 = auto; else one of 32, 64, 128, 160, 256, or 320 (CTA-pair wide tile: N % 320 == 0) */
   int tile_order; /* 0 = auto; 1 = M-fastest tile order; 2 = N-inner (all N tiles of an M block back to back) */
   int cta_pair; /* 0 = auto; 1 = force the 1-CTA kernel; 2 = force the CTA-pair (tcgen05 cta_group::2, 256-row tile) kernel */
   /* optional stream-K scratch: gillb200_gemm_streamk_workspace_bytes() bytes of device memory, ZERO before its first
@@ -216,6 +216,12 @@ int gillb200_image_to_u8(const void* x, int dtype, long long pixels, int ldx, in
  * resized_u8 (optional, device) receives the intermediate uint8 [B,S,S,3] image. */
 int gillb200_clip_preprocess_u8(const void* img, int B, int H, int W, int S, const float* mean3, const float* std3,
                                 void* out, int out_dtype, void* resized_u8, void* stream);
+/* Same resample, general geometry: resize to RH x RW, then take the S x S window at (top, left) of the resized image. With
+ * RH / RW = (shortest edge -> S, aspect kept) and the centred window this is the HF CLIP feature extractor applied to image
+ * PROMPTS (resize shortest edge + centre crop: gill/utils.py:117-119, gill/models.py:608, scripts/extract_img_embs.py:37). */
+int gillb200_clip_preprocess_u8_crop(const void* img, int B, int H, int W, int RH, int RW, int top, int left, int S,
+                                     const float* mean3, const float* std3, void* out, int out_dtype, void* resized_u8,
+                                     void* stream);
 int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int n, void* out, long long ldo, int out_dtype,
                          void* stream);
 int gillb200_cast_add(const void* x, int x_dtype, const void* y, int y_dtype, long long y_period, void* out,

@@ -110,21 +110,46 @@ def _pil_coeffs(in_size: int, out_size: int):
     return out
 
 
-def pil_bicubic_resize_u8(img, size: int):
-    """img: uint8 numpy [H,W,3] -> uint8 [size,size,3], bit-identical to PIL.Image.resize((size,size), BICUBIC)."""
+def pil_bicubic_resize_u8(img, size, size_w=None):
+    """img: uint8 numpy [H,W,3] -> uint8 [size, size_w or size, 3], bit-identical to PIL.Image.resize((w, h), BICUBIC)."""
     import numpy as np
 
+    out_h, out_w = size, (size if size_w is None else size_w)
     H, W, _ = img.shape
     a = img.astype(np.int64)
-    tmp = np.empty((H, size, 3), dtype=np.int64)
-    for o, (x0, kk) in enumerate(_pil_coeffs(W, size)):
+    tmp = np.empty((H, out_w, 3), dtype=np.int64)
+    for o, (x0, kk) in enumerate(_pil_coeffs(W, out_w)):
         acc = (1 << 21) + (a[:, x0:x0 + len(kk), :] * np.asarray(kk, dtype=np.int64)[None, :, None]).sum(1)
         tmp[:, o, :] = np.clip(acc >> 22, 0, 255)
-    out = np.empty((size, size, 3), dtype=np.int64)
-    for o, (y0, kk) in enumerate(_pil_coeffs(H, size)):
+    out = np.empty((out_h, out_w, 3), dtype=np.int64)
+    for o, (y0, kk) in enumerate(_pil_coeffs(H, out_h)):
         acc = (1 << 21) + (tmp[y0:y0 + len(kk), :, :] * np.asarray(kk, dtype=np.int64)[:, None, None]).sum(0)
         out[o] = np.clip(acc >> 22, 0, 255)
     return out.astype(np.uint8)
+
+
+def hf_clip_geometry(H: int, W: int, size: int = 224):
+    """transformers==4.30.2 CLIPImageProcessor (openai/clip-vit-large-patch14 preprocessor_config.json: resize shortest edge
+    224 bicubic, center crop 224): get_resize_output_image_size(default_to_square=False) + image_transforms.center_crop."""
+    if H <= W:
+        RH, RW = size, int(size * W / H)
+    else:
+        RH, RW = int(size * H / W), size
+    return RH, RW, (RH - size) // 2, (RW - size) // 2
+
+
+def clip_feature_extractor(img, size: int = 224):
+    """What `utils.get_pixel_values_for_model(feature_extractor, img)` (gill/utils.py:117-119) returns for a uint8 RGB image
+    [H,W,3]: resize shortest edge (PIL bicubic, 8-bit) -> centre crop -> /255 -> normalise. float32 [3,size,size] plus the
+    cropped uint8 image."""
+    import numpy as np
+
+    H, W, _ = img.shape
+    RH, RW, top, left = hf_clip_geometry(H, W, size)
+    r = pil_bicubic_resize_u8(img, RH, RW)[top:top + size, left:left + size]
+    x = (r.astype(np.float64) * (1 / 255)).astype(np.float32)
+    x = (x - np.asarray(CLIP_MEAN, dtype=np.float32)) / np.asarray(CLIP_STD, dtype=np.float32)
+    return torch.from_numpy(np.ascontiguousarray(x.transpose(2, 0, 1))), r
 
 
 def clip_preprocess(img, size: int = 224):

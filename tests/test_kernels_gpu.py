@@ -1,4 +1,5 @@
 """GPU parity tests of the primitive kernels, called through the C ABI (gill_b200.ops -> libgillb200.so)."""
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -101,6 +102,38 @@ def test_conv3x3_implicit_gemm(ops, case):
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1) + rb[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1) + res.float()
     assert rel(got, ref) < 1e-4
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 320, "res"), (3, 32, 32, 128, 640, "rowbias"), (16, 16, 16, 64, 320, "res"),
+                                  (75, 16, 16, 64, 320, "stats"), (38, 32, 32, 64, 640, "res"), (5, 8, 8, 64, 320, "res")])
+def test_conv3x3_wide_pair_tile(ops, case):
+    """block_n = 320: the CTA-pair wide tile (two N = 160 MMAs per K-step into one 320-column accumulator, no TMEM double
+    buffering), including tile counts that exercise whole rounds, a split tail (both N halves on different pairs) and an
+    unsplit tail, the residual / per-sample row bias / GroupNorm-statistics epilogues and an M tail (5*64 = 320 rows)."""
+    B, H, W, C, Co, mode = case
+    torch.manual_seed(5)
+    x = torch.randn(B, H, W, C, device=dev).half()
+    w = (torch.randn(Co, C, 3, 3, device=dev) / (3 * C ** 0.5)).half()
+    bias = torch.randn(Co, device=dev)
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    kw = {}
+    if mode == "res":
+        res = torch.randn(B, H, W, Co, device=dev).half()
+        kw["residual"] = res
+        ref = ref + res.float()
+    elif mode == "rowbias":
+        rb = torch.randn(B, Co, device=dev)
+        kw["rowbias"] = rb
+        ref = ref + rb[:, None, None, :]
+    got = ops.conv3x3(x, wk, bias=bias, block_n=320, stats=(mode == "stats"), **kw)
+    assert got.dtype == torch.float16 and rel(got, ref) < 2e-3
+    auto = ops.conv3x3(x, wk, bias=bias, block_n=160, **kw)
+    assert rel(got, auto) < 1e-3
+    if mode == "stats":
+        st = got.gn_stats.view(B, H * W // 32, Co, 2)
+        g32 = got.float().view(B, H * W // 32, 32, Co)
+        assert rel(st[..., 0], g32.sum(2)) < 1e-3 and rel(st[..., 1], (g32 * g32).sum(2)) < 1e-3
 
 
 @pytest.mark.parametrize("case", [(1024, 1280, 5120, 0), (4096, 1280, 1536, 0), (520, 384, 2048, 128), (1024, 10240, 1280, 256)])
@@ -438,6 +471,27 @@ def test_clip_preprocess_u8_is_pil_exact(ops, hw):
 def _slab_stats(out2d):
     o = out2d.float().view(out2d.shape[0] // 32, 32, out2d.shape[1])
     return torch.stack([o.sum(1), (o * o).sum(1)], -1)
+
+
+@pytest.mark.parametrize("hw", [(300, 400), (500, 333), (224, 224), (640, 480), (231, 517)])
+def test_clip_feature_extractor_on_device_is_pil_exact(ops, hw):
+    """Image PROMPTS / bank images (gill/utils.py:117-119): resize shortest edge to 224 (PIL 8-bit bicubic), centre crop,
+    rescale, normalise -- the device kernel's cropped uint8 image is bit-identical to PIL, pixel_values match the oracle."""
+    from PIL import Image
+    from oracle import clip as oclip
+
+    h, w = hw
+    rng = np.random.default_rng(2)
+    img = rng.integers(0, 256, size=(2, h, w, 3), dtype=np.uint8)
+    img[:, : h // 3] = (np.linspace(0, 255, w)[None, None, :, None]).astype(np.uint8)
+    pv, rz = ops.clip_preprocess_u8(torch.from_numpy(img).to(dev), 224, out_dtype=torch.float32, return_resized=True,
+                                    mode="feature_extractor")
+    RH, RW, top, left = oclip.hf_clip_geometry(h, w)
+    for b in range(2):
+        ref = np.asarray(Image.fromarray(img[b]).resize((RW, RH), resample=Image.BICUBIC))[top:top + 224, left:left + 224]
+        assert np.array_equal(rz[b].cpu().numpy(), ref)
+        opv, _ = oclip.clip_feature_extractor(img[b])
+        assert torch.allclose(pv[b].cpu(), opv, atol=1e-6)
 
 
 def test_epilogue_groupnorm_statistics(ops):

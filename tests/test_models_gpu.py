@@ -583,6 +583,127 @@ def test_emit_images_batch_equals_per_prompt_calls(gill_small):
         gill.load_sd = True
 
 
+def test_batched_varlen_surface_equals_per_prompt_calls(gill_small):
+    """BASELINE configs[4] surface: prompts of unequal length (right-padded prefill, per-sample [IMG] offsets),
+    num_gen_images > 1, retrieval with per-prompt seen lists and the device re-rank -- each prompt's results equal what the
+    reference-shaped batch-1 call returns for it."""
+    from gill_b200.clip import CLIPVisionB200
+    from oracle import clip as oclip, retrieval as orc
+
+    gill = gill_small
+    m = gill.model
+    g = torch.Generator().manual_seed(8)
+    f1, f2 = torch.randn(1024, generator=g), torch.randn(1024, generator=g)
+    prompts = [[f1, "a picture of a dog", f2, "and another one of a cat on a mat"], ["only text here"], [f2, "x"]]
+    bank = orc.synthetic_bank_chunk(0, 5000, 256)
+    cfg = dict(oclip.CLIP_L14, layers=1)
+    tower = CLIPVisionB200(oclip.init_clip(cfg, seed=8), cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"],
+                           cfg["patch"], cfg["image"], device=dev)
+    old = (m.visual_model, gill.emb_matrix, gill.path_array)
+    m.visual_model, gill.emb_matrix = tower, bank.to(dev)
+    gill.path_array = [f"http://127.0.0.1:9/{i}.jpg" for i in range(5000)]
+    try:
+        lat = torch.randn(6, 4, 32, 32, generator=g).half().to(dev)
+        seen = [[], [7, 8], []]
+        out = gill.generate_for_images_and_texts_batch(prompts, num_gen_images=2, latents=lat, num_inference_steps=2, seen=seen)
+        info = gill.last_batch_info
+        assert len(out) == 3 and all(info["forced_ok"]) and len(set(info["prompt_lens"])) == 3      # really ragged
+        for i, (cap, d) in enumerate(out):
+            assert cap.endswith("[IMG0][IMG1][IMG2][IMG3][IMG4][IMG5][IMG6][IMG7]")
+            assert len(d["gen"]) == 2 and d["gen"][0][0].shape == (64, 64, 3) and d["gen"][0][0].dtype == torch.uint8
+            sc = [x[1] for x in d["gen"]]
+            assert sc == sorted(sc, reverse=True) and all(abs(x) <= 1.01 for x in sc)
+            rv, ri = orc.retrieval_topk(bank, info["ret_q"][i:i + 1].cpu(), 3, exclude_idx=seen[i])
+            assert [x[0] for x in d["ret"]] == ri[0].tolist()
+            assert np.allclose([x[2] for x in d["ret"]], rv[0].tolist(), rtol=1e-5, atol=1e-4)
+        # per-prompt reference-shaped calls: same [IMG] hidden states -> same mapper output
+        gill.load_sd = False
+        for i, pl in enumerate(prompts):
+            single = gill.generate_for_images_and_texts(pl, num_words=2, gen_scale_factor=1e5)
+            assert rel(info["gen_emb"][i:i + 1], single[1]["gen"][0]) < 2e-2
+        # images: the same latents through the pipeline directly
+        gill.load_sd = True
+        direct = gill.sd_pipe(prompt_embeds=info["gen_emb"].repeat_interleave(2, dim=0), latents=lat, num_inference_steps=2,
+                              output_type="uint8").images
+        assert torch.equal(direct, info["images"])
+    finally:
+        gill.load_sd = True
+        m.visual_model, gill.emb_matrix, gill.path_array = old
+
+
+def test_pil_prompts_and_bank_builder_on_device(gill_small, tmp_path):
+    """PIL image prompts without a host feature extractor (device pre-processing -> CLIP tower -> visual prefix,
+    gill/models.py:604-612) and the bank builder (scripts/extract_img_embs.py:26-43 + the load-time preparation
+    models.py:895-900) against the oracle tower / reference expressions."""
+    from PIL import Image
+    from gill_b200 import bank as gbank, retrieval
+    from gill_b200.clip import CLIPVisionB200
+    from oracle import clip as oclip
+
+    gill = gill_small
+    m = gill.model
+    cfg = dict(oclip.CLIP_L14, layers=1)
+    csd = {k: v.bfloat16().float() for k, v in oclip.init_clip(cfg, seed=8).items()}
+    tower = CLIPVisionB200(csd, cfg["hidden"], cfg["layers"], cfg["heads"], cfg["mlp"], cfg["patch"], cfg["image"], device=dev)
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, size=s_, dtype=np.uint8) for s_ in ((300, 400, 3), (300, 400, 3), (480, 360, 3))]
+    old = m.visual_model
+    m.visual_model = tower
+    try:
+        # ---- PIL prompt -> visual prefix embeddings
+        embs, _ = gill._encode_prompts([Image.fromarray(imgs[0]), "a caption"], always_add_bos=False)
+        assert embs.shape[1] == m.args.n_visual_tokens + 3                      # 4 prefix tokens + BOS + 2 words
+        pv, _ = oclip.clip_feature_extractor(imgs[0])
+        _, pooled = oclip.clip_vision_forward(csd, pv[None].bfloat16().float(), cfg)
+        w, b = m.visual_embeddings.weight.float().cpu(), m.visual_embeddings.bias.float().cpu()
+        ref = (pooled @ w.T + b).view(1, m.args.n_visual_tokens, -1)
+        assert rel(embs[:, :m.args.n_visual_tokens], ref) < 2e-2
+        # ---- bank builder
+        paths = [f"img{i}.jpg" for i in range(3)]
+        gbank.build_bank(gill, [Image.fromarray(a) for a in imgs], paths, str(tmp_path / "bank"), shards=2)
+        got = gbank.load_bank_rows(str(tmp_path / "bank"), 0, 3, device="cpu")
+        assert gbank.load_paths(str(tmp_path / "bank")) == paths and got.shape == (3, m.args.ret_emb_dim)
+        wf, bf = m.visual_fc.weight.float().cpu(), m.visual_fc.bias.float().cpu()
+        rows = []
+        for a in imgs:
+            pv, _ = oclip.clip_feature_extractor(a)
+            _, pooled = oclip.clip_vision_forward(csd, pv[None].bfloat16().float(), cfg)
+            rows.append(pooled @ wf.T + bf)
+        expect = retrieval.prepare_bank(torch.cat(rows).numpy(), m.logit_scale.detach().cpu())
+        assert rel(got.float(), expect.float()) < 2e-2
+        # rows are unit vectors times exp(logit_scale)
+        assert torch.allclose(got.float().norm(dim=1), torch.full((3,), float(m.logit_scale.exp())), rtol=2e-2)
+    finally:
+        m.visual_model = old
+
+
+def test_get_log_likelihood_scores_matches_oracle(gill_small):
+    """gill/models.py:764-807 against the fp32 OPT oracle's logits: -mean CE over text positions, image positions ignored."""
+    from oracle import opt as oopt
+
+    gill = gill_small
+    m = gill.model
+    g = torch.Generator().manual_seed(9)
+    feat = torch.randn(1024, generator=g)
+    prompts = [feat, "a picture of a small dog", feat, "and a cat"]
+    got = gill.get_log_likelihood_scores(prompts)
+    # the same inputs through the oracle
+    embs, _ = gill._encode_prompts(prompts, always_add_bos=False)
+    tok = m.tokenizer
+    ids = [torch.full((1, 4), -100), tok("a picture of a small dog", return_tensors="pt").input_ids,
+           torch.full((1, 4), -100), tok("and a cat", return_tensors="pt").input_ids[:, 1:]]
+    ids = torch.cat(ids, 1)
+    lm = m.lm
+    hs, _ = lm.forward(embs, need_logits=False)
+    logits = (hs[0, :-1].float() @ lm.embed.float().T).cpu()
+    lab = ids[0, 1:]
+    keep = lab != -100
+    ref = -torch.nn.functional.cross_entropy(logits[keep], lab[keep]).item()
+    assert np.isfinite(got) and abs(got - ref) < 2e-2 * abs(ref) + 1e-3
+    with pytest.raises(ValueError):
+        gill.get_log_likelihood_scores([1.5])
+
+
 def test_smoke_entry_point():
     import __graft_entry__ as g
 

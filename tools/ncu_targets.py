@@ -34,4 +34,25 @@ elif which == "big":
 elif which == "gn":
     x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, device=dev); b = torch.randn(320, device=dev)
     for _ in range(3): ops.groupnorm(x, w, b, 32, 1e-5, silu=True)
+elif which in ("attn48", "xattn48"):
+    # round-2 layout: head pitch 48 (hd 40), V's ones column, P through tensor memory
+    B, H, L, hd, pt = 16, 8, 4096, 40, 48
+    Lk = L if which == "attn48" else 77
+    buf = torch.zeros(B, L, 3, H, pt, device=dev)
+    buf[..., :hd] = torch.randn(B, L, 3, H, hd, device=dev)
+    buf[:, :, 2, :, hd] = 1.0
+    buf = buf.view(B, L, 3 * H * pt).half()
+    q, k, v = buf[:, :, : H * pt], buf[:, :Lk, H * pt: 2 * H * pt], buf[:, :Lk, 2 * H * pt:]
+    for _ in range(4): ops.attention(q, k, v, H, 64, hd ** -0.5, ones_col=hd, head_stride=pt)
+elif which == "topk":
+    from gill_b200 import retrieval
+    bank = torch.randn(1_000_000, 768, device=dev).bfloat16(); q = torch.randn(1024, 768, device=dev).bfloat16()
+    for _ in range(3): retrieval.retrieval_topk(bank, q, 16)
+elif which == "topk1":
+    from gill_b200 import retrieval
+    bank = torch.randn(3_000_000, 256, device=dev).bfloat16(); q = torch.randn(1, 256, device=dev).bfloat16()
+    for _ in range(3): retrieval.retrieval_topk(bank, q, 3, exclude_idx=[5, 9])
+elif which == "convwide":
+    x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, 2880, device=dev).half() * 0.02; bias = torch.randn(320, device=dev)
+    for _ in range(3): ops.conv3x3(x, w, bias=bias, block_n=320)
 torch.cuda.synchronize()
