@@ -151,5 +151,6 @@ def build_bank(model, images: Iterable, paths: Sequence[str], out_dir: str, shar
     if n != len(paths):
         raise ValueError(f"{n} images for {len(paths)} paths")
     emb = torch.cat(embs, 0)
-    bank = retrieval.prepare_bank(emb.numpy(), m.logit_scale.detach())
+    # the reference prepares the bank in the model dtype, bf16 after load_gill's model.bfloat16() (models.py:876, :896-899)
+    bank = retrieval.prepare_bank(emb.numpy(), m.logit_scale.detach().to(torch.bfloat16))
     save_prepared_bank(bank.cpu(), list(paths), out_dir, shards=shards)

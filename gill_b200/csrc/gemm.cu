@@ -155,7 +155,10 @@ static int wide_min_kb() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("GILLB200_WIDE_GEMM_KB");
-    v = e ? atoi(e) : 1 << 20;  // default: convs only (see the measurements next to the selection)
+    // measured (tools/gpu_gemm_bench.py, profiles/r02_gemm_shapes.log): from K = 960 up the wide tile wins or ties on
+    // every N % 320 == 0 linear with enough tiles (M4096 N1280 K5120 61.7 -> 45.3 us, K2560 35.8 -> 28.3, K1280 24.3 -> 20.8,
+    // M65536 N320 K1280 68.0 -> 65.0); at K <= 768 the un-overlapped epilogue costs more than the fill it saves
+    v = e ? atoi(e) : 15;
   }
   return v;
 }

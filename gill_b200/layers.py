@@ -43,6 +43,12 @@ class TextFcLayer(nn.Module):
             raise NotImplementedError(mode)
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._packed_key = None
+        # Attention of the mapper on the tcgen05 flash kernel with fp16 operands (q/k/v and P carry 11 significant bits,
+        # the output is split back into bf16 hi + lo exactly) instead of the fp32 SIMT kernel: measured at B=256, 11
+        # launches, 2.11 ms -> see profiles/r02_mapper_profile_*.log. GILLB200_MAPPER_ATTN=f32 restores the SIMT path.
+        import os
+
+        self.tc_attention = os.environ.get("GILLB200_MAPPER_ATTN", "tc") != "f32"
 
     # ---------------------------------------------------------------------------------------------------- weights
     def _pack(self):
@@ -105,16 +111,21 @@ class TextFcLayer(nn.Module):
     def _mha(self, pk, name, q_hi, q_lo, kv_hi, kv_lo, B, Lq, Lk, residual, self_attn):
         W, bias = pk[name + ".in_proj_weight"], pk[name + ".in_proj_bias"]
         scale = (_D // _H) ** -0.5
+        pdt = torch.float16 if self.tc_attention else torch.float32      # projection output = attention operand dtype
         if self_attn:
-            qkv = ops.gemm(q_hi, W, a2=q_lo, a2_mode=2, bias=bias, out_dtype=torch.float32).view(B, Lq, 3 * _D)
+            qkv = ops.gemm(q_hi, W, a2=q_lo, a2_mode=2, bias=bias, out_dtype=pdt).view(B, Lq, 3 * _D)
             q, k, v = qkv[:, :, :_D], qkv[:, :, _D:2 * _D], qkv[:, :, 2 * _D:]
         else:
-            q = ops.gemm(q_hi, W[:_D], a2=q_lo, a2_mode=2, bias=bias[:_D], out_dtype=torch.float32).view(B, Lq, _D)
-            kv = ops.gemm(kv_hi, W[_D:], a2=kv_lo, a2_mode=2, bias=bias[_D:], out_dtype=torch.float32).view(B, Lk, 2 * _D)
+            q = ops.gemm(q_hi, W[:_D], a2=q_lo, a2_mode=2, bias=bias[:_D], out_dtype=pdt).view(B, Lq, _D)
+            kv = ops.gemm(kv_hi, W[_D:], a2=kv_lo, a2_mode=2, bias=bias[_D:], out_dtype=pdt).view(B, Lk, 2 * _D)
             k, v = kv[:, :, :_D], kv[:, :, _D:]
         a_hi = torch.empty((B, Lq, _D), device=q_hi.device, dtype=torch.bfloat16)
         a_lo = torch.empty_like(a_hi)
-        ops.attn_small_f32(q, k, v, _H, scale, out=a_hi, out_lo=a_lo)
+        if self.tc_attention:
+            a16 = ops.attention(q, k, v, _H, _D // _H, scale)                            # [B, Lq, 512] fp16
+            ops.cast_add(a16, None, torch.bfloat16, out=a_hi, out_lo=a_lo)               # fp16 = bf16 hi + bf16 lo exactly
+        else:
+            ops.attn_small_f32(q, k, v, _H, scale, out=a_hi, out_lo=a_lo)
         return ops.gemm(a_hi.view(B * Lq, _D), pk[name + ".out_proj.weight"], a2=a_lo.view(B * Lq, _D), a2_mode=2,
                         bias=pk[name + ".out_proj.bias"], residual=residual, out_dtype=torch.float32)
 

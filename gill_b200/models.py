@@ -687,11 +687,15 @@ class GILL(nn.Module):
         embs = torch.cat([e.to(dt) for e in input_embs], dim=1)
         ids = torch.cat(input_ids, dim=1)
         hs, _ = m.lm.forward(embs, need_logits=False)
-        logits = m.lm.logits_of(hs[0, :-1])                                              # position t predicts token t+1
         labels = ids[0, 1:]
         keep = labels != -100
         if not bool(keep.any()):
             return float("nan")                                                          # mean over zero tokens, as torch does
+        # position t predicts token t+1; the vocabulary is padded to a multiple of 8 columns of -inf for the vector kernels
+        V = m.lm.embed.shape[0]
+        Vp = (V + 7) // 8 * 8
+        logits = torch.full((embs.shape[1] - 1, Vp), -float("inf"), device=dev, dtype=torch.float32)
+        ops.gemm(hs[0, :-1].contiguous(), m.lm.embed, out=logits[:, :V])
         probs = ops.softmax_rows(logits, 1.0, torch.float32)
         tok = probs[torch.arange(labels.numel(), device=dev), labels.clamp_min(0)]
         return float(tok[keep].log().mean().item())
