@@ -183,6 +183,29 @@ __global__ void cast_add_kernel(const void* __restrict__ x, int x_dtype, const v
   }
 }
 
+// 16-bit -> bf16 (+ bf16 residue), 8 elements per thread: the GILLMapper's fp16 attention output split back into the
+// hi + lo operand pair of the next split-precision GEMM (the scalar kernel above took 20 us per 10 M elements).
+__global__ void __launch_bounds__(256) cast_split8_kernel(const uint4* __restrict__ x, int x_is_bf16, uint4* __restrict__ out,
+                                                          uint4* __restrict__ out_lo, long long nvec) {
+  pdl_wait();
+  pdl_launch();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 u = __ldg(x + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = x_is_bf16 ? unpack_bf16x2(w[j]) : unpack_f16x2(w[j]);
+      hi[j] = pack_bf16x2(f.x, f.y);
+      const float2 h = unpack_bf16x2(hi[j]);
+      lo[j] = pack_bf16x2(f.x - h.x, f.y - h.y);
+    }
+    out[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (out_lo) out_lo[i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // fp32 attention for short sequences (GILLMapper: 4 heads x 128, Lq <= 77, Lk in {8, 77}; gill/layers.py:43).
 // One CTA per (batch, head). q/k/v fp32 with row stride ld*, head h at column h*HD. Output fp32 or bf16 hi+lo.
 template <int HD>
@@ -459,6 +482,13 @@ extern "C" int gillb200_cast_add(const void* x, int x_dtype, const void* y, int 
                                  int out_dtype, void* out_lo, long long n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && n > 0, "cast_add: bad args");
+  if (!y && x_dtype != DT_F32 && out_dtype == DT_BF16 && n % 8 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+      reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(out_lo) % 16 == 0) {
+    GB_CUDA(launch_pdl(cast_split8_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x),
+                       x_dtype == DT_BF16 ? 1 : 0, reinterpret_cast<uint4*>(out), reinterpret_cast<uint4*>(out_lo), n / 8));
+    GB_COUNT_LAUNCH(1);
+    return 0;
+  }
   GB_CUDA(launch_pdl(cast_add_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());

@@ -95,13 +95,13 @@ int num_sms() {
 
 // Shared-memory plan: [num_stages x stage][1 KB barriers][epilogue staging] (+1 KB alignment slack). The smem-staged
 // epilogue trades ring stages for staging buffers.
-static int plan_smem(GemmParams& p, int stage_bytes, int max_stages) {
+static int plan_smem(GemmParams& p, int stage_bytes, int max_stages, int resident_bytes = 0) {
   const int epi_bytes = p.epi_tma ? p.epi_warps * p.epi_nbuf * p.epi_buf_bytes : 0;
-  int stages = (SMEM_BUDGET - 2048 - epi_bytes) / stage_bytes;
+  int stages = (SMEM_BUDGET - 2048 - epi_bytes - resident_bytes) / stage_bytes;
   if (stages > max_stages) stages = max_stages;
   if (stages > 8) stages = 8;
   p.num_stages = stages;
-  return stages * stage_bytes + 2048 + epi_bytes;
+  return resident_bytes + stages * stage_bytes + 2048 + epi_bytes;
 }
 
 template <int BN>
@@ -111,12 +111,26 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
   }
-  const int smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
-  GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (BN=%d)", BN);
   const int num_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles = num_m * num_n;
   int grid = tiles < num_sms() ? tiles : num_sms();
+  int smem_bytes;
+  if (p.b_resident) {
+    // B-stationary: the weight tile [BN x K] sits in front of an A-only ring; n-inner order + a grid that is a multiple of
+    // the N-tile count pin one N tile to each CTA
+    p.b_res_bytes = p.num_k_blocks * C::B_BYTES;
+    smem_bytes = plan_smem(p, C::A_BYTES, 8, p.b_res_bytes);
+    if (p.num_stages < 3) {
+      p.b_resident = 0;
+      p.b_res_bytes = 0;
+    } else {
+      grid = num_sms() / num_n * num_n;
+      p.tile_order = 2;
+    }
+  }
+  if (!p.b_resident) smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
+  GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (BN=%d)", BN);
   if (p.sk_per > 0) {  // stream-K: every SM gets an equal share of the (tile, k-block) units
     const long long total = 1LL * tiles * p.num_k_blocks;
     grid = num_sms();
@@ -144,6 +158,52 @@ static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
   GB_CUDA(launch_pdl(gemm2_kernel<BN>, dim3(2 * pairs), dim3(GEMM_THREADS), smem_bytes, stream, p));  // cluster (2,1,1)
   GB_COUNT_LAUNCH(1);
   return 0;
+}
+
+// Split-K second pass (see GemmParams::ksplit): out = act-free epilogue of sum_s partial[s] -- bias, per-sample row bias,
+// residual, 16-bit rounding and the GroupNorm statistics of the rounded output (same layout as the staged epilogue's
+// stats_out: per 32-row slab and column {sum, sumsq}). One thread per column, 32 rows per CTA: every load / store of a
+// warp is one contiguous row segment.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int S, int M, int N,
+                                                            const float* __restrict__ bias, const float* __restrict__ rowbias,
+                                                            long long ld_rowbias, int rows_per_group,
+                                                            const uint16_t* __restrict__ residual, long long ldr,
+                                                            uint16_t* __restrict__ out, long long ldo, int out_bf16,
+                                                            float2* __restrict__ stats_out) {
+  pdl_wait();
+  pdl_launch();
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  const int row0 = blockIdx.y * 32;
+  if (col >= N) return;
+  const float b = bias ? bias[col] : 0.f;
+  float cs = 0.f, cq = 0.f;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;
+    float v = b;
+    for (int s = 0; s < S; ++s) v += part[(static_cast<size_t>(s) * M + row) * N + col];
+    if (rowbias) v += rowbias[static_cast<long long>(row / rows_per_group) * ld_rowbias + col];
+    if (residual) {
+      const uint16_t h = residual[static_cast<long long>(row) * ldr + col];
+      v += out_bf16 ? __uint_as_float(static_cast<uint32_t>(h) << 16) : __half2float(__ushort_as_half(h));
+    }
+    uint16_t o;
+    float back;
+    if (out_bf16) {
+      const __nv_bfloat16 t = __float2bfloat16_rn(v);
+      o = __bfloat16_as_ushort(t);
+      back = __bfloat162float(t);
+    } else {
+      const __half t = __float2half_rn(v);
+      o = __half_as_ushort(t);
+      back = __half2float(t);
+    }
+    out[static_cast<long long>(row) * ldo + col] = o;
+    cs += back;
+    cq = fmaf(back, back, cq);
+  }
+  if (stats_out) stats_out[static_cast<size_t>(blockIdx.y) * N + col] = make_float2(cs, cq);
 }
 
 // Pick the N tile width from a small cost model fitted to measurements on B200 (tools/gpu_sweep_shapes.py,
@@ -196,13 +256,18 @@ extern "C" long long gillb200_launch_count(void) { return gb::g_launch_count; }
 
 // stream-K scratch: [sms x GEMM_EPI_WARPS] arrival flags (padded to 16 KB), then one 128 x 256 fp32 partial tile per SM
 static constexpr long long SK_FLAG_BYTES = 16384;
+// (also the split-K scratch of the CTA-pair kernel: ksplit fp32 partial copies of the output, at most SPLITK_BYTES)
+static constexpr long long SPLITK_BYTES = 64LL << 20;
 extern "C" long long gillb200_gemm_streamk_workspace_bytes(void) {
-  return SK_FLAG_BYTES + 1LL * gb::num_sms() * BLOCK_M * 256 * sizeof(float);
+  const long long sk = 1LL * gb::num_sms() * BLOCK_M * 256 * sizeof(float);
+  return SK_FLAG_BYTES + (sk > SPLITK_BYTES ? sk : SPLITK_BYTES);
 }
 
-extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
+extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GB_CHECK_ARG(a != nullptr, "null args");
+  GB_CHECK_ARG(a_in != nullptr, "null args");
+  gillb200_gemm_args aa = *a_in;  // (a split-K launch redirects the output / epilogue fields of this copy, see below)
+  gillb200_gemm_args* a = &aa;
   GB_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "bad GEMM shape M=%d N=%d K=%d", a->M, a->N, a->K);
   GB_CHECK_ARG(a->in_dtype == DT_BF16 || a->in_dtype == DT_F16, "operand dtype must be bf16 or fp16");
   GB_CHECK_ARG(a->out != nullptr && a->a != nullptr && a->b != nullptr, "null operand");
@@ -212,6 +277,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = a->M;
+  p.M_out = a->M;
   p.N = a->N;
   int kb_main;
   if (a->conv3x3) {
@@ -304,7 +370,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     env_sk = e ? atoi(e) : 1;
   }
   // (stream-K partial/flag traffic assumes the previous GEMM of the stream has fully drained: never with PDL overlap)
-  if (a->sk_workspace && a->stream_k != 1 && (a->stream_k == 2 || env_sk) && a->tile_order != 2 && a->cta_pair != 2 &&
+  if (a->sk_workspace && a->stream_k != 1 && a->stream_k != 3 && (a->stream_k == 2 || env_sk) && a->tile_order != 2 && a->cta_pair != 2 &&
       !pdl_enabled()) {
     if (a->stream_k == 2) {
       want_sk = true;
@@ -343,6 +409,40 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
       bn = 320;
       pair = true;
       want_sk = false;
+    }
+    // Too few wide tiles for the 74 SM pairs (8x8 level: 16, 16x16 C640: 32): cut K into slices so that tiles x slices
+    // fills them, fp32 partials through the scratch buffer, second pass = splitk_reduce_kernel. OPT-IN (stream_k = 3 or
+    // GILLB200_SPLITK=1): measured on B200 it LOSES to the 1-CTA stream-K it was meant to replace -- 8x8 C1280->1280, B=16:
+    // 104.8 us main launch + 42 us reduce vs 63.6 us (ncu launch list, profiles/r02_splitk_launches.csv). With 64 pairs
+    // pulling 4-D halo boxes of the same 2.6 MB activation the per-k-block time rose 4.5x over the 16-pair unsplit run
+    // (the aggregate L2 -> SM rate stayed at ~1.1 KB per clock), so more SMs bought nothing.
+    static int env_splitk = -1;
+    if (env_splitk < 0) {
+      const char* e = getenv("GILLB200_SPLITK");
+      env_splitk = e ? atoi(e) : 0;
+    }
+    if (can_wide && a->block_n == 0 && env_wide && (env_splitk || a->stream_k == 3) && a->conv3x3 && a->sk_workspace && a->M % 256 == 0 &&
+        tiles_w < (num_sms() / 2) * 2 / 3 && tiles_w >= 8 && a->out_dtype != DT_F32 && a->act == ACT_NONE && a->alpha == 1.f &&
+        !a->out_lo && !a->rowstats_out && !a->ln_stats && (!a->residual || a->res_dtype == a->out_dtype) && !a->bias_along_m) {
+      int S = static_cast<int>((num_sms() / 2) / tiles_w);
+      while (S > 1 && p.num_k_blocks / S < 20) --S;
+      while (S > 1 && 1LL * S * a->M * a->N * 4 > SPLITK_BYTES) --S;
+      if (S > 1) {
+        bn = 320;
+        pair = true;
+        want_sk = false;
+        p.ksplit = S;
+        p.kb_per_split = (p.num_k_blocks + S - 1) / S;
+        p.M_out = S * a->M;
+        // main launch: plain fp32 partial tiles into the scratch buffer; the real epilogue runs in splitk_reduce_kernel
+        aa.out = reinterpret_cast<char*>(a_in->sk_workspace) + SK_FLAG_BYTES;
+        aa.ldo = a->N;
+        aa.out_dtype = DT_F32;
+        aa.bias = nullptr;
+        aa.rowbias = nullptr;
+        aa.residual = nullptr;
+        aa.stats_out = nullptr;
+      }
     }
     GB_CHECK_ARG(bn != 320 || pair, "block_n 320 exists only as the CTA-pair wide tile (N %% 320 == 0, no GEGLU, no stream-K)");
   }
@@ -392,14 +492,15 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     }
     const int esz = a->out_dtype == DT_F32 ? 4 : 2;
     const int n_out = a->act == ACT_GEGLU ? a->N / 2 : a->N;
-    bool ok = env_epi != 0 && a->out_lo == nullptr && reinterpret_cast<uintptr_t>(a->out) % 16 == 0 &&
-              (a->ldo * esz) % 16 == 0;
+    bool ok = env_epi != 0 && reinterpret_cast<uintptr_t>(a->out) % 16 == 0 && (a->ldo * esz) % 16 == 0;
+    // bf16 hi + lo outputs (split-precision activations of the GILLMapper FFN): staged too, as two panels per store
+    if (a->out_lo) ok = ok && !a->residual && a->act != ACT_GEGLU && reinterpret_cast<uintptr_t>(a->out_lo) % 16 == 0;
     if (a->residual)
       ok = ok && a->res_dtype == a->out_dtype && reinterpret_cast<uintptr_t>(a->residual) % 16 == 0 &&
            (a->ldr * esz) % 16 == 0;
     if (a->act == ACT_GEGLU && bn % 64 != 0) ok = false;  // explicitly requested odd tile width
     if (ok) {
-      const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
+      const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)p.M_out};
       const uint32_t box[2] = {EPI_PANEL_COLS, 32};
       const uint64_t so[1] = {(uint64_t)a->ldo * esz};
       int r = encode_tmap(&p.tma_out, a->out, a->out_dtype, 2, dims, so, box, esz == 4 ? 128 : 64, nullptr);
@@ -407,6 +508,10 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
       if (a->residual) {
         const uint64_t sr[1] = {(uint64_t)a->ldr * esz};
         r = encode_tmap(&p.tma_res, a->residual, a->res_dtype, 2, dims, sr, box, esz == 4 ? 128 : 64, nullptr);
+        if (r) return r;
+      }
+      if (a->out_lo) {
+        r = encode_tmap(&p.tma_out_lo, a->out_lo, DT_BF16, 2, dims, so, box, 64, nullptr);
         if (r) return r;
       }
       p.epi_tma = 1;
@@ -488,6 +593,32 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a, void* stream_) {
     }
   }
 
+  // ---- B-stationary 1-CTA mode (see GemmParams::b_resident): short-K plain linears with many M tiles per CTA and <= 4 N tiles
+  {
+    static int env_bres = -1;
+    if (env_bres < 0) {
+      const char* e = getenv("GILLB200_BRES");  // "0": off (A/B aid)
+      env_bres = e ? atoi(e) : 1;
+    }
+    const int num_m = (a->M + BLOCK_M - 1) / BLOCK_M, num_n = (a->N + bn - 1) / bn;
+    if (env_bres && !pair && p.sk_per == 0 && !a->conv3x3 && a->a2_mode == 0 && p.epi_tma && p.num_k_blocks <= 8 && num_n <= 4 &&
+        a->tile_order != 1 && bn >= 128 && 1LL * num_m * num_n >= 3LL * num_sms())
+      p.b_resident = 1;
+  }
+  if (p.ksplit > 1) {
+    GB_CHECK_ARG(p.epi_tma && pair && bn == 320, "split-K needs the staged epilogue of the wide pair kernel");
+    int r = launch_gemm2<320>(p, stream);
+    if (r) return r;
+    const gillb200_gemm_args* o = a_in;
+    dim3 grid((o->N + 255) / 256, (o->M + 31) / 32);
+    GB_CUDA(launch_pdl(splitk_reduce_kernel, grid, dim3(256), 0, stream, reinterpret_cast<const float*>(aa.out), p.ksplit, o->M,
+                       o->N, o->bias, o->rowbias, static_cast<long long>(o->ld_rowbias), o->rows_per_group > 0 ? o->rows_per_group : 1,
+                       reinterpret_cast<const uint16_t*>(o->residual), static_cast<long long>(o->ldr),
+                       reinterpret_cast<uint16_t*>(o->out), static_cast<long long>(o->ldo), o->out_dtype == DT_BF16 ? 1 : 0,
+                       reinterpret_cast<float2*>(o->stats_out)));
+    GB_COUNT_LAUNCH(1);
+    return 0;
+  }
   if (pair) {
     switch (bn) {
       case 64: return launch_gemm2<64>(p, stream);

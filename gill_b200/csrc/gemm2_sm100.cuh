@@ -100,14 +100,28 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   const bool leader = rank == 0;
   const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m2 * num_n;
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int num_tiles = num_m2 * num_n * ksplit;  // work units: (tile, K slice)
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const PairSched sched0 = make_pair_sched(p.num_k_blocks, pair, num_pairs, num_tiles, C::NMMA == 2);
+  const PairSched sched0 = make_pair_sched(p.num_k_blocks, pair, num_pairs, num_tiles, C::NMMA == 2 && ksplit == 1);
+  // unit -> (tile, first k-block, one-past-last k-block, output row offset of the slice)
+  auto unit_of = [&](int unit, int* tile, int* kb0, int* kb1, int* row_off) {
+    if (ksplit == 1) {
+      *tile = unit, *kb0 = 0, *kb1 = p.num_k_blocks, *row_off = 0;
+    } else {
+      const int sl = unit % ksplit;
+      *tile = unit / ksplit;
+      *kb0 = sl * p.kb_per_split;
+      *kb1 = min(p.num_k_blocks, *kb0 + p.kb_per_split);
+      *row_off = sl * p.M;
+    }
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
     if (p.kb_split < p.num_k_blocks) tma_prefetch_desc(&p.tma_a2);
+    mbar_init(&bars->b_full, 1);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
@@ -130,6 +144,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   }
   tc_fence_before();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
+  __syncthreads();     // (CTA-scope barrier as well: racecheck does not model barrier.cluster as ordering the allocator's
+                       // shared-memory write of the TMEM base address against the reads below)
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
   pdl_wait();
@@ -143,7 +159,9 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       PairSched sched = sched0;
       Seg sg;
       while (sched.next(sg)) {
-        const int tile = sg.tile / 3, part = sg.tile % 3;  // part 0: whole tile; 1 / 2: one N half of a wide tile
+        const int part = sg.tile % 3;  // part 0: whole tile; 1 / 2: one N half of a wide tile
+        int tile, kb0, kb1, row_off;
+        unit_of(sg.tile / 3, &tile, &kb0, &kb1, &row_off);
         const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         const int n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0) + static_cast<int>(rank) * (C::MMA_N / 2);
         const int nmma = part == 0 ? C::NMMA : 1;
@@ -154,7 +172,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           cy0 = (m0 % per_img) / p.conv_W;
           cx0 = m0 % p.conv_W;
         }
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem_tiles + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -204,10 +222,12 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       Seg sg;
       while (sched.next(sg)) {
         const int nmma = sg.tile % 3 == 0 ? C::NMMA : 1;
+        int tile_, kb0, kb1, row_off_;
+        unit_of(sg.tile / 3, &tile_, &kb0, &kb1, &row_off_);
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (!ready) mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           const bool wrap = stage + 1 == p.num_stages;
@@ -217,9 +237,9 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
               if (C::NMMA == 2 && nmma == 2)
-                umma2_f16(tmem_d + C::MMA_N, da + 2 * k, db + SUB_STEP + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma2_f16(tmem_d + C::MMA_N, da + 2 * k, db + SUB_STEP + 2 * k, idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             }
             umma2_commit_mcast(&bars->empty[stage], 0b11);  // frees this smem slot in BOTH CTAs
           }
@@ -244,8 +264,10 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         epilogue_warp_tma_dispatch<BLOCK_N, C::ACC_STRIDE, C::NACC>(
             p, bars, epi_stage, tmem_base, sched0,
             [&](int code, int* row_base, int* n0, int* ncols) {
-              const int tile = code / 3, part = code % 3;
-              *row_base = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+              const int part = code % 3;
+              int tile, kb0, kb1, row_off;
+              unit_of(code / 3, &tile, &kb0, &kb1, &row_off);
+              *row_base = row_off + (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
               *n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0);
               if (part != 0) *ncols = C::MMA_N;
             },

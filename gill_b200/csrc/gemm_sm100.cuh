@@ -65,6 +65,7 @@ struct alignas(64) GemmParams {
   // ahead of time (tma_res). Global memory only ever sees full-line bulk transactions.
   CUtensorMap tma_out;
   CUtensorMap tma_res;
+  CUtensorMap tma_out_lo;  // second store target when out_lo is set (generic staged epilogue, bf16, no residual)
   int epi_tma;
   int epi_variant;    // EV_* specialisation of the staged epilogue
   int epi_warps;      // epilogue warps that take part (multiple of 4, <= GEMM_EPI_WARPS)
@@ -92,6 +93,17 @@ struct alignas(64) GemmParams {
   const float* ln_cs;
   int rowstats_ld, ln_ld, ln_np, ln_C;
   float ln_eps;
+  // split-K of the CTA-pair kernel (ksplit > 1): every 256-row tile is cut into ksplit K slices of kb_per_split k-blocks;
+  // slice s of a tile is an independent work unit that writes its fp32 partial tile to rows [s * M, (s + 1) * M) of the
+  // (fp32) output, which the host points at a scratch buffer; splitk_reduce_kernel adds the slices and applies the real
+  // epilogue. For the UNet's 8x8 / 16x16 convs, whose 16-32 wide tiles cannot fill 74 SM pairs.
+  // B-stationary mode of the 1-CTA kernel (b_resident != 0; plain A, short K, n-inner tile order with the grid a multiple
+  // of the N-tile count so that a CTA keeps ONE N tile): the CTA's whole [BLOCK_N x K] weight tile is loaded once into
+  // shared memory in front of the (A-only) ring; per tile only the 128 x K activation block travels. The 64x64-level
+  // linears (K = 320 / 384) are bound by operand traffic: 180 KB per 128 x 160 x 320 tile without this, 80 KB with it.
+  int b_resident, b_res_bytes;
+  int ksplit, kb_per_split;
+  int M_out;  // rows of the output matrix the epilogue may touch: M, or ksplit * M for a split-K launch
   int debug_mode;  // 0 normal. 1: no TMA after the ring is primed (MMA ceiling). 2: no MMA issue (TMA-fill ceiling). Results invalid.
 };
 
@@ -252,11 +264,23 @@ __device__ __forceinline__ SegIter make_seg_iter(const GemmParams& p, int num_ti
 
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
-                                              int num_m, SegIter it) {
+                                              int num_m, SegIter it, uint8_t* b_res = nullptr, uint64_t* b_full = nullptr) {
   using C = GemmCfg<BLOCK_N>;
   int stage = 0;
   uint32_t phase = 0;
   const int tile_begin = it.tile;
+  const bool bres = p.b_resident != 0;
+  const int stage_bytes = bres ? C::A_BYTES : C::STAGE_BYTES;
+  if (bres) {  // the CTA's single N tile: all K blocks of the weights, once
+    SegIter peek = it;
+    Seg s0;
+    if (peek.next(s0) && elect_one()) {
+      const int n0 = tile_coord(s0.tile, num_m).n_blk * BLOCK_N;
+      mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(p.b_res_bytes));
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) tma_load_2d(b_res + kb * C::B_BYTES, &p.tma_b, b_full, kb * BLOCK_K, n0);
+    }
+    __syncwarp();
+  }
   Seg sg;
   while (it.next(sg)) {
     const int tile = sg.tile;
@@ -275,7 +299,7 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
       // divergent lane the compiler has to wrap every UTMALDG / UTCHMMA in an ELECT + BRA.U.ANY loop and shuttle
       // operands through R2UR, which made the issue loop ~430 cycles per k-block (measured, profiles/).
       mbar_wait(&empty[stage], phase ^ 1);
-      uint8_t* sa = smem_tiles + stage * C::STAGE_BYTES;
+      uint8_t* sa = smem_tiles + stage * stage_bytes;
       uint8_t* sb = sa + C::A_BYTES;
       if (p.debug_mode == 1 && (phase != 0 || tile != tile_begin)) {  // measurement only: reuse stale smem
         if (elect_one()) mbar_arrive(&full[stage]);
@@ -287,7 +311,7 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
         continue;
       }
       if (elect_one()) {
-        mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+        mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(stage_bytes));
         if (kb >= p.kb_split) {
           tma_load_2d(sa, &p.tma_a2, &full[stage], (kb - p.kb_split) * BLOCK_K, m0);
         } else if (p.a_mode == A_CONV3X3) {
@@ -298,7 +322,7 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
         } else {
           tma_load_2d(sa, &p.tma_a, &full[stage], kb * BLOCK_K, m0);
         }
-        tma_load_2d(sb, &p.tma_b, &full[stage], (kb % p.b_kb_wrap) * BLOCK_K, n0);
+        if (!bres) tma_load_2d(sb, &p.tma_b, &full[stage], (kb % p.b_kb_wrap) * BLOCK_K, n0);
       }
       __syncwarp();
       if (++stage == p.num_stages) {
@@ -312,8 +336,9 @@ __device__ __forceinline__ void gemm_producer(const GemmParams& p, uint8_t* smem
 template <int BLOCK_N>
 __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tiles, uint64_t* full, uint64_t* empty,
                                          uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base,
-                                         SegIter it) {
+                                         SegIter it, uint8_t* b_res = nullptr, uint64_t* b_full = nullptr) {
   using C = GemmCfg<BLOCK_N>;
+  const bool bres = p.b_resident != 0;
   const uint32_t idesc = make_idesc_f16(BLOCK_M, BLOCK_N, p.in_dtype == DT_BF16, false);
   // Measured (GILLB200_GEMM_DEBUG=1, no TMA): a k-block took ~300 cycles of issue-side preparation PLUS 3 x N/2
   // cycles -- tcgen05.mma issue blocks while the previous MMA occupies the pipe, so everything between the last MMA of
@@ -323,15 +348,21 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
   const uint32_t s0 = smem_u32(smem_tiles);
   const uint64_t da0 = make_smem_desc_sw128(s0, 16, 1024);
   const uint64_t db0 = make_smem_desc_sw128(s0 + C::A_BYTES, 16, 1024);
-  constexpr uint64_t DESC_STEP = C::STAGE_BYTES >> 4;
+  const uint64_t DESC_STEP = static_cast<uint64_t>(bres ? C::A_BYTES : C::STAGE_BYTES) >> 4;
+  const uint64_t db_res0 = bres ? make_smem_desc_sw128(smem_u32(b_res), 16, 1024) : 0;
   uint64_t da = da0, db = db0;
   int stage = 0;
   uint32_t phase = 0;
   int acc = 0;
   uint32_t acc_phase = 0;
   bool ready = false;  // full[stage] of the current phase already seen complete by the look-ahead probe
+  bool b_ready = !bres;
   Seg sg;
   while (it.next(sg)) {
+    if (!b_ready) {  // (inside the loop: a CTA without tiles never loads, so it must never wait)
+      mbar_wait(b_full, 0);
+      b_ready = true;
+    }
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
@@ -344,10 +375,11 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
       ready = mbar_test_wait(&full[nstage], nphase);
       if (elect_one()) {
         if (p.debug_mode != 2) {
+          const uint64_t dbk = bres ? db_res0 + static_cast<uint64_t>(kb) * (C::B_BYTES >> 4) : db;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, ((kb - sg.kb0) | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_d, da + 2 * k, dbk + 2 * k, idesc, ((kb - sg.kb0) | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty[stage]);  // frees the smem slot when these MMAs retire
@@ -609,7 +641,7 @@ __device__ __forceinline__ uint8_t* epi_unit(uint8_t* buf, int r, int u, bool f3
 
 // v[0..cnt) -> (+ residual already sitting in the buffer) -> buffer, at output column `oc` of the panel
 __device__ __forceinline__ void epi_to_smem(const GemmParams& p, uint8_t* buf, int r, int oc, const float* v, int cnt,
-                                            bool has_res) {
+                                            bool has_res, uint8_t* buf_lo = nullptr) {
   if (p.out_dtype == DT_F32) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -651,6 +683,16 @@ __device__ __forceinline__ void epi_to_smem(const GemmParams& p, uint8_t* buf, i
           o.y = pack_bf16x2(f[2], f[3]);
           o.z = pack_bf16x2(f[4], f[5]);
           o.w = pack_bf16x2(f[6], f[7]);
+          if (buf_lo) {  // bf16 residue of the rounded values: the split-precision operand of the next GEMM
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+            uint32_t lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 h = unpack_bf16x2(ow[j]);
+              lw[j] = pack_bf16x2(f[2 * j] - h.x, f[2 * j + 1] - h.y);
+            }
+            *reinterpret_cast<uint4*>(epi_unit(buf_lo, r, (oc >> 3) + i, false)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
         } else {
           o.x = pack_f16x2(f[0], f[1]);
           o.y = pack_f16x2(f[2], f[3]);
@@ -688,6 +730,7 @@ __device__ __forceinline__ void epi_f16_units(uint8_t* buf, int lane, int u0, fl
 }
 
 struct GemmSmemBars {
+  uint64_t b_full;  // B-stationary mode: the resident weight tile has landed
   uint64_t full[8];
   uint64_t empty[8];
   uint64_t tmem_full[2];
@@ -745,8 +788,8 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
     const uint32_t taddr = tmem_base + acc * ACC_STRIDE + (static_cast<uint32_t>(quad * 32) << 16);
     // panels entirely beyond N (last N tile) or a slab entirely beyond M produce nothing
     int pe = min(pe0, (n_out_total - no0 + EPI_PANEL_COLS - 1) / EPI_PANEL_COLS);
-    if (row0 >= p.M) pe = pb0;
-    const int row = min(row0 + lane, p.M - 1);  // rows >= M are clipped by the TMA store; clamp only for bias reads
+    if (row0 >= p.M_out) pe = pb0;
+    const int row = min(row0 + lane, p.M_out - 1);  // rows >= M are clipped by the TMA store; clamp only for bias reads
     const float* rb_row = nullptr;
     if (VAR == EV_BIAS_ROWBIAS) rb_row = p.rowbias + static_cast<long long>(row / p.rows_per_group) * p.ld_rowbias;
     float ln_rstd = 1.f, ln_rm = 0.f;  // folded LayerNorm of this lane's row: rstd and rstd * mean
@@ -848,6 +891,13 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       const bool last = pnl == pe - 1;
       const int nacc = n0 + pnl * acc_per_panel;  // first accumulator column (global) of this panel
 
+      uint8_t* sbuf_lo = nullptr;
+      if (VAR == EV_GENERIC && p.out_lo != nullptr) {  // hi panel in buffer 0, lo panel in buffer 1, both stored per panel
+        sbuf = stage;
+        sbuf_lo = stage + panel_bytes;
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
       if (VAR == EV_GENERIC) {
         if (has_res) mbar_wait(&res_bar[buf], (par >> buf) & 1);
         const int halves = geglu ? 2 : 1;
@@ -865,7 +915,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[16 * c + j]);
             const int cnt = epi_math16(p, row, n0 + acol + 16 * c, v);
-            epi_to_smem(p, sbuf, lane, geglu ? h * 16 + 8 * c : 16 * c, v, cnt, has_res);
+            epi_to_smem(p, sbuf, lane, geglu ? h * 16 + 8 * c : 16 * c, v, cnt, has_res, sbuf_lo);
           }
         }
       } else if (GEGLU) {
@@ -942,7 +992,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         }
         if (VAR == EV_BIAS_RES) mbar_wait(&res_bar[buf], (par >> buf) & 1);
         epi_f16_units<4, VAR == EV_BIAS_RES>(sbuf, lane, 0, f);
-        if ((VAR == EV_BIAS || VAR == EV_BIAS_RES) && p.rowstats_out != nullptr && row0 + lane < p.M) {
+        if ((VAR == EV_BIAS || VAR == EV_BIAS_RES) && p.rowstats_out != nullptr && row0 + lane < p.M_out) {
           // f[] now holds this row's 32 final values (residual included): partial LayerNorm sums for the next GEMM
           float rs = 0.f, rq = 0.f;
 #pragma unroll
@@ -975,6 +1025,7 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       __syncwarp();
       if (lane == 0) {
         tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
+        if (sbuf_lo) tma_store_2d(&p.tma_out_lo, sbuf_lo, no0 + pnl * EPI_PANEL_COLS, row0);
         tma_store_commit();
       }
       par ^= 1u << buf;
@@ -1032,8 +1083,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   using C = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_tiles = smem;
-  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + p.num_stages * C::STAGE_BYTES);
+  uint8_t* b_res = smem;  // B-stationary mode: [resident weight tile][A ring]; else the ring starts at `smem`
+  uint8_t* smem_tiles = smem + (p.b_resident ? p.b_res_bytes : 0);
+  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem_tiles + p.num_stages * (p.b_resident ? C::A_BYTES : C::STAGE_BYTES));
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
@@ -1045,7 +1097,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
     if (p.kb_split < p.num_k_blocks) tma_prefetch_desc(&p.tma_a2);
-    for (int i = 0; i < C::STAGES; ++i) {
+    mbar_init(&bars->b_full, 1);
+    for (int i = 0; i < 8; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
     }
@@ -1076,9 +1129,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_kernel(const __grid_cons
   const int order = n_inner ? -num_n : num_m;  // see tile_coord()
   const SegIter seg_it = make_seg_iter(p, num_tiles, blockIdx.x, gridDim.x);
   if (warp == 0) {
-    gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, order, seg_it);
+    gemm_producer<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, order, seg_it, b_res, &bars->b_full);
   } else if (warp == 1) {
-    gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base, seg_it);
+    gemm_mma<BLOCK_N>(p, smem_tiles, bars->full, bars->empty, bars->tmem_full, bars->tmem_empty, tmem_base, seg_it, b_res,
+                      &bars->b_full);
   } else if (warp >= 4) {
     if (!p.epi_tma) {
       gemm_epilogue<BLOCK_N>(p, bars->tmem_full, bars->tmem_empty, tmem_base, order, num_tiles);

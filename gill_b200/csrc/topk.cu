@@ -66,6 +66,7 @@ topk_scores_kernel(const __grid_constant__ GemmParams p, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tma_a);
     tma_prefetch_desc(&p.tma_b);
+    mbar_init(&bars->b_full, 1);
     for (int i = 0; i < C::STAGES; ++i) {
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);

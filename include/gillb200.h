@@ -84,7 +84,8 @@ typedef struct gillb200_gemm_args {
    * use (the arrival flags re-arm themselves) and not shared between concurrently running GEMMs. When given, shapes
    * whose tile count fills the SMs badly (the UNet's 8x8 / 16x16 levels) split their K range evenly over all SMs. */
   void* sk_workspace;
-  int stream_k; /* 0 = auto (when sk_workspace is given); 1 = never; 2 = always (if the kernel variant supports it) */
+  int stream_k; /* 0 = auto (when sk_workspace is given); 1 = never; 2 = always (if the kernel variant supports it);
+                 * 3 = split-K over the CTA-pair wide tile + reduce pass (small-M N % 320 == 0 convs; opt-in, see gemm.cu) */
   /* optional: GroupNorm statistics of the output, float [M/32, N, 2] = per 32-row slab and column {sum, sum of squares} of
    * the rounded 16-bit output values (consumed by gillb200_groupnorm_from_stats). Needs a 16-bit output, M % 32 == 0,
    * N % 32 == 0, 16-byte aligned rows and no GEGLU. */

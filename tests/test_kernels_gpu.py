@@ -136,6 +136,41 @@ def test_conv3x3_wide_pair_tile(ops, case):
         assert rel(st[..., 0], g32.sum(2)) < 1e-3 and rel(st[..., 1], (g32 * g32).sum(2)) < 1e-3
 
 
+@pytest.mark.parametrize("case", [(16, 8, 8, 320, 640, "res"), (16, 8, 8, 320, 1280, "rowbias"), (8, 16, 16, 320, 640, "stats"),
+                                  (16, 8, 8, 640, 1280, "stats_res")])
+def test_conv3x3_split_k_pair(ops, case):
+    """Small-M convs (UNet 8x8 / 16x16 levels), stream_k=3: K cut into slices over the wide CTA-pair tile, fp32 partials
+    through the scratch buffer, second pass adds bias / row bias / residual, rounds and leaves the GroupNorm statistics.
+    (Opt-in: measured slower than the default 1-CTA stream-K on B200, see gemm.cu.)"""
+    B, H, W, C, Co, mode = case
+    torch.manual_seed(6)
+    x = torch.randn(B, H, W, C, device=dev).half()
+    w = (torch.randn(Co, C, 3, 3, device=dev) / (3 * C ** 0.5)).half()
+    bias = torch.randn(Co, device=dev)
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    kw = {}
+    if "res" in mode:
+        res = torch.randn(B, H, W, Co, device=dev).half()
+        kw["residual"] = res
+        ref = ref + res.float()
+    if mode == "rowbias":
+        rb = torch.randn(B, Co, device=dev)
+        kw["rowbias"] = rb
+        ref = ref + rb[:, None, None, :]
+    n0 = ops.lib().gillb200_launch_count()
+    got = ops.conv3x3(x, wk, bias=bias, stats="stats" in mode, stream_k=3, **kw)
+    assert ops.lib().gillb200_launch_count() - n0 == 2                      # main launch + split-K reduce
+    assert got.dtype == torch.float16 and rel(got, ref) < 2e-3
+    plain = ops.conv3x3(x, wk, bias=bias, block_n=160, stream_k=1, **kw)
+    assert rel(got, plain) < 1e-3
+    if "stats" in mode:
+        st = got.gn_stats.view(B, H * W // 32, Co, 2)
+        g32 = got.float().view(B, H * W // 32, 32, Co)
+        assert rel(st[..., 0], g32.sum(2)) < 1e-3 and rel(st[..., 1], (g32 * g32).sum(2)) < 1e-3
+    assert torch.equal(ops.conv3x3(x, wk, bias=bias, stream_k=3, **kw), got)   # deterministic (fixed slice order)
+
+
 @pytest.mark.parametrize("case", [(1024, 1280, 5120, 0), (4096, 1280, 1536, 0), (520, 384, 2048, 128), (1024, 10240, 1280, 256)])
 def test_gemm_stream_k(ops, case):
     """stream_k=2 forces the K range of every tile to be shared between CTAs (fp32 partials through the workspace,

@@ -669,7 +669,7 @@ def test_pil_prompts_and_bank_builder_on_device(gill_small, tmp_path):
             pv, _ = oclip.clip_feature_extractor(a)
             _, pooled = oclip.clip_vision_forward(csd, pv[None].bfloat16().float(), cfg)
             rows.append(pooled @ wf.T + bf)
-        expect = retrieval.prepare_bank(torch.cat(rows).numpy(), m.logit_scale.detach().cpu().bfloat16())
+        expect = retrieval.prepare_bank(torch.cat(rows).detach().numpy(), m.logit_scale.detach().cpu().bfloat16())
         assert rel(got.float(), expect.float()) < 2e-2
         # rows are unit vectors times exp(logit_scale)
         assert torch.allclose(got.float().norm(dim=1), torch.full((3,), float(m.logit_scale.detach().bfloat16().exp())), rtol=2e-2)
