@@ -493,8 +493,17 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
     const int esz = a->out_dtype == DT_F32 ? 4 : 2;
     const int n_out = a->act == ACT_GEGLU ? a->N / 2 : a->N;
     bool ok = env_epi != 0 && reinterpret_cast<uintptr_t>(a->out) % 16 == 0 && (a->ldo * esz) % 16 == 0;
-    // bf16 hi + lo outputs (split-precision activations of the GILLMapper FFN): staged too, as two panels per store
-    if (a->out_lo) ok = ok && !a->residual && a->act != ACT_GEGLU && reinterpret_cast<uintptr_t>(a->out_lo) % 16 == 0;
+    // bf16 hi + lo outputs (split-precision activations of the GILLMapper FFN): the staged form exists (two panels per
+    // store) but measured SLOWER than the direct epilogue (M19712 N2048 K512 relu: 266 vs 234 us per launch -- both staging
+    // buffers are busy every panel, so each panel waits for the previous pair of stores); opt-in via GILLB200_EPI_LO=1
+    if (a->out_lo) {
+      static int env_lo = -1;
+      if (env_lo < 0) {
+        const char* e = getenv("GILLB200_EPI_LO");
+        env_lo = e ? atoi(e) : 0;
+      }
+      ok = ok && env_lo && !a->residual && a->act != ACT_GEGLU && reinterpret_cast<uintptr_t>(a->out_lo) % 16 == 0;
+    }
     if (a->residual)
       ok = ok && a->res_dtype == a->out_dtype && reinterpret_cast<uintptr_t>(a->residual) % 16 == 0 &&
            (a->ldr * esz) % 16 == 0;
@@ -597,8 +606,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
   {
     static int env_bres = -1;
     if (env_bres < 0) {
-      const char* e = getenv("GILLB200_BRES");  // "0": off (A/B aid)
-      env_bres = e ? atoi(e) : 1;
+      // OPT-IN ("1"): measured on B200 (profiles/r02_gemm_bres.log) it does not pay -- M65536 N320 K384 +res 49.9 us with the
+      // resident weight tile vs 45.8 without, K320 34.4 vs 33.3: these linears are bound by the activation stream and the
+      // epilogue, the weight tiles were L2 hits all along
+      const char* e = getenv("GILLB200_BRES");
+      env_bres = e ? atoi(e) : 0;
     }
     const int num_m = (a->M + BLOCK_M - 1) / BLOCK_M, num_n = (a->N + bn - 1) / bn;
     if (env_bres && !pair && p.sk_per == 0 && !a->conv3x3 && a->a2_mode == 0 && p.epi_tma && p.num_k_blocks <= 8 && num_n <= 4 &&
