@@ -870,6 +870,355 @@ __global__ void __launch_bounds__(160, 4) attn3_kernel(const __grid_constant__ A
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ================================================================================================================
+// attn4: 48-key tiles, S MMA decoupled from the softmax (hd_cols <= 48: the UNet's 64x64 level, head pitch 48).
+//
+// ncu on attn3 (profiles/r02_ncu_full_attn48.txt): XU pipe 70 %, and the hottest stall of the softmax warps is the wait for
+// S_{j+1}: with P aliased onto the upper half of the S columns, Q.K_{j+1}^T can only be issued AFTER P.V_j, i.e. after the
+// whole softmax of tile j -- every tile pays one MMA round trip (issue + ~200 MMA clocks + commit + wake-up) with the
+// warp idle. TMEM has no room for a separate P at 64 keys (64 S + 32 P + 48 O = 144 > 128 columns at 4 CTAs per SM),
+// but at 48 keys it has: S [0,48) | P [48,72) | O [72,120). So here the softmax warps release S as soon as the scores
+// sit in registers (s_free), the issuer starts Q.K_{j+1}^T at once -- it runs UNDER the exponentials of tile j -- and
+// P.V_j follows when P_j arrives. In steady state a softmax warp never waits for the tensor pipe. K and V tiles are
+// double buffered (6 KB each) and fetched two / one tiles ahead.
+struct Attn4Cfg {
+  static constexpr int BKV = 48;
+  static constexpr int Q_BYTES = 128 * 128;
+  static constexpr int KV_BYTES = BKV * 128;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = Q_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
+  static constexpr int TMEM_S = 0, TMEM_P = 48, TMEM_O = 72, TMEM_COLS = 128;
+  static_assert(4 * (SMEM_BYTES + 1024) <= 228 * 1024, "smem for 4 CTAs per SM");
+  static_assert(KV_BYTES % 1024 == 0, "swizzle atoms");
+};
+struct Attn4Bars {
+  uint64_t q_full, k_full[2], v_full[2], s_full, s_free, p_full, pv_done;
+  uint32_t tmem_ptr;
+};
+
+// max of N raw scores (N = 32 or 16), unmasked: balanced tree of 3-input FMNMX3 (depth 4 at N = 32; a running
+// mx = max3(mx, a, b) chain would be 15 dependent instructions)
+template <int N>
+__device__ __forceinline__ float attn_max_n(const uint32_t* v) {
+  static_assert(N == 32 || N == 16, "chunk width");
+  float t[N / 3 + 1];
+#pragma unroll
+  for (int i = 0; i < N / 3; ++i)
+    t[i] = fmax3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+  if (N == 32) {
+    t[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    return fmax3(fmax3(t[0], t[1], t[2]), fmax3(t[3], t[4], t[5]), fmax3(fmax3(t[6], t[7], t[8]), t[9], t[10]));
+  }
+  return fmax3(fmax3(t[0], t[1], t[2]), fmax3(t[3], t[4], __uint_as_float(v[15])), t[2]);
+}
+template <int N>
+__device__ __forceinline__ float attn_max_n_masked(const uint32_t* v, int c, int lim) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (c + i <= lim) mx = fmaxf(mx, __uint_as_float(v[i]));
+  return mx;
+}
+// p = exp2(s * scale - m) for N columns -> N / 2 packed pairs (see attn_exp32)
+template <int N, bool MASKED, bool SUM, bool BF16>
+__device__ __forceinline__ float attn_exp_n(const uint32_t* v, int c, int lim, float scale_log2, float m, uint32_t* pk) {
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(v[i]), scale_log2, -m));
+    float p1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m));
+    if (MASKED) {
+      p0 = (c + i <= lim) ? p0 : 0.f;
+      p1 = (c + i + 1 <= lim) ? p1 : 0.f;
+    }
+    if (SUM) sum += p0 + p1;
+    pk[i >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+  }
+  return sum;
+}
+
+// 2^x for two lanes on the FMA pipe (no MUFU): round-to-nearest split x = n + f (magic-number add), degree-3 minimax of
+// 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the 4.9e-4 rounding of the 16-bit P), exponent added as an integer.
+// 4 packed fp32 pair instructions + 2 min + 2 integer per pair. x is clamped at -30 (P below 2^-24 rounds to 0 in fp16 and
+// is far below bf16's resolution next to the row maximum).
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+  const f32x2 x = pk2(fmaxf(x0, -30.f), fmaxf(x1, -30.f));
+  const f32x2 t = add2(x, pk2(12582912.f, 12582912.f));
+  const f32x2 n = add2(t, pk2(-12582912.f, -12582912.f));
+  const f32x2 f = fma2(n, pk2(-1.f, -1.f), x);
+  f32x2 q = fma2(pk2(0.05517132208f, 0.05517132208f), f, pk2(0.24261054397f, 0.24261054397f));
+  q = fma2(q, f, pk2(0.69326096773f, 0.69326096773f));
+  q = fma2(q, f, pk2(0.99992811680f, 0.99992811680f));
+  float t0, t1, q0, q1;
+  upk2(t, t0, t1);
+  upk2(q, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+// Interior (unmasked) tiles: packed scale-and-subtract, and every POLY-th pair of exponentials on the FMA pipe instead of
+// the MUFU (POLY = 0: none). The softmax is bound by the 16 ex2 per clock and SM of the XU pipe with issue slots to spare.
+template <int N, bool SUM, bool BF16, int POLY>
+__device__ __forceinline__ float attn_exp_n_fast(const uint32_t* v, float scale_log2, float m, uint32_t* pk, int phase) {
+  const f32x2 sc = pk2(scale_log2, scale_log2), nm = pk2(-m, -m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    float x0, x1, p0, p1;
+    upk2(fma2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc, nm), x0, x1);
+    if (POLY > 0 && ((i >> 1) + phase) % POLY == POLY - 1) {
+      exp2_poly2(x0, x1, p0, p1);
+    } else {
+      p0 = fast_exp2(x0);
+      p1 = fast_exp2(x1);
+    }
+    if (SUM) sum += p0 + p1;
+    pk[i >> 1] = BF16 ? pack_bf16x2(p0, p1) : pack_f16x2(p0, p1);
+  }
+  return sum;
+}
+
+template <int POLY>
+__global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ AttnParams p) {
+  using C = Attn4Cfg;
+  constexpr int BKV = C::BKV;
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Attn4Bars* bars = reinterpret_cast<Attn4Bars*>(smem + C::OFF_BAR);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int kv_len = p.kv_lens ? p.kv_lens[b] : p.Lk;
+  int n_tiles = (kv_len + BKV - 1) / BKV;
+  if (p.causal) {
+    const int last_visible = min(kv_len - 1, q0 + 127 + p.causal_offset);
+    n_tiles = min(n_tiles, last_visible / BKV + 1);
+  }
+  if (n_tiles < 1) n_tiles = 1;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tma_q);
+    tma_prefetch_desc(&p.tma_k);
+    tma_prefetch_desc(&p.tma_v);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->k_full[0], 1);
+    mbar_init(&bars->k_full[1], 1);
+    mbar_init(&bars->v_full[0], 1);
+    mbar_init(&bars->v_full[1], 1);
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->s_free, 4);
+    mbar_init(&bars->p_full, 4);
+    mbar_init(&bars->pv_done, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(&bars->tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+  const int col0 = head * p.hd_cols;
+  const int ksteps = p.hd_cols >> 4;
+  const bool bf16 = p.in_dtype == DT_BF16;
+
+  if (warp == 4) {
+    // ---------------- issuer warp: TMA loads + every tcgen05.mma of the CTA (one lane)
+    if (lane_id() == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, BKV, bf16, false);
+      const uint32_t idesc_o = make_idesc_f16(128, p.hd_cols, bf16, true);  // B = V, MN-major
+      const uint32_t sq = smem_u32(smem + C::OFF_Q), sk = smem_u32(smem + C::OFF_K), sv = smem_u32(smem + C::OFF_V);
+      auto load_k = [&](int j) {
+        mbar_arrive_expect_tx(&bars->k_full[j & 1], C::KV_BYTES);
+        tma_load_3d(smem + C::OFF_K + (j & 1) * C::KV_BYTES, &p.tma_k, &bars->k_full[j & 1], col0, j * BKV, b);
+      };
+      auto load_v = [&](int j) {
+        mbar_arrive_expect_tx(&bars->v_full[j & 1], C::KV_BYTES);
+        tma_load_3d(smem + C::OFF_V + (j & 1) * C::KV_BYTES, &p.tma_v, &bars->v_full[j & 1], col0, j * BKV, b);
+      };
+      auto mma_s = [&](int slot) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          if (k < ksteps)
+            umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + k * 32, 16, 1024),
+                     make_smem_desc_sw128(sk + slot * C::KV_BYTES + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+      };
+      mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
+      tma_load_3d(smem + C::OFF_Q, &p.tma_q, &bars->q_full, col0, q0, b);
+      load_k(0);
+      load_v(0);
+      if (n_tiles > 1) load_k(1);
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->k_full[0], 0);
+      tc_fence_after();
+      mma_s(0);
+      umma_commit(&bars->s_full);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          mbar_wait(&bars->s_free, j & 1);  // S_j sits in the softmax warps' registers (so Q.K_j^T has retired)
+          tc_fence_after();
+          mbar_wait(&bars->k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          mma_s((j + 1) & 1);               // runs under the exponentials of tile j
+          umma_commit(&bars->s_full);
+          if (j + 2 < n_tiles) load_k(j + 2);  // slot j & 1: its reader Q.K_j^T has retired
+          if (j >= 1) mbar_wait(&bars->pv_done, (j - 1) & 1);  // P.V_{j-1} has released V slot (j + 1) & 1
+          load_v(j + 1);
+        }
+        mbar_wait(&bars->p_full, j & 1);  // all four softmax warps have stored P_j
+        mbar_wait(&bars->v_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)
+          umma_f16_ts(tmem_base + C::TMEM_O, tmem_base + C::TMEM_P + k * 8,
+                      make_smem_desc_sw128(sv + (j & 1) * C::KV_BYTES + k * (16 * 128), BKV * 128, 1024), idesc_o,
+                      (j | k) != 0 ? 1u : 0u);
+        umma_commit(&bars->pv_done);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row
+    const int qrow = q0 + tid;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t ts = tmem_base + C::TMEM_S + lane_off;
+    const uint32_t tp = tmem_base + C::TMEM_P + lane_off;
+    const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+    float m_used = 0.f, l = 0.f;
+    const bool use_ones = p.ones_col >= 0;
+    const int causal_lim = p.causal ? qrow + p.causal_offset : 0x7fffffff;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&bars->s_full, j & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[16];
+      tmem_ld_32x32b_x32(ts, s0);
+      tmem_ld_32x32b_x16(ts + 32, s1);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&bars->s_free);
+      const int kv0 = j * BKV;
+      const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
+      const bool no_mask = __all_sync(0xffffffffu, lim >= BKV - 1);
+      float mx = no_mask ? fmaxf(attn_max_n<32>(s0), attn_max_n<16>(s1))
+                         : fmaxf(attn_max_n_masked<32>(s0, 0, lim), attn_max_n_masked<16>(s1, 32, lim));
+      mx *= p.scale_log2;
+      float alpha = 1.f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mx == -INFINITY ? 0.f : mx;
+      } else if (mx > m_used + 8.f) {
+        alpha = fast_exp2(m_used - mx);
+        m_used = mx;
+        need = true;
+      }
+      uint32_t pk[24];
+      float part;
+      if (no_mask) {
+        if (use_ones) {
+          part = bf16 ? attn_exp_n_fast<32, false, true, POLY>(s0, p.scale_log2, m_used, pk, 0) +
+                            attn_exp_n_fast<16, false, true, POLY>(s1, p.scale_log2, m_used, pk + 16, 16)
+                      : attn_exp_n_fast<32, false, false, POLY>(s0, p.scale_log2, m_used, pk, 0) +
+                            attn_exp_n_fast<16, false, false, POLY>(s1, p.scale_log2, m_used, pk + 16, 16);
+        } else {
+          part = bf16 ? attn_exp_n_fast<32, true, true, POLY>(s0, p.scale_log2, m_used, pk, 0) +
+                            attn_exp_n_fast<16, true, true, POLY>(s1, p.scale_log2, m_used, pk + 16, 16)
+                      : attn_exp_n_fast<32, true, false, POLY>(s0, p.scale_log2, m_used, pk, 0) +
+                            attn_exp_n_fast<16, true, false, POLY>(s1, p.scale_log2, m_used, pk + 16, 16);
+        }
+      } else {
+        part = bf16 ? attn_exp_n<32, true, true, true>(s0, 0, lim, p.scale_log2, m_used, pk) +
+                          attn_exp_n<16, true, true, true>(s1, 32, lim, p.scale_log2, m_used, pk + 16)
+                    : attn_exp_n<32, true, true, false>(s0, 0, lim, p.scale_log2, m_used, pk) +
+                          attn_exp_n<16, true, true, false>(s1, 32, lim, p.scale_log2, m_used, pk + 16);
+      }
+      // P.V_{j-1} must have retired before P_j overwrites P_{j-1} and before O is rescaled (long done in steady state)
+      if (j >= 1) {
+        mbar_wait(&bars->pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (__any_sync(0xffffffffu, need)) {
+        l *= alpha;
+#pragma unroll 1
+        for (int c = 0; c < p.hd_cols; c += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(to + c, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32b_x16(to + c, v);
+        }
+      }
+      l += part;
+      {
+        uint32_t pa[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pa[i] = pk[i];
+        tmem_st_32x32b_x16(tp, pa);
+        tmem_st_32x32b_x8(tp + 16, pk + 16);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&bars->p_full);
+    }
+    // ---- epilogue: O / l
+    mbar_wait(&bars->pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    if (use_ones) {
+      l = __uint_as_float(tmem_ld_32x32b_x1(to + p.ones_col));
+      tmem_wait_ld();
+    }
+    const float inv = 1.f / l;
+    uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
+                     static_cast<long long>(qrow) * p.ldo + col0;
+#pragma unroll 1
+    for (int c = 0; c < p.hd_cols; c += 16) {
+      uint32_t v[16];
+      tmem_ld_32x32b_x16(to + c, v);
+      tmem_wait_ld();
+      if (qrow < p.Lq) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+        store16(orow + c, f, 16, p.out_dtype);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int POLY>
+static int launch_attn4_t(const AttnParams& p, cudaStream_t stream) {
+  using C = Attn4Cfg;
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    GB_CUDA(cudaFuncSetAttribute(attn4_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  }
+  dim3 grid((p.Lq + 127) / 128, p.H, p.B);
+  GB_CUDA(launch_pdl(attn4_kernel<POLY>, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_COUNT_LAUNCH(1);
+  return 0;
+}
+static int launch_attn4(const AttnParams& p, cudaStream_t stream) {
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("GILLB200_ATTN_POLY");  // every n-th pair of exponentials on the FMA pipe; 0: all on the MUFU
+    poly = e ? atoi(e) : 3;
+  }
+  if (poly == 2) return launch_attn4_t<2>(p, stream);
+  if (poly == 3) return launch_attn4_t<3>(p, stream);
+  if (poly == 4) return launch_attn4_t<4>(p, stream);
+  if (poly == 6) return launch_attn4_t<6>(p, stream);
+  return launch_attn4_t<0>(p, stream);
+}
+
 static int launch_attn3(const AttnParams& p, cudaStream_t stream) {
   using C = Attn2Cfg<64>;
   static PerDeviceOnce configured;
@@ -935,7 +1284,13 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   // (hd 80 self-attention 120 vs 132 us, its 77-key cross-attention 33.5 vs 43.9 us); the 192-wide tile and the causal
   // bf16 OPT prefill keep the warp-specialised kernel (23.3 vs 26.1 us at 16x16)
   const bool use_attn2 = impl == 2 || (impl != 1 && (a->hd_pad == 64 || (a->hd_pad == 128 && !a->causal)));
-  const int bkv = (!use_attn2 && a->hd_pad == 128) ? 128 : 64;  // K/V TMA box rows = the kernel's KV tile
+  static int attn4 = -1;
+  if (attn4 < 0) {
+    const char* e = getenv("GILLB200_ATTN4");  // "0": 64-key attn3 instead of the 48-key decoupled-S kernel (A/B aid)
+    attn4 = e ? atoi(e) : 1;
+  }
+  const bool use_attn4 = use_attn2 && impl == 0 && attn4 && a->hd_pad == 64 && hd_cols <= 48;
+  const int bkv = use_attn4 ? 48 : (!use_attn2 && a->hd_pad == 128) ? 128 : 64;  // K/V TMA box rows = the kernel's KV tile
   AttnParams p;
   memset(&p, 0, sizeof(p));
   const uint64_t cols = (uint64_t)a->H * hd_cols;  // boxes that reach past the last head are zero filled by TMA
@@ -984,6 +1339,7 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
       const char* e = getenv("GILLB200_ATTN_ISSUER");
       issuer = e ? atoi(e) : 1;
     }
+    if (use_attn4) return launch_attn4(p, stream);
     if (issuer && a->hd_pad == 64) return launch_attn3(p, stream);
     if (ptmem) {
       if (a->hd_pad == 64) return launch_attn2<64, true>(p, stream);

@@ -818,9 +818,12 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
     if (pb0 >= pe) release_fn(acc);
 
     if (sk_partial) {
-      // park this warp's share of the fp32 accumulators: sk_ws[cta][row 0..127][col 0..BLOCK_N), one 128-byte line per
-      // lane and 32-column chunk; then raise this warp's flag (the finisher's warp with the same index consumes it)
-      float* ws = p.sk_ws + (static_cast<size_t>(blockIdx.x) * BLOCK_M + quad * 32 + lane) * BLOCK_N;
+      // park this warp's share of the fp32 accumulators, then raise this warp's flag (the finisher's warp with the same
+      // index consumes it). Scratch layout (private to the two warps, so free to choose): sk_ws[cta][quad][32-column
+      // chunk][float4 i = 0..7][lane] -- every warp store / load is 512 contiguous bytes. (Round 1 used row-major
+      // [row][col]: one 128-byte line PER LANE and instruction = 32 L1 wavefronts per access; the finisher of a tile cut 4
+      // ways read 524 KB that way on the critical path of the launch.)
+      float* ws = p.sk_ws + (static_cast<size_t>(blockIdx.x) * BLOCK_M + quad * 32) * BLOCK_N + lane * 4;
       for (int pnl = pb0; pnl < pe; ++pnl) {
         const int halves = geglu ? 2 : 1;
 #pragma unroll 1
@@ -830,10 +833,10 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           tmem_ld_32x32b_x32(taddr + acol, r);
           tmem_wait_ld();
           if (pnl == pe - 1 && h == halves - 1) release_fn(acc);
-          float4* dst = reinterpret_cast<float4*>(ws + acol);
+          float4* dst = reinterpret_cast<float4*>(ws + acol * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            __stcg(dst + i, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+            __stcg(dst + i * 32, make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
                                         __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
         }
       }
@@ -868,10 +871,10 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
     auto sk_add = [&](uint32_t (&r)[32], int acol) {
       for (int c = sk_first; c <= sk_last; ++c) {
         const float4* src = reinterpret_cast<const float4*>(
-            p.sk_ws + (static_cast<size_t>(c) * BLOCK_M + quad * 32 + lane) * BLOCK_N + acol);
+            p.sk_ws + (static_cast<size_t>(c) * BLOCK_M + quad * 32) * BLOCK_N + acol * 32 + lane * 4);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float4 t = __ldcg(src + i);
+          const float4 t = __ldcg(src + i * 32);
           r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + t.x);
           r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + t.y);
           r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + t.z);

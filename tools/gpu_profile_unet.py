@@ -23,5 +23,5 @@ for k, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
     print(f"  {k:12s} {d['ms']/3:7.3f} ms  {d['launches']//3:4d} launches  " + (f"{d['flops']/d['ms']/1e9:7.1f} TF/s" if d["flops"] else f"{d['bytes']/d['ms']/1e6:7.0f} GB/s"))
 print("top shapes:")
 shp = ops.profile_summary(rec, by_shape=True)
-for k, d in sorted(shp.items(), key=lambda kv: -kv[1]["ms"])[:40]:
+for k, d in sorted(shp.items(), key=lambda kv: -kv[1]["ms"])[:70]:
     print(f"  {d['ms']/3:7.3f} ms  x{d['launches']//3:3d}  {d['ms']/d['launches']*1e3:8.1f} us  " + (f"{d['flops']/d['ms']/1e9:7.1f} TF/s" if d["flops"] else f"{d['bytes']/d['ms']/1e6:7.0f} GB/s") + f"  {k}")
