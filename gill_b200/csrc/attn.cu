@@ -881,18 +881,29 @@ __global__ void __launch_bounds__(160, 4) attn3_kernel(const __grid_constant__ A
 // sit in registers (s_free), the issuer starts Q.K_{j+1}^T at once -- it runs UNDER the exponentials of tile j -- and
 // P.V_j follows when P_j arrives. In steady state a softmax warp never waits for the tensor pipe. K and V tiles are
 // double buffered (6 KB each) and fetched two / one tiles ahead.
+// BKV keys per tile, KCH 64-column chunks of the head (KCH = 1: hd_cols <= 48 at 4 CTAs per SM and 48 keys;
+// KCH = 2: hd_cols <= 96 at 2 CTAs per SM and 64 keys, S [0,64) | P [64,96) | O [96,192) of 256 columns -- the UNet's
+// 32x32 level, head dim 80 at pitch 96).
+template <int BKV_, int KCH_>
 struct Attn4Cfg {
-  static constexpr int BKV = 48;
-  static constexpr int Q_BYTES = 128 * 128;
-  static constexpr int KV_BYTES = BKV * 128;
+  static constexpr int BKV = BKV_, KCH = KCH_;
+  static constexpr int Q_CHUNK = 128 * 128;       // one 64-column chunk of the 128 query rows
+  static constexpr int KV_CHUNK = BKV * 128;      // one 64-column chunk of a K or V tile
+  static constexpr int Q_BYTES = KCH * Q_CHUNK;
+  static constexpr int KV_BYTES = KCH * KV_CHUNK;
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = Q_BYTES;
   static constexpr int OFF_V = OFF_K + 2 * KV_BYTES;
   static constexpr int OFF_BAR = OFF_V + 2 * KV_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 128 + 1024;
-  static constexpr int TMEM_S = 0, TMEM_P = 48, TMEM_O = 72, TMEM_COLS = 128;
-  static_assert(4 * (SMEM_BYTES + 1024) <= 228 * 1024, "smem for 4 CTAs per SM");
-  static_assert(KV_BYTES % 1024 == 0, "swizzle atoms");
+  static constexpr int HD_MAX = KCH == 1 ? 48 : 96;
+  static constexpr int TMEM_S = 0, TMEM_P = BKV, TMEM_O = BKV + BKV / 2;
+  static constexpr int TMEM_COLS = TMEM_O + HD_MAX <= 128 ? 128 : 256;
+  static constexpr int CTAS_PER_SM = 512 / TMEM_COLS;
+  static_assert(TMEM_O + HD_MAX <= TMEM_COLS, "TMEM layout");
+  static_assert(CTAS_PER_SM * (SMEM_BYTES + 1024) <= 228 * 1024, "smem for the intended occupancy");
+  static_assert(KV_CHUNK % 1024 == 0, "swizzle atoms");
+  static_assert(BKV == 48 || BKV == 64, "softmax register tiles are written for 48 / 64 keys");
 };
 struct Attn4Bars {
   uint64_t q_full, k_full[2], v_full[2], s_full, s_free, p_full, pv_done;
@@ -980,10 +991,10 @@ __device__ __forceinline__ float attn_exp_n_fast(const uint32_t* v, float scale_
   return sum;
 }
 
-template <int POLY>
-__global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ AttnParams p) {
-  using C = Attn4Cfg;
-  constexpr int BKV = C::BKV;
+template <int BKV_, int KCH_, int POLY>
+__global__ void __launch_bounds__(160, Attn4Cfg<BKV_, KCH_>::CTAS_PER_SM) attn4_kernel(const __grid_constant__ AttnParams p) {
+  using C = Attn4Cfg<BKV_, KCH_>;
+  constexpr int BKV = C::BKV, KCH = C::KCH;
   pdl_wait();
   pdl_launch();
   extern __shared__ uint8_t smem_raw[];
@@ -1035,21 +1046,30 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
       const uint32_t sq = smem_u32(smem + C::OFF_Q), sk = smem_u32(smem + C::OFF_K), sv = smem_u32(smem + C::OFF_V);
       auto load_k = [&](int j) {
         mbar_arrive_expect_tx(&bars->k_full[j & 1], C::KV_BYTES);
-        tma_load_3d(smem + C::OFF_K + (j & 1) * C::KV_BYTES, &p.tma_k, &bars->k_full[j & 1], col0, j * BKV, b);
+#pragma unroll
+        for (int c = 0; c < KCH; ++c)
+          tma_load_3d(smem + C::OFF_K + (j & 1) * C::KV_BYTES + c * C::KV_CHUNK, &p.tma_k, &bars->k_full[j & 1],
+                      col0 + c * 64, j * BKV, b);
       };
       auto load_v = [&](int j) {
         mbar_arrive_expect_tx(&bars->v_full[j & 1], C::KV_BYTES);
-        tma_load_3d(smem + C::OFF_V + (j & 1) * C::KV_BYTES, &p.tma_v, &bars->v_full[j & 1], col0, j * BKV, b);
+#pragma unroll
+        for (int c = 0; c < KCH; ++c)
+          tma_load_3d(smem + C::OFF_V + (j & 1) * C::KV_BYTES + c * C::KV_CHUNK, &p.tma_v, &bars->v_full[j & 1],
+                      col0 + c * 64, j * BKV, b);
       };
       auto mma_s = [&](int slot) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < 4 * KCH; ++k)
           if (k < ksteps)
-            umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + k * 32, 16, 1024),
-                     make_smem_desc_sw128(sk + slot * C::KV_BYTES + k * 32, 16, 1024), idesc_s, k != 0 ? 1u : 0u);
+            umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + (k >> 2) * C::Q_CHUNK + (k & 3) * 32, 16, 1024),
+                     make_smem_desc_sw128(sk + slot * C::KV_BYTES + (k >> 2) * C::KV_CHUNK + (k & 3) * 32, 16, 1024),
+                     idesc_s, k != 0 ? 1u : 0u);
       };
       mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
-      tma_load_3d(smem + C::OFF_Q, &p.tma_q, &bars->q_full, col0, q0, b);
+#pragma unroll
+      for (int c = 0; c < KCH; ++c)
+        tma_load_3d(smem + C::OFF_Q + c * C::Q_CHUNK, &p.tma_q, &bars->q_full, col0 + c * 64, q0, b);
       load_k(0);
       load_v(0);
       if (n_tiles > 1) load_k(1);
@@ -1076,7 +1096,7 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
           umma_f16_ts(tmem_base + C::TMEM_O, tmem_base + C::TMEM_P + k * 8,
-                      make_smem_desc_sw128(sv + (j & 1) * C::KV_BYTES + k * (16 * 128), BKV * 128, 1024), idesc_o,
+                      make_smem_desc_sw128(sv + (j & 1) * C::KV_BYTES + k * (16 * 128), C::KV_CHUNK, 1024), idesc_o,
                       (j | k) != 0 ? 1u : 0u);
         umma_commit(&bars->pv_done);
       }
@@ -1094,9 +1114,11 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&bars->s_full, j & 1);
       tc_fence_after();
-      uint32_t s0[32], s1[16];
+      constexpr int N1 = BKV - 32;  // second register tile: 16 (48 keys) or 32 (64 keys)
+      uint32_t s0[32], s1[N1];
       tmem_ld_32x32b_x32(ts, s0);
-      tmem_ld_32x32b_x16(ts + 32, s1);
+      if constexpr (N1 == 16) tmem_ld_32x32b_x16(ts + 32, s1);
+      else tmem_ld_32x32b_x32(ts + 32, s1);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -1104,8 +1126,8 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
       const int kv0 = j * BKV;
       const int lim = min(kv_len - 1, causal_lim) - kv0;  // columns > lim are masked
       const bool no_mask = __all_sync(0xffffffffu, lim >= BKV - 1);
-      float mx = no_mask ? fmaxf(attn_max_n<32>(s0), attn_max_n<16>(s1))
-                         : fmaxf(attn_max_n_masked<32>(s0, 0, lim), attn_max_n_masked<16>(s1, 32, lim));
+      float mx = no_mask ? fmaxf(attn_max_n<32>(s0), attn_max_n<N1>(s1))
+                         : fmaxf(attn_max_n_masked<32>(s0, 0, lim), attn_max_n_masked<N1>(s1, 32, lim));
       mx *= p.scale_log2;
       float alpha = 1.f;
       bool need = false;
@@ -1116,25 +1138,25 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
         m_used = mx;
         need = true;
       }
-      uint32_t pk[24];
+      uint32_t pk[BKV / 2];
       float part;
       if (no_mask) {
         if (use_ones) {
           part = bf16 ? attn_exp_n_fast<32, false, true, POLY>(s0, p.scale_log2, m_used, pk, 0) +
-                            attn_exp_n_fast<16, false, true, POLY>(s1, p.scale_log2, m_used, pk + 16, 16)
+                            attn_exp_n_fast<N1, false, true, POLY>(s1, p.scale_log2, m_used, pk + 16, 16)
                       : attn_exp_n_fast<32, false, false, POLY>(s0, p.scale_log2, m_used, pk, 0) +
-                            attn_exp_n_fast<16, false, false, POLY>(s1, p.scale_log2, m_used, pk + 16, 16);
+                            attn_exp_n_fast<N1, false, false, POLY>(s1, p.scale_log2, m_used, pk + 16, 16);
         } else {
           part = bf16 ? attn_exp_n_fast<32, true, true, POLY>(s0, p.scale_log2, m_used, pk, 0) +
-                            attn_exp_n_fast<16, true, true, POLY>(s1, p.scale_log2, m_used, pk + 16, 16)
+                            attn_exp_n_fast<N1, true, true, POLY>(s1, p.scale_log2, m_used, pk + 16, 16)
                       : attn_exp_n_fast<32, true, false, POLY>(s0, p.scale_log2, m_used, pk, 0) +
-                            attn_exp_n_fast<16, true, false, POLY>(s1, p.scale_log2, m_used, pk + 16, 16);
+                            attn_exp_n_fast<N1, true, false, POLY>(s1, p.scale_log2, m_used, pk + 16, 16);
         }
       } else {
         part = bf16 ? attn_exp_n<32, true, true, true>(s0, 0, lim, p.scale_log2, m_used, pk) +
-                          attn_exp_n<16, true, true, true>(s1, 32, lim, p.scale_log2, m_used, pk + 16)
+                          attn_exp_n<N1, true, true, true>(s1, 32, lim, p.scale_log2, m_used, pk + 16)
                     : attn_exp_n<32, true, true, false>(s0, 0, lim, p.scale_log2, m_used, pk) +
-                          attn_exp_n<16, true, true, false>(s1, 32, lim, p.scale_log2, m_used, pk + 16);
+                          attn_exp_n<N1, true, true, false>(s1, 32, lim, p.scale_log2, m_used, pk + 16);
       }
       // P.V_{j-1} must have retired before P_j overwrites P_{j-1} and before O is rescaled (long done in steady state)
       if (j >= 1) {
@@ -1159,7 +1181,14 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
 #pragma unroll
         for (int i = 0; i < 16; ++i) pa[i] = pk[i];
         tmem_st_32x32b_x16(tp, pa);
-        tmem_st_32x32b_x8(tp + 16, pk + 16);
+        if constexpr (BKV == 48) {
+          tmem_st_32x32b_x8(tp + 16, pk + 16);
+        } else {
+          uint32_t pb[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pb[i] = pk[16 + i];
+          tmem_st_32x32b_x16(tp + 16, pb);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -1194,29 +1223,32 @@ __global__ void __launch_bounds__(160, 4) attn4_kernel(const __grid_constant__ A
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int POLY>
+template <int BKV, int KCH, int POLY>
 static int launch_attn4_t(const AttnParams& p, cudaStream_t stream) {
-  using C = Attn4Cfg;
+  using C = Attn4Cfg<BKV, KCH>;
   static PerDeviceOnce configured;
   if (configured.need()) {
-    GB_CUDA(cudaFuncSetAttribute(attn4_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    GB_CUDA(cudaFuncSetAttribute(attn4_kernel<BKV, KCH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  GB_CUDA(launch_pdl(attn4_kernel<POLY>, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl(attn4_kernel<BKV, KCH, POLY>, grid, dim3(160), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }
+template <int BKV, int KCH>
 static int launch_attn4(const AttnParams& p, cudaStream_t stream) {
   static int poly = -1;
   if (poly < 0) {
-    const char* e = getenv("GILLB200_ATTN_POLY");  // every n-th pair of exponentials on the FMA pipe; 0: all on the MUFU
-    poly = e ? atoi(e) : 3;
+    // every n-th pair of exponentials on the FMA pipe; 0: all on the MUFU. Measured (profiles/r02_attn4_poly.log, 16 x 8
+    // heads): 48-key tiles, 4096^2, hd 40: 665 (0) / 618 (6) / 611 (4) / 606 (3) / 646 us (2); 64-key tiles, 1024^2, hd 80
+    // (2 CTAs per SM, bound by the MMA round trips rather than the XU pipe): 88.9 (0) / 91.0 (3) / 90.8 us (4)
+    const char* e = getenv("GILLB200_ATTN_POLY");
+    poly = e ? atoi(e) : (KCH == 1 ? 3 : 0);
   }
-  if (poly == 2) return launch_attn4_t<2>(p, stream);
-  if (poly == 3) return launch_attn4_t<3>(p, stream);
-  if (poly == 4) return launch_attn4_t<4>(p, stream);
-  if (poly == 6) return launch_attn4_t<6>(p, stream);
-  return launch_attn4_t<0>(p, stream);
+  if (poly == 2) return launch_attn4_t<BKV, KCH, 2>(p, stream);
+  if (poly == 3) return launch_attn4_t<BKV, KCH, 3>(p, stream);
+  if (poly == 4) return launch_attn4_t<BKV, KCH, 4>(p, stream);
+  return launch_attn4_t<BKV, KCH, 0>(p, stream);
 }
 
 static int launch_attn3(const AttnParams& p, cudaStream_t stream) {
@@ -1287,9 +1319,11 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
   static int attn4 = -1;
   if (attn4 < 0) {
     const char* e = getenv("GILLB200_ATTN4");  // "0": 64-key attn3 instead of the 48-key decoupled-S kernel (A/B aid)
-    attn4 = e ? atoi(e) : 1;
+    attn4 = e ? atoi(e) : 3;
   }
-  const bool use_attn4 = use_attn2 && impl == 0 && attn4 && a->hd_pad == 64 && hd_cols <= 48;
+  // attn4 bit 0: hd_cols <= 48 (48-key tiles, 4 CTAs per SM); bit 1: hd_cols <= 96 under hd_pad 128 (64-key tiles, 2 CTAs)
+  const bool use_attn4 = use_attn2 && impl == 0 && (attn4 & 1) && a->hd_pad == 64 && hd_cols <= 48;
+  const bool use_attn4w = use_attn2 && impl == 0 && (attn4 & 2) && a->hd_pad == 128 && hd_cols <= 96 && !a->causal;
   const int bkv = use_attn4 ? 48 : (!use_attn2 && a->hd_pad == 128) ? 128 : 64;  // K/V TMA box rows = the kernel's KV tile
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -1339,7 +1373,8 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
       const char* e = getenv("GILLB200_ATTN_ISSUER");
       issuer = e ? atoi(e) : 1;
     }
-    if (use_attn4) return launch_attn4(p, stream);
+    if (use_attn4) return launch_attn4<48, 1>(p, stream);
+    if (use_attn4w) return launch_attn4<64, 2>(p, stream);
     if (issuer && a->hd_pad == 64) return launch_attn3(p, stream);
     if (ptmem) {
       if (a->hd_pad == 64) return launch_attn2<64, true>(p, stream);

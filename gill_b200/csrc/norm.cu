@@ -552,6 +552,100 @@ __global__ void __launch_bounds__(256, 4) gn_apply2_kernel(GnSrc src, int dtype,
   }
 }
 
+// GroupNorm from the producers' statistics in ONE launch, for the UNet's 32x32 / 16x16 / 8x8 levels (HW <= 1024, i.e. at
+// most 32 statistics slabs per sample). A CTA owns (sample, block of CB channels = whole groups and whole 16-byte vectors,
+// pixel range): its prologue reduces the slabs x CB producer sums of ITS groups (one warp per group, fixed order) into
+// scale / shift in shared memory, then it streams its pixels. The two-launch form (gn_finalize_stats_kernel +
+// gn_apply2_kernel) cost 15-23 us per GroupNorm at these levels for 2.6-21 MB tensors -- two dependent launches of latency
+// for a few microseconds of traffic; 49 of the 61 GroupNorms of a UNet evaluation are at these levels.
+template <int UNR>
+__global__ void __launch_bounds__(256, 4) gn_fused_kernel(GnSrc src, const float2* __restrict__ st0,
+                                                          const float2* __restrict__ st1, int dtype, int HW, int G, int CB,
+                                                          int pix_per_cta, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float eps, int silu,
+                                                          void* __restrict__ out, int out_dtype) {
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ float gn_sm[];  // [2 * CB]: scale, shift
+  const int C = src.C0 + src.C1, cpg = C / G, slabs = HW >> 5;
+  const int nblk = C / CB;
+  const int cb = blockIdx.x % nblk, pc = blockIdx.x / nblk, b = blockIdx.y;
+  const int c0 = cb * CB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float cnt = static_cast<float>(cpg) * HW;
+  for (int gl = warp; gl < CB / cpg; gl += 8) {
+    const int cg = c0 + gl * cpg;  // first channel of the group
+    float sm = 0.f, sq = 0.f;
+    const int n = slabs * cpg;
+    for (int i = lane; i < n; i += 32) {
+      const int sl = i / cpg, c = cg + (i - sl * cpg);
+      const float2 v = c < src.C0 ? __ldg(st0 + (static_cast<size_t>(b) * slabs + sl) * src.C0 + c)
+                                  : __ldg(st1 + (static_cast<size_t>(b) * slabs + sl) * src.C1 + (c - src.C0));
+      sm += v.x;
+      sq += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sm += __shfl_xor_sync(0xffffffffu, sm, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean = sm / cnt;
+    const float rstd = rsqrtf(fmaxf(sq / cnt - mean * mean, 0.f) + eps);
+    for (int j = lane; j < cpg; j += 32) {
+      const float a = rstd * w[cg + j];
+      gn_sm[gl * cpg + j] = a;
+      gn_sm[CB + gl * cpg + j] = bias[cg + j] - mean * a;
+    }
+  }
+  __syncthreads();
+  const int nv = CB >> 3;
+  const int p0 = pc * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const int total = (p1 - p0) * nv;
+  const bool bf = dtype == DT_BF16, obf = out_dtype == DT_BF16;
+  const uint16_t* x0 = static_cast<const uint16_t*>(src.x0) + static_cast<long long>(b) * HW * src.C0;
+  const uint16_t* x1 = static_cast<const uint16_t*>(src.x1) + static_cast<long long>(b) * HW * src.C1;
+  uint16_t* o = static_cast<uint16_t*>(out) + static_cast<long long>(b) * HW * C;
+  for (int e = threadIdx.x; e < total; e += 256 * UNR) {
+    uint4 raw[UNR];
+    int vv[UNR], px[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int ee = e + u * 256;
+      raw[u] = make_uint4(0u, 0u, 0u, 0u);
+      px[u] = p0 + ee / nv;
+      vv[u] = ee - (ee / nv) * nv;
+      if (ee < total) {
+        const int c = c0 + vv[u] * 8;
+        const uint16_t* ptr = c < src.C0 ? x0 + static_cast<long long>(px[u]) * src.C0 + c
+                                         : x1 + static_cast<long long>(px[u]) * src.C1 + (c - src.C0);
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(ptr));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (e + u * 256 < total) {
+        const float4 a0 = *reinterpret_cast<const float4*>(gn_sm + vv[u] * 8), a1 = *reinterpret_cast<const float4*>(gn_sm + vv[u] * 8 + 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(gn_sm + CB + vv[u] * 8), d1 = *reinterpret_cast<const float4*>(gn_sm + CB + vv[u] * 8 + 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const uint32_t wd[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        uint32_t r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = bf ? unpack_bf16x2(wd[j]) : unpack_f16x2(wd[j]);
+          float y0 = fmaf(f.x, a[2 * j], d[2 * j]), y1 = fmaf(f.y, a[2 * j + 1], d[2 * j + 1]);
+          if (silu) {
+            y0 = __fdividef(y0, 1.f + __expf(-y0));
+            y1 = __fdividef(y1, 1.f + __expf(-y1));
+          }
+          r[j] = obf ? pack_bf16x2(y0, y1) : pack_f16x2(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(o + static_cast<long long>(px[u]) * C + c0 + vv[u] * 8) = make_uint4(r[0], r[1], r[2], r[3]);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ row softmax
 // out[r, :] = softmax(scale * x[r, :]); one CTA per row; x may be fp32 or 16-bit, out 16-bit. n % 8 == 0.
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const void* __restrict__ x, long long ldx, int in_dtype,
@@ -711,6 +805,38 @@ extern "C" int gillb200_groupnorm_from_stats(const void* x0, int C0, const void*
   GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16, "groupnorm_from_stats: 16-bit activations only");
   GB_CHECK_ARG(B <= 1024, "groupnorm: batch %d > 1024", B);
   GnSrc src{x0, x1, C0, C1};
+  {
+    static int env_fused = -1;
+    if (env_fused < 0) {
+      const char* e = getenv("GILLB200_GN_FUSED");  // "0": always the two-launch form (A/B aid)
+      env_fused = e ? atoi(e) : 1;
+    }
+    // channel block of a CTA: whole groups and whole 16-byte vectors, at least 64 channels when C allows it
+    const int cpg = C / G;
+    int CB = cpg;
+    while (CB % 8) CB += cpg;
+    while (CB < 64 && C % (2 * CB) == 0) CB *= 2;
+    // measured (tools/gpu_small_level.py through CUDA graphs, B = 16, profiles/r02_gn_fused.log): 8x8 C1280 8.6 -> 5.2 us,
+    // 8x8 C2560 9.9 -> 6.7, 16x16 C640 9.3 -> 6.6; from 16x16 C1280 up the flat two-launch form wins (32x32 C640 15.9 vs
+    // 19.5 us: 160-byte channel-block segments stream worse than whole rows), so the fused form is kept for small tensors
+    if (env_fused && static_cast<long long>(HW) * C <= 200000 && HW <= 1024 && out_dtype != DT_F32 && C % CB == 0 &&
+        CB / cpg <= 64) {
+      constexpr int UNR = 4;
+      const int nblk = C / CB;
+      // ~4 CTAs per SM over the whole batch; every CTA at least one full unrolled iteration
+      int pchunks = (4 * num_sms() + B * nblk - 1) / (B * nblk);
+      const int min_pix = (256 * UNR + CB / 8 - 1) / (CB / 8);
+      if (pchunks > (HW + min_pix - 1) / min_pix) pchunks = (HW + min_pix - 1) / min_pix;
+      if (pchunks < 1) pchunks = 1;
+      const int ppc = (HW + pchunks - 1) / pchunks;
+      pchunks = (HW + ppc - 1) / ppc;
+      GB_CUDA(launch_pdl(gn_fused_kernel<UNR>, dim3(nblk * pchunks, B), dim3(256), static_cast<size_t>(2 * CB) * sizeof(float),
+                         stream, src, reinterpret_cast<const float2*>(stats0), reinterpret_cast<const float2*>(stats1), dtype, HW,
+                         G, CB, ppc, w, b, eps, silu, out, out_dtype));
+      GB_COUNT_LAUNCH(1);
+      return 0;
+    }
+  }
   float* partial = reinterpret_cast<float*>(workspace) + 1024;
   float* scale_shift = partial + 128LL * B * G * 2;  // same workspace layout as gillb200_groupnorm
   GB_CUDA(launch_pdl(gn_finalize_stats_kernel, dim3(G, B), dim3(128), 0, stream, reinterpret_cast<const float2*>(stats0), C0,

@@ -225,6 +225,87 @@ __global__ void topk_merge_kernel(const float* __restrict__ cand_val, const long
   }
 }
 
+// Same merge with the candidates held in registers (R * kc <= 32 * MAXC): one global read of the lists instead of K. The
+// looped form above re-read all R * kc candidates in each of the K rounds -- 46 us under ncu for 1024 queries x 36 lists x 16
+// (profiles/r01_ncu_launch_list_summary.csv), a fixed cost that weighed on small bank shards (375 k rows per GPU at N = 8).
+template <int MAXC>
+__global__ void __launch_bounds__(128) topk_merge_reg_kernel(const float* __restrict__ cand_val,
+                                                             const long long* __restrict__ cand_idx, int R,
+                                                             long long q_stride, long long r_stride, long long r_stride_i,
+                                                             int kc, int Q, int K, float* __restrict__ out_val,
+                                                             long long* __restrict__ out_idx) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const int lane = threadIdx.x & 31;
+  const int total = R * kc;
+  constexpr long long EMPTY = 0x7fffffffffffffffLL;
+  float v[MAXC];
+  long long id[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int t = lane + 32 * c;
+    v[c] = -INFINITY;
+    id[c] = EMPTY;
+    if (t < total) {
+      const int r = t / kc, j = t - r * kc;
+      v[c] = cand_val[r * r_stride + q * q_stride + j];
+      id[c] = cand_idx[r * r_stride_i + q * q_stride + j];
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    float bv = -INFINITY;
+    long long bi = EMPTY;
+    int bc = -1;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (v[c] > bv || (v[c] == bv && id[c] < bi)) {
+        bv = v[c];
+        bi = id[c];
+        bc = c;
+      }
+    }
+    float gv = bv;
+    long long gi = bi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, gv, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, gi, o);
+      if (ov > gv || (ov == gv && oi < gi)) {
+        gv = ov;
+        gi = oi;
+      }
+    }
+    if (lane == 0) {
+      out_val[static_cast<long long>(q) * K + k] = gv;
+      out_idx[static_cast<long long>(q) * K + k] = gi;
+    }
+    // retire every copy of the winner (the looped form's "strictly after the previous winner" emits a pair once)
+    if (bc >= 0 && gv == bv && gi == bi) {
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (v[c] == gv && id[c] == gi) {
+          v[c] = -INFINITY;
+          id[c] = EMPTY;
+        }
+    }
+  }
+}
+
+static cudaError_t launch_topk_merge(const float* cand_val, const long long* cand_idx, int R, long long q_stride,
+                                     long long r_stride, long long r_stride_i, int kc, int Q, int K, float* out_val,
+                                     long long* out_idx, cudaStream_t stream) {
+  const int wpb = 4;
+  const dim3 grid((Q + wpb - 1) / wpb), block(wpb * 32);
+  const int total = R * kc;
+  if (total <= 32 * 8)
+    topk_merge_reg_kernel<8><<<grid, block, 0, stream>>>(cand_val, cand_idx, R, q_stride, r_stride, r_stride_i, kc, Q, K, out_val, out_idx);
+  else if (total <= 32 * 24)
+    topk_merge_reg_kernel<24><<<grid, block, 0, stream>>>(cand_val, cand_idx, R, q_stride, r_stride, r_stride_i, kc, Q, K, out_val, out_idx);
+  else
+    topk_merge_kernel<<<grid, block, 0, stream>>>(cand_val, cand_idx, R, q_stride, r_stride, r_stride_i, kc, Q, K, out_val, out_idx);
+  return cudaGetLastError();
+}
+
 
 // ================================================================================================================
 // Small query batches (Q <= 4; the reference's own call shape is Q = 1, K = 3, gill/models.py:676-683).
@@ -553,13 +634,9 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
             : QT == 2 ? launch_topk_stream_q<2>(sp, grid, stream)
                       : launch_topk_stream_q<4>(sp, grid, stream);
     if (r) return r;
-    const int wpb = 4;
-    topk_merge_kernel<<<(Q + wpb - 1) / wpb, wpb * 32, 0, stream>>>(sp.part_val, sp.part_idx, grid, KMAX,
-                                                                   static_cast<long long>(QT) * KMAX,
-                                                                   static_cast<long long>(QT) * KMAX, K, Q, K, out_val,
-                                                                   out_idx);
+    GB_CUDA(launch_topk_merge(sp.part_val, sp.part_idx, grid, KMAX, static_cast<long long>(QT) * KMAX,
+                              static_cast<long long>(QT) * KMAX, K, Q, K, out_val, out_idx, stream));
     GB_COUNT_LAUNCH(1);
-    GB_CUDA(cudaGetLastError());
     return 0;
   }
 
@@ -613,12 +690,9 @@ extern "C" int gillb200_topk_scores(const void* bank, long long n_local, int d, 
   topk_scores_kernel<<<num_m * splits, TOPK_THREADS, C::SMEM_BYTES, stream>>>(p, e);
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
-  const int warps_per_block = 4;
-  topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      e.part_val, e.part_idx, splits * 2, KMAX, static_cast<long long>(e.q_pad) * KMAX,
-      static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx);
+  GB_CUDA(launch_topk_merge(e.part_val, e.part_idx, splits * 2, KMAX, static_cast<long long>(e.q_pad) * KMAX,
+                            static_cast<long long>(e.q_pad) * KMAX, KMAX, Q, K, out_val, out_idx, stream));
   GB_COUNT_LAUNCH(1);
-  GB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -627,12 +701,9 @@ extern "C" int gillb200_topk_merge(const float* cand_val, const long long* cand_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(cand_val && cand_idx && out_val && out_idx, "null pointer");
   GB_CHECK_ARG(R >= 1 && Q >= 1 && K >= 1 && K <= R * Kc, "bad merge shape R=%d Q=%d Kc=%d K=%d", R, Q, Kc, K);
-  const int warps_per_block = 4;
-  topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      cand_val, cand_idx, R, Kc, static_cast<long long>(Q) * Kc, static_cast<long long>(Q) * Kc, Kc, Q, K, out_val,
-      out_idx);
+  GB_CUDA(launch_topk_merge(cand_val, cand_idx, R, Kc, static_cast<long long>(Q) * Kc, static_cast<long long>(Q) * Kc, Kc, Q,
+                            K, out_val, out_idx, stream));
   GB_COUNT_LAUNCH(1);
-  GB_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -643,10 +714,7 @@ extern "C" int gillb200_topk_merge_strided(const float* cand_val, long long r_st
   GB_CHECK_ARG(cand_val && cand_idx && out_val && out_idx, "null pointer");
   GB_CHECK_ARG(R >= 1 && Q >= 1 && K >= 1 && K <= R * Kc && q_stride >= Kc, "bad merge shape R=%d Q=%d Kc=%d K=%d", R, Q,
                Kc, K);
-  const int warps_per_block = 4;
-  topk_merge_kernel<<<(Q + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(
-      cand_val, cand_idx, R, q_stride, r_stride_val, r_stride_idx, Kc, Q, K, out_val, out_idx);
+  GB_CUDA(launch_topk_merge(cand_val, cand_idx, R, q_stride, r_stride_val, r_stride_idx, Kc, Q, K, out_val, out_idx, stream));
   GB_COUNT_LAUNCH(1);
-  GB_CUDA(cudaGetLastError());
   return 0;
 }

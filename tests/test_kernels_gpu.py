@@ -556,7 +556,8 @@ def test_epilogue_groupnorm_statistics(ops):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 64, 320, 0, True), (2, 32, 32, 640, 320, True), (2, 8, 8, 1280, 1280, False),
-                                  (2, 16, 16, 1280, 640, True)])
+                                  (2, 16, 16, 1280, 640, True), (2, 16, 16, 640, 0, True), (3, 8, 8, 1280, 0, True),
+                                  (2, 32, 32, 320, 0, False), (16, 32, 32, 640, 0, True)])
 def test_groupnorm_from_epilogue_statistics_equals_two_pass(ops, case):
     B, H, W, C0, C1, silu = case
     torch.manual_seed(31)

@@ -50,3 +50,15 @@ x = torch.randn(16, 8, 8, 1280, device=dev).half(); w = torch.randn(1280, device
 print(tag, "groupnorm 8x8 C1280 (stats kernel + apply): %.1f us" % timeit(lambda: ops.groupnorm(x, w, bb, 32, 1e-5, silu=True)))
 x2 = torch.randn(1024, 1280, device=dev).half()
 print(tag, "layernorm rows1024 C1280: %.1f us" % timeit(lambda: ops.layernorm(x2, w, bb, 1e-5)))
+
+# GroupNorm(+SiLU) from the producer's statistics at every UNet level (one fused launch for HW <= 1024, else finalize + apply)
+for (HW, C0, C1) in [(8, 1280, 0), (8, 1280, 1280), (16, 1280, 0), (16, 1280, 1280), (16, 640, 0), (32, 640, 0), (32, 640, 640), (32, 320, 0), (64, 320, 0), (64, 320, 320)]:
+    def produce(C):
+        a = torch.randn(16 * HW * HW, 64, device=dev).half(); wt = (torch.randn(C, 64, device=dev) * 0.2).half()
+        o = ops.gemm(a, wt, stats=True); o4 = o.view(16, HW, HW, C); o4.gn_stats = o.gn_stats
+        return o4
+    x0 = produce(C0); x1 = produce(C1) if C1 else None
+    C = C0 + C1
+    w = torch.randn(C, device=dev); bb = torch.randn(C, device=dev); out = torch.empty(16, HW, HW, C, device=dev, dtype=torch.float16)
+    t = timeit(lambda: ops.groupnorm(x0, w, bb, 32, 1e-5, silu=True, x2=x1, out=out))
+    print(f"{tag} groupnorm(from stats) B16 {HW}x{HW} C{C0}+{C1}: {t:6.1f} us  {4.0 * 16 * HW * HW * C / t / 1e3:6.0f} GB/s", flush=True)
