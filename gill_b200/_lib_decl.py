@@ -27,6 +27,7 @@ def declare(L):
     d("gillb200_im2col3x3", vp, ci, ci, ci, ci, ci, vp, cll, vp)
     d("gillb200_plms_step", vp, ci, cf, vp, ci, ci, cf, cf, vp, vp, vp, ci, cll, vp)
     d("gillb200_image_to_u8", vp, ci, cll, ci, ci, vp, vp)
+    d("gillb200_tap_sum3x3", vp, cll, ci, ci, ci, ci, vp, vp, ci, cll, vp)
     d("gillb200_l2norm_rows", vp, cll, ci, ci, vp, cll, ci, vp)
     d("gillb200_cast_add", vp, ci, vp, ci, cll, vp, ci, vp, cll, vp)
     d("gillb200_attn_small_f32", vp, cll, cll, vp, cll, cll, vp, cll, cll, ci, ci, ci, ci, ci, cf, vp, cll, cll, ci, vp, vp)

@@ -422,6 +422,69 @@ extern "C" int gillb200_gather_add_rows(const void* x, const void* table, const 
   return 0;
 }
 
+// out[b,h,w,o] = bias[o] + sum_{tap} y[(b, h + dy - 1, w + dx - 1), tap * COUT + o]   (tap = dy * 3 + dx; zero padding)
+template <int COUT>
+__global__ void __launch_bounds__(256) tap_sum3x3_kernel(const float* __restrict__ y, long long ldy, int B, int H, int W,
+                                                         const float* __restrict__ bias, void* __restrict__ out,
+                                                         int out_dtype, long long ldo) {
+  pdl_wait();
+  pdl_launch();
+  const long long pix = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (pix >= static_cast<long long>(B) * H * W) return;
+  const int w = static_cast<int>(pix % W), h = static_cast<int>((pix / W) % H);
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = bias ? bias[o] : 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int hh = h + dy - 1;
+    if (hh < 0 || hh >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ww = w + dx - 1;
+      if (ww < 0 || ww >= W) continue;
+      const float* src = y + (pix + (dy - 1) * W + (dx - 1)) * ldy + (dy * 3 + dx) * COUT;
+      if (COUT == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src));
+        acc[0] += t.x;
+        acc[1 % COUT] += t.y;
+        acc[2 % COUT] += t.z;
+        acc[3 % COUT] += t.w;
+      } else {
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += __ldg(src + o);
+      }
+    }
+  }
+  if (out_dtype == DT_F32) {
+    float* o = static_cast<float*>(out) + pix * ldo;
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) o[i] = acc[i];
+  } else {
+    uint16_t* o = static_cast<uint16_t*>(out) + pix * ldo;
+#pragma unroll
+    for (int i = 0; i < COUT; ++i)
+      o[i] = out_dtype == DT_BF16 ? __bfloat16_as_ushort(__float2bfloat16_rn(acc[i])) : __half_as_ushort(__float2half_rn(acc[i]));
+  }
+}
+
+extern "C" int gillb200_tap_sum3x3(const float* y, long long ldy, int B, int H, int W, int Cout, const float* bias, void* out,
+                                   int out_dtype, long long ldo, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GB_CHECK_ARG(y && out && B > 0 && H > 0 && W > 0, "tap_sum3x3: bad args");
+  GB_CHECK_ARG(Cout == 3 || Cout == 4 || Cout == 8, "tap_sum3x3: Cout must be 3, 4 or 8 (got %d)", Cout);
+  GB_CHECK_ARG(ldy >= 9 * Cout && ldo >= Cout, "tap_sum3x3: ldy=%lld ldo=%lld too small for Cout=%d", ldy, ldo, Cout);
+  GB_CHECK_ARG(Cout != 4 || (ldy % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0), "tap_sum3x3: Cout 4 needs 16-byte rows");
+  const long long n = static_cast<long long>(B) * H * W;
+  const dim3 grid(static_cast<unsigned>((n + 255) / 256));
+  if (Cout == 3) GB_CUDA(launch_pdl(tap_sum3x3_kernel<3>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
+  else if (Cout == 4) GB_CUDA(launch_pdl(tap_sum3x3_kernel<4>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
+  else GB_CUDA(launch_pdl(tap_sum3x3_kernel<8>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
+  GB_COUNT_LAUNCH(1);
+  GB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int gillb200_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && C % 8 == 0, "upsample2x: bad args");

@@ -481,6 +481,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(GnSrc src, int dtype, int
   }
 }
 
+// y = x * a + d for a pair of channels, then SiLU, in packed fp32 (FFMA2 / FMUL2 / FADD2: the elementwise pass is bound by
+// issue slots -- ncu r02: 62 % issue-active, XU 52 %, DRAM 22 % -- so halving the fp32 instruction count is what pays).
+// Same rounded fp32 operations per lane as the scalar form: bit-identical results.
+__device__ __forceinline__ uint32_t gn_affine_silu2(float2 f, float a0, float a1, float d0, float d1, bool silu, bool obf) {
+  f32x2 y = fma2(pk2(f.x, f.y), pk2(a0, a1), pk2(d0, d1));
+  float y0, y1;
+  if (silu) {
+    float z0, z1;
+    upk2(mul2(y, pk2(-1.4426950408889634f, -1.4426950408889634f)), z0, z1);
+    float e0, e1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+    float s0, s1;
+    upk2(add2(pk2(e0, e1), pk2(1.f, 1.f)), s0, s1);
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(s1));
+    upk2(mul2(y, pk2(r0, r1)), y0, y1);
+  } else {
+    upk2(y, y0, y1);
+  }
+  return obf ? pack_bf16x2(y0, y1) : pack_f16x2(y0, y1);
+}
+
 // Flat elementwise normalise (+SiLU) for 16-bit activations: a CTA's slice of one sample is a contiguous run of 16-byte
 // vectors, thread t takes vectors t, t + 256, ... (every warp load/store is 512 contiguous bytes, no idle lanes for any
 // channel count) with UNR independent loads in flight; the per-channel scale / shift of the sample live in shared
@@ -539,12 +563,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply2_kernel(GnSrc src, int dtype,
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = bf ? unpack_bf16x2(w[j]) : unpack_f16x2(w[j]);
-          float y0 = fmaf(f.x, a[2 * j], d[2 * j]), y1 = fmaf(f.y, a[2 * j + 1], d[2 * j + 1]);
-          if (silu) {
-            y0 = __fdividef(y0, 1.f + __expf(-y0));
-            y1 = __fdividef(y1, 1.f + __expf(-y1));
-          }
-          r[j] = obf ? pack_bf16x2(y0, y1) : pack_f16x2(y0, y1);
+          r[j] = gn_affine_silu2(f, a[2 * j], a[2 * j + 1], d[2 * j], d[2 * j + 1], silu != 0, obf);
         }
         *reinterpret_cast<uint4*>(o + (e + u * 256) * 8) = make_uint4(r[0], r[1], r[2], r[3]);
       }
@@ -633,12 +652,7 @@ __global__ void __launch_bounds__(256, 4) gn_fused_kernel(GnSrc src, const float
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = bf ? unpack_bf16x2(wd[j]) : unpack_f16x2(wd[j]);
-          float y0 = fmaf(f.x, a[2 * j], d[2 * j]), y1 = fmaf(f.y, a[2 * j + 1], d[2 * j + 1]);
-          if (silu) {
-            y0 = __fdividef(y0, 1.f + __expf(-y0));
-            y1 = __fdividef(y1, 1.f + __expf(-y1));
-          }
-          r[j] = obf ? pack_bf16x2(y0, y1) : pack_f16x2(y0, y1);
+          r[j] = gn_affine_silu2(f, a[2 * j], a[2 * j + 1], d[2 * j], d[2 * j + 1], silu != 0, obf);
         }
         *reinterpret_cast<uint4*>(o + static_cast<long long>(px[u]) * C + c0 + vv[u] * 8) = make_uint4(r[0], r[1], r[2], r[3]);
       }
@@ -734,10 +748,27 @@ static int launch_gn_apply(const GnSrc& src, int dtype, int B, int HW, const flo
   if (impl == 2 && dtype != DT_F32 && out_dtype != DT_F32 && C / 8 <= 256 * 8) {
     constexpr int UNR = 8;
     const long long total = static_cast<long long>(HW) * (C / 8);
-    // ~8 CTAs per SM over the whole batch (two waves at 4 resident CTAs), never less than one full iteration per CTA
-    long long per = (total * B + 8LL * num_sms() - 1) / (8LL * num_sms());
-    const long long unit = 256LL * UNR;
-    per = (per + unit - 1) / unit * unit;
+    // ONE wave: at most 4 resident CTAs per SM over the whole batch, equal slices. (Round 1 aimed at 8 CTAs per SM and
+    // rounded the slice up to whole unrolled iterations: 64x64 C320 at B = 16 became 640 CTAs on 592 slots -- a second
+    // wave of 48 CTAs doubled the kernel's time.) The unrolled loop predicates its tail, so a slice is any multiple of
+    // 256 vectors; never less than one full unrolled iteration per CTA.
+    static int env_wave = -1;
+    if (env_wave < 0) {
+      const char* e = getenv("GILLB200_GN_ONEWAVE");  // "0": round-1 sizing (A/B aid)
+      env_wave = e ? atoi(e) : 1;
+    }
+    long long per;
+    if (env_wave) {
+      int bps = 4 * num_sms() / B;  // CTAs per sample
+      if (bps < 1) bps = 1;
+      per = (total + bps - 1) / bps;
+      per = (per + 255) / 256 * 256;
+      if (per < 256LL * UNR) per = 256LL * UNR;
+    } else {
+      per = (total * B + 8LL * num_sms() - 1) / (8LL * num_sms());
+      const long long unit = 256LL * UNR;
+      per = (per + unit - 1) / unit * unit;
+    }
     const int blocks = static_cast<int>((total + per - 1) / per);
     GB_CUDA(launch_pdl(gn_apply2_kernel<UNR>, dim3(blocks, B), dim3(256), static_cast<size_t>(2 * C) * sizeof(float), stream,
                        src, dtype, HW, scale_shift, silu, out, out_dtype, per));

@@ -461,6 +461,32 @@ def gather_add_rows(table: torch.Tensor, idx: torch.Tensor, x: Optional[torch.Te
     return out
 
 
+def conv3x3_taps_weight(w: torch.Tensor, cout: int, pad_to: int = 16) -> torch.Tensor:
+    """[Cout(+pad), 9*C] conv weight (k = tap*C + c) -> per-tap GEMM weight [9*cout (padded to a multiple of pad_to), C] with
+    row tap*cout + o = W[o, tap*C : (tap+1)*C] (see conv3x3_narrow)."""
+    C = w.shape[1] // 9
+    wt = w[:cout].reshape(cout, 9, C).permute(1, 0, 2).reshape(9 * cout, C)
+    rows = (9 * cout + pad_to - 1) // pad_to * pad_to
+    out = torch.zeros((rows, C), dtype=w.dtype, device=w.device)
+    out[: 9 * cout] = wt
+    return out.contiguous()
+
+
+def conv3x3_narrow(x: torch.Tensor, w_taps: torch.Tensor, cout: int, bias: Optional[torch.Tensor] = None,
+                   out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """3x3 / pad 1 convolution with very few output channels (UNet conv_out 320 -> 4, VAE conv_out 128 -> 3) as ONE plain
+    GEMM [B*H*W, C] x [C, 9*cout] (fp32 per-tap products; the activation is read once, not nine shifted times through a
+    32-column tile that is 7/8 padding) + a nine-tap shifted sum. x NHWC [B,H,W,C] 16-bit -> NHWC [B,H,W,cout]."""
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and w_taps.shape[1] == C and w_taps.shape[0] >= 9 * cout
+    y = gemm(x.view(B * H * W, C), w_taps, out_dtype=torch.float32)
+    out = torch.empty((B, H, W, cout), device=x.device, dtype=out_dtype or x.dtype)
+    with _P("tap_sum3x3", 0.0, 4.0 * y.numel() + out.element_size() * out.numel(), f"B{B} {H}x{W} Cout{cout}"):
+        check(lib().gillb200_tap_sum3x3(y.data_ptr(), y.stride(0), B, H, W, cout, _ptr(bias), out.data_ptr(), _DT[out.dtype],
+                                        cout, _stream()), "gillb200_tap_sum3x3")
+    return out
+
+
 def upsample2x(x: torch.Tensor) -> torch.Tensor:
     B, H, W, C = x.shape
     assert x.is_contiguous()

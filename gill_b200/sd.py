@@ -26,6 +26,9 @@ import torch
 from . import ops
 
 SD = Dict[str, torch.Tensor]
+# conv_out (320 -> 4 in the UNet, 128 -> 3 in the VAE) as a plain GEMM onto per-tap products + shifted sum; "0": the implicit
+# 3x3 conv through a 32-column tile (A/B aid)
+NARROW_CONV_OUT = os.environ.get("GILLB200_NARROW_CONV_OUT", "1") != "0"
 
 UNET_CFG = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
                 cross_attention_dim=768, heads=8, norm_groups=32, has_attn_down=(True, True, True, False),
@@ -242,6 +245,8 @@ class UNetB200:
         self._put("conv_norm_out.bias", sd["conv_norm_out.bias"], f32)
         self._put("conv_out.weight", _conv_w(sd["conv_out.weight"], self.dt))
         self._put("conv_out.bias", sd["conv_out.bias"], f32)
+        # conv_out (C -> 4) as one plain GEMM onto the 36 per-tap products + a shifted sum (ops.conv3x3_narrow)
+        self._put("conv_out.taps", ops.conv3x3_taps_weight(_conv_w(sd["conv_out.weight"], self.dt), sd["conv_out.weight"].shape[0]))
         # all resnet time projections as one [sum_c, 1280] matrix
         ws, bs, off = [], [], 0
         for p in self._temb_names:
@@ -438,6 +443,8 @@ class UNetB200:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
                 h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=True)
         n = ops.groupnorm(h, w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.G, 1e-5, silu=True)
+        if NARROW_CONV_OUT:
+            return ops.conv3x3_narrow(n, w["conv_out.taps"], w["conv_out.bias"].numel(), bias=w["conv_out.bias"])
         return ops.conv3x3(n, w["conv_out.weight"], bias=w["conv_out.bias"], block_n=32)
 
 
@@ -473,6 +480,8 @@ class VAEDecoderB200:
         wp = torch.zeros((8, w.shape[1]), dtype=w.dtype, device=self.dev)
         wp[: w.shape[0]] = w
         self.w["decoder.conv_out.weight"] = wp
+        self.w["decoder.conv_out.taps"] = ops.conv3x3_taps_weight(w, self.cfg["out_channels"])
+        self.w["decoder.conv_out.bias3"] = self.w["decoder.conv_out.bias"].clone()
         b = torch.zeros(8, dtype=f32, device=self.dev)
         b[: self.cfg["out_channels"]] = self.w["decoder.conv_out.bias"]
         self.w["decoder.conv_out.bias"] = b
@@ -533,7 +542,10 @@ class VAEDecoderB200:
                 h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=True)
         n = ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], self.G, 1e-6,
                           silu=True)
-        img = ops.conv3x3(n, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"], block_n=32)
+        if NARROW_CONV_OUT:
+            img = ops.conv3x3_narrow(n, w["decoder.conv_out.taps"], cfg["out_channels"], bias=w["decoder.conv_out.bias3"])
+        else:
+            img = ops.conv3x3(n, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"], block_n=32)
         return ops.image_to_u8(img, cfg["out_channels"])
 
 

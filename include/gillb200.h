@@ -202,6 +202,11 @@ int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype, float scal
  *   l2norm_rows     : x / ||x|| (gill/models.py:674)
  *   cast_add        : out = cast(x + y[i % y_period]) with optional bf16 residue (gill/layers.py:32 `x + input_embs`)
  *   attn_small_f32  : fp32 attention for the GILLMapper's short sequences (nn.MultiheadAttention, layers.py:43)
+ *   tap_sum3x3      : second half of a 3x3 convolution with very few output channels (UNet conv_out 320 -> 4,
+ *                     gill/custom_sd.py:633 `self.unet(...)`'s last layer; VAE conv_out 128 -> 3, custom_sd.py:387):
+ *                     y[pixel, tap * Cout + o] holds the per-tap products W_tap x (one plain GEMM that reads the
+ *                     activation ONCE instead of nine shifted times), out[b,h,w,o] = bias[o] + sum over the nine taps of
+ *                     y at the tap's neighbour pixel (zero outside the image)
  * ------------------------------------------------------------------------------------------------------------- */
 int gillb200_gather_add_rows(const void* x, const void* table, const long long* idx, long long idx_offset,
                              long long rows, int D, int dtype, void* out, void* stream);
@@ -211,6 +216,8 @@ int gillb200_plms_step(const void* eps_pair, int eps_dtype, float guidance, floa
                        float c_sample, float c_eps, float* latents, float* cur_sample, void* lat16_pair, int lat16_dtype,
                        long long n, void* stream);
 int gillb200_image_to_u8(const void* x, int dtype, long long pixels, int ldx, int channels, void* out, void* stream);
+int gillb200_tap_sum3x3(const float* y, long long ldy, int B, int H, int W, int Cout, const float* bias, void* out,
+                        int out_dtype, long long ldo, void* stream);
 /* CLIP pre-processing of generated images for the re-rank step (gill/models.py:733-737 `img.resize((224,224))` + the HF
  * feature extractor, gill/utils.py:117-119): uint8 NHWC [B,H,W,3] -> PIL-exact bicubic resize to S x S (8-bit two-pass
  * fixed-point ImagingResample) -> /255 -> (x - mean)/std -> NCHW [B,3,S,S] in out_dtype. mean3 / std3 are HOST pointers.

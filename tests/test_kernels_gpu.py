@@ -612,3 +612,18 @@ def test_layernorm_folded_into_the_consuming_gemm(ops, C, N, geglu):
     n = ops.layernorm(x, gam, bet, 1e-5)
     two = ops.gemm(n, W, bias=b, act="geglu" if geglu else None)
     assert rel(out, two) < 3e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,cout", [(2, 64, 64, 320, 4), (1, 32, 48, 128, 3), (2, 8, 8, 64, 4)])
+def test_conv3x3_narrow_equals_conv2d(ops, B, H, W, C, cout):
+    """conv_out as one plain GEMM onto per-tap products + nine-tap shifted sum == F.conv2d(padding=1)."""
+    torch.manual_seed(77)
+    x = torch.randn(B, H, W, C, device=dev).half()
+    w4 = (torch.randn(cout, C, 3, 3, device=dev) * 0.05).half()
+    bias = torch.randn(cout, device=dev)
+    wk = w4.permute(0, 2, 3, 1).reshape(cout, 9 * C).contiguous()        # k = (ky*3+kx)*C + c, as sd._conv_w lays it out
+    got = ops.conv3x3_narrow(x, ops.conv3x3_taps_weight(wk, cout), cout, bias=bias)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w4.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert got.shape == ref.shape and got.dtype == torch.float16
+    assert rel(got, ref) < 1e-3
+    assert (got.float() - ref).abs().max() < 2e-2
