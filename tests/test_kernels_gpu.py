@@ -446,6 +446,30 @@ def test_fused_attention_growing_max(ops, hd, hp, dt):
     assert torch.isfinite(got.float()).all() and rel(got, ref) < (1e-2 if dt == torch.bfloat16 else 3e-3)
 
 
+@pytest.mark.parametrize("hd,pt,tile,dt", [(40, 48, 64, torch.float16), (80, 96, 128, torch.float16), (32, 48, 64, torch.bfloat16)])
+def test_attn4_growing_max_kv_lens_and_ragged_tiles(ops, hd, pt, tile, dt):
+    """The decoupled-S kernels (48-key tiles at pitch 48, 64-key tiles at pitch 96): rescale path (row max rising far beyond
+    2^8 along the keys), per-sample key counts that end inside a tile, Lq not a multiple of 128."""
+    torch.manual_seed(14)
+    B, H, Lq, Lk = 3, 4, 333, 500
+    buf = torch.zeros(B, Lk, 3, H, pt, device=dev)
+    x = torch.randn(B, Lk, 3, H, hd, device=dev)
+    x[:, :, 1] *= torch.linspace(0.05, 12.0, Lk, device=dev).view(1, Lk, 1, 1)      # key norms grow along the sequence
+    buf[..., :hd] = x
+    use_ones = dt == torch.float16
+    if use_ones:
+        buf[:, :, 2, :, hd] = 1.0
+    buf = buf.view(B, Lk, 3 * H * pt).to(dt)
+    q, k, v = buf[:, :Lq, : H * pt], buf[:, :, H * pt: 2 * H * pt], buf[:, :, 2 * H * pt:]
+    kvl = torch.tensor([500, 49, 257], device=dev, dtype=torch.int32)
+    got = ops.attention(q, k, v, H, tile, hd ** -0.5, ones_col=hd if use_ones else 0, head_stride=pt, kv_lens=kvl)
+    ref = attn_ref(q, k, v, H, pt, hd ** -0.5, kv_lens=kvl)
+    tol = 1e-2 if dt == torch.bfloat16 else 3e-3
+    assert torch.isfinite(got.float()).all() and rel(got, ref) < tol
+    got2 = ops.attention(q, k, v, H, tile, hd ** -0.5, ones_col=hd if use_ones else 0, head_stride=pt)
+    assert rel(got2, attn_ref(q, k, v, H, pt, hd ** -0.5)) < tol
+
+
 def test_fused_attention_kv_lens_and_views(ops):
     torch.manual_seed(11)
     B, H, L, hp = 3, 4, 200, 128
