@@ -142,20 +142,21 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-template <int BN>
+template <int BN, bool HALO = false>
 static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   static PerDeviceOnce configured;
   if (configured.need()) {
-    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
   }
-  const int smem_bytes = plan_smem(p, C::STAGE_BYTES, C::STAGES);
+  // halo mode: two resident halo-tile slots in front of a ring of B half-tiles (8 stages at most: the barrier block)
+  const int smem_bytes = HALO ? plan_smem(p, C::B_BYTES, 8, C::HALO_RES) : plan_smem(p, C::STAGE_BYTES, C::STAGES);
   GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (pair, BN=%d)", BN);
   const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles = num_m2 * num_n;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  GB_CUDA(launch_pdl(gemm2_kernel<BN>, dim3(2 * pairs), dim3(GEMM_THREADS), smem_bytes, stream, p));  // cluster (2,1,1)
+  GB_CUDA(launch_pdl(gemm2_kernel<BN, HALO>, dim3(2 * pairs), dim3(GEMM_THREADS), smem_bytes, stream, p));  // cluster (2,1,1)
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -219,6 +220,15 @@ static int wide_min_kb() {
     // every N % 320 == 0 linear with enough tiles (M4096 N1280 K5120 61.7 -> 45.3 us, K2560 35.8 -> 28.3, K1280 24.3 -> 20.8,
     // M65536 N320 K1280 68.0 -> 65.0); at K <= 768 the un-overlapped epilogue costs more than the fill it saves
     v = e ? atoi(e) : 15;
+  }
+  return v;
+}
+
+static int conv_halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GILLB200_CONV_HALO");  // "0": one TMA box per tap (round-1 form; A/B aid)
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
@@ -389,7 +399,10 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
     // (K >= 640: M16384 N5120 121 -> 115 us, M4096 N10240 97 -> 91 us) and loses on the K = 320 linears of the 64x64
     // level, whose time is all epilogue (152 vs 170 us)
     const long long tiles2 = 1LL * ((a->M + 255) / 256) * ((a->N + bn - 1) / bn);
-    pair = tiles2 >= (num_sms() / 2) * 3 / 4 && p.num_k_blocks >= (bn == 256 ? 10 : 32);
+    // (3x3 convs that qualify for the halo-tile A path take the pair kernel at any depth: VAE 512x512 C128->128, 18 k-blocks)
+    const bool halo_ok = a->conv3x3 && conv_halo_enabled() && p.conv_stride == 1 && a->conv_W % 16 == 0 && a->conv_H % 16 == 0 &&
+                         a->M % 256 == 0 && a->a2_mode == 0 && bn >= 128;
+    pair = tiles2 >= (num_sms() / 2) * 3 / 4 && (p.num_k_blocks >= (bn == 256 ? 10 : 32) || halo_ok);
   }
   // Wide pair tile (256 x 320, two N = 160 MMAs per K-step, see Gemm2Cfg) for N % 320 == 0. Measured on B200
   // (tools/gpu_conv_bench.py, profiles/r02_conv_wide.log, B = 16): 64x64 C320->320 142 -> 110 us, 32x32 C640->640 134 -> 107,
@@ -409,6 +422,13 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       bn = 320;
       pair = true;
       want_sk = false;
+      // With the halo-tile A path (below) the narrow 256 x 160 pair tile no longer pays for re-fetching A per N tile, keeps
+      // two accumulator stages (epilogue under the next tile's MMAs) and quantises better (64x64 C320->320: 512 tiles on 74
+      // pairs instead of 256). Measured (profiles/r02_conv_halo.log): C320->320 104.9 -> 93.7 us, 64x64 C640->320 177.1 ->
+      // 173.0, 32x32 C640->640 92.3 -> 89.5, C320->640 56.5 -> 52.4; from C = 960 up the wide tile wins or ties.
+      if (a->block_n == 0 && a->conv3x3 && a->conv_C <= 640 && conv_halo_enabled() && p.conv_stride == 1 && a->conv_W % 16 == 0 &&
+          a->conv_H % 16 == 0 && a->M % 256 == 0)
+        bn = 160;
     }
     // Too few wide tiles for the 74 SM pairs (8x8 level: 16, 16x16 C640: 32): cut K into slices so that tiles x slices
     // fills them, fp32 partials through the scratch buffer, second pass = splitk_reduce_kernel. OPT-IN (stream_k = 3 or
@@ -630,6 +650,45 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
                        reinterpret_cast<float2*>(o->stats_out)));
     GB_COUNT_LAUNCH(1);
     return 0;
+  }
+  // ---- halo-tile implicit conv (A_CONV3X3_HALO, see gemm_sm100.cuh): stride-1 3x3 convs on the CTA-pair kernel with the
+  // staged epilogue, W and H multiples of 16 (an M tile = a 16 x 8 pixel block). One halo tile per 64-channel block feeds
+  // all nine taps, so the A traffic of a CTA drops 9 x 16 KB -> 23 KB per channel block.
+  {
+    const int env_halo = conv_halo_enabled();
+    if (env_halo && pair && a->conv3x3 && p.conv_stride == 1 && p.epi_tma && p.ksplit <= 1 && a->a2_mode == 0 &&
+        a->conv_W % 16 == 0 && a->conv_H % 16 == 0 && !a->out_lo && (bn == 128 || bn == 160 || bn == 256 || bn == 320) &&
+        a->ldo == (a->act == ACT_GEGLU ? a->N / 2 : a->N) && (!a->residual || a->ldr == a->ldo) && a->M % 256 == 0) {
+      const int esz = a->out_dtype == DT_F32 ? 4 : 2;
+      const int n_out = a->act == ACT_GEGLU ? a->N / 2 : a->N;
+      {
+        const uint64_t dims[4] = {(uint64_t)a->conv_C, (uint64_t)a->conv_W, (uint64_t)a->conv_H, (uint64_t)a->conv_B};
+        const uint64_t strides[3] = {(uint64_t)a->conv_C * 2, (uint64_t)a->conv_W * a->conv_C * 2,
+                                     (uint64_t)a->conv_H * a->conv_W * a->conv_C * 2};
+        const uint32_t box[4] = {64, 10, 18, 1};
+        int r = encode_tmap(&p.tma_a, a->a, bf16 ? DT_BF16 : DT_F16, 4, dims, strides, box, 128, nullptr);
+        if (r) return r;
+      }
+      {
+        const uint64_t dims[3] = {(uint64_t)n_out, (uint64_t)a->conv_W, (uint64_t)a->conv_B * a->conv_H};
+        const uint32_t box[3] = {EPI_PANEL_COLS, 8, 4};
+        const uint64_t so[2] = {(uint64_t)a->ldo * esz, (uint64_t)a->conv_W * a->ldo * esz};
+        int r = encode_tmap(&p.tma_out, a->out, a->out_dtype, 3, dims, so, box, esz == 4 ? 128 : 64, nullptr);
+        if (r) return r;
+        if (a->residual) {
+          const uint64_t sr[2] = {(uint64_t)a->ldr * esz, (uint64_t)a->conv_W * a->ldr * esz};
+          r = encode_tmap(&p.tma_res, a->residual, a->res_dtype, 3, dims, sr, box, esz == 4 ? 128 : 64, nullptr);
+          if (r) return r;
+        }
+      }
+      p.a_mode = A_CONV3X3_HALO;
+      switch (bn) {
+        case 128: return launch_gemm2<128, true>(p, stream);
+        case 160: return launch_gemm2<160, true>(p, stream);
+        case 320: return launch_gemm2<320, true>(p, stream);
+        default: return launch_gemm2<256, true>(p, stream);
+      }
+    }
   }
   if (pair) {
     switch (bn) {

@@ -38,6 +38,8 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
   static constexpr int ACC_STRIDE = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : BLOCK_N <= 256 ? 256 : 512;
   static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
+  // A_CONV3X3_HALO: two resident halo-tile slots in front of a B-only ring
+  static constexpr int HALO_RES = 2 * HALO_BYTES;
   static_assert(MMA_N % 32 == 0 && MMA_N >= 64 && MMA_N <= 256 && TMEM_COLS <= 512, "invalid 2-CTA UMMA N");
   static_assert(B_SUB % 1024 == 0, "B sub-tiles must keep 1024-B alignment");
 };
@@ -85,14 +87,16 @@ __device__ __forceinline__ PairSched make_pair_sched(int kb_per_tile, int pair, 
   return s;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool HALO = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ GemmParams p) {
   using C = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_tiles = smem;
-  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem + p.num_stages * C::STAGE_BYTES);
+  // HALO: [2 halo slots][num_stages x B half-tiles]; else [num_stages x (A + B half-tile)]
+  constexpr int RING_STAGE = HALO ? C::B_BYTES : C::STAGE_BYTES;
+  uint8_t* smem_tiles = smem + (HALO ? C::HALO_RES : 0);
+  GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem_tiles + p.num_stages * RING_STAGE);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
@@ -122,13 +126,15 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     tma_prefetch_desc(&p.tma_b);
     if (p.kb_split < p.num_k_blocks) tma_prefetch_desc(&p.tma_a2);
     mbar_init(&bars->b_full, 1);
-    for (int i = 0; i < C::STAGES; ++i) {
+    for (int i = 0; i < (HALO ? 8 : C::STAGES); ++i) {  // (the halo mode's B-only ring is deeper than C::STAGES)
       mbar_init(&bars->full[i], 1);
       mbar_init(&bars->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
       mbar_init(&bars->tmem_empty[i], 2 * (p.epi_tma ? p.epi_warps : GEMM_EPI_WARPS));
+      mbar_init(&bars->halo_full[i], 1);
+      mbar_init(&bars->halo_empty[i], 1);
     }
     if (p.epi_tma) {
       tma_prefetch_desc(&p.tma_out);
@@ -152,7 +158,50 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   pdl_launch();
 
   if (warp == 0) {
-    {
+    if constexpr (HALO) {
+      // ---------------- TMA producer, halo mode: per 64-channel block ONE halo tile (all nine taps) + nine weight tiles
+      int stage = 0, hb = 0;
+      uint32_t phase = 0, hphase = 0;
+      PairSched sched = sched0;
+      Seg sg;
+      const int hw = p.conv_W * p.conv_H, bxn = p.conv_W >> 3;
+      while (sched.next(sg)) {
+        const int part = sg.tile % 3;
+        const int tile = sg.tile / 3;
+        const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0) + static_cast<int>(rank) * (C::MMA_N / 2);
+        const int nmma = part == 0 ? C::NMMA : 1;
+        const int cb0 = m0 / hw, blk = (m0 - cb0 * hw) >> 7;
+        const int cx0 = (blk % bxn) * 8, cy0 = (blk / bxn) * 16;
+        for (int cb = 0; cb < p.conv_cblocks; ++cb) {
+          mbar_wait(&bars->halo_empty[hb], hphase ^ 1);
+          const uint32_t hfull_leader = mapa_u32(smem_u32(&bars->halo_full[hb]), 0);
+          if (elect_one()) {
+            if (leader) mbar_arrive_expect_tx(&bars->halo_full[hb], 2 * HALO_TX);
+            tma2_load_4d(smem + hb * HALO_BYTES, &p.tma_a, hfull_leader, cb * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
+          }
+          __syncwarp();
+          hb ^= 1;
+          if (hb == 0) hphase ^= 1;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bars->empty[stage], phase ^ 1);
+            uint8_t* sb = smem_tiles + stage * RING_STAGE;
+            const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
+            if (elect_one()) {
+              if (leader) mbar_arrive_expect_tx(&bars->full[stage], 2 * nmma * C::B_SUB);
+              const int bcol = (tap * p.conv_cblocks + cb) * BLOCK_K;  // weight column of (tap, channel block)
+              tma2_load_2d(sb, &p.tma_b, full_leader, bcol, n0);
+              if (C::NMMA == 2 && nmma == 2) tma2_load_2d(sb + C::B_SUB, &p.tma_b, full_leader, bcol, n0 + C::MMA_N);
+            }
+            __syncwarp();
+            if (++stage == p.num_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else {
       // ---------------- TMA producer (both CTAs); warp-uniform loop, one elected lane issues
       int stage = 0;
       uint32_t phase = 0;
@@ -199,6 +248,65 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             stage = 0;
             phase ^= 1;
           }
+        }
+      }
+    }
+  } else if (warp == 1 && HALO) {
+    if (leader) {
+      // ---------------- MMA issuer, halo mode: A descriptors walk the nine shifted views of the resident halo tile
+      const uint32_t idesc = make_idesc_f16(2 * BLOCK_M, C::MMA_N, p.in_dtype == DT_BF16, false);
+      const uint64_t dh0 = make_smem_desc_sw128(smem_u32(smem), 16, 1280);  // 8-pixel groups one halo row (10 px) apart
+      const uint64_t db0 = make_smem_desc_sw128(smem_u32(smem_tiles), 16, 1024);
+      constexpr uint64_t DESC_STEP = RING_STAGE >> 4;
+      constexpr uint64_t SUB_STEP = C::B_SUB >> 4;
+      uint64_t db = db0;
+      int stage = 0, hb = 0;
+      uint32_t phase = 0, hphase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      bool ready = false;
+      PairSched sched = sched0;
+      Seg sg;
+      while (sched.next(sg)) {
+        const int nmma = sg.tile % 3 == 0 ? C::NMMA : 1;
+        mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
+        for (int cb = 0; cb < p.conv_cblocks; ++cb) {
+          mbar_wait(&bars->halo_full[hb], hphase);
+          tc_fence_after();
+          const uint64_t dh = dh0 + static_cast<uint64_t>(hb) * (HALO_BYTES >> 4);
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!ready) mbar_wait(&bars->full[stage], phase);
+            tc_fence_after();
+            const bool wrap = stage + 1 == p.num_stages;
+            const int nstage = wrap ? 0 : stage + 1;
+            const uint32_t nphase = wrap ? phase ^ 1 : phase;
+            ready = mbar_test_wait(&bars->full[nstage], nphase);
+            const uint64_t da = dh + static_cast<uint64_t>((tap / 3) * 10 + tap % 3) * (128 >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                umma2_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+                if (C::NMMA == 2 && nmma == 2)
+                  umma2_f16(tmem_d + C::MMA_N, da + 2 * k, db + SUB_STEP + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
+              }
+              umma2_commit_mcast(&bars->empty[stage], 0b11);
+              if (tap == 8) umma2_commit_mcast(&bars->halo_empty[hb], 0b11);  // every tap of this halo tile has been read
+            }
+            __syncwarp();
+            db = wrap ? db0 : db + DESC_STEP;
+            stage = nstage;
+            phase = nphase;
+          }
+          hb ^= 1;
+          if (hb == 0) hphase ^= 1;
+        }
+        if (elect_one()) umma2_commit_mcast(&bars->tmem_full[acc], 0b11);
+        __syncwarp();
+        if (++acc == C::NACC) {
+          acc = 0;
+          acc_phase ^= 1;
         }
       }
     }

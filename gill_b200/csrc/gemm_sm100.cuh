@@ -30,7 +30,16 @@ constexpr int GEMM_EPI_WARPS = 8;  // 2 per SM sub-partition; 384 threads leave 
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warps 0-3: producer / MMA / TMEM alloc / spare
 constexpr int SMEM_BUDGET = 227 * 1024;
 
-enum { A_PLAIN = 0, A_CONV3X3 = 1 };
+// A_CONV3X3_HALO (CTA-pair kernel only, stride 1, W and H multiples of 16): an M tile is a 16 (y) x 8 (x) block of
+// output pixels and its A operand for ALL NINE taps of a 64-channel block is ONE 18 x 10 pixel halo tile in shared
+// memory (one 4-D TMA box, OOB zero fill = padding); tap (dy, dx) is the same tile read through a descriptor whose
+// start address is shifted by (dy * 10 + dx) 128-byte rows, 8-row groups 1280 bytes apart. The SWIZZLE_128B pattern is
+// a function of the absolute shared-memory address on both sides (TMA write, tcgen05.mma read), so shifted starts and
+// SBO = 1280 read exactly the rows they name (tools/exp/shifted_desc.cu, profiles/r02_shifted_desc_experiment.log).
+// The K loop runs 64-channel block outer, tap inner; A traffic per CTA drops from 9 x 16 KB to 23 KB per channel block.
+enum { A_PLAIN = 0, A_CONV3X3 = 1, A_CONV3X3_HALO = 2 };
+constexpr int HALO_BYTES = 24576;           // slot size (1024-aligned); the box itself is 18 * 10 * 128 = 23040 bytes
+constexpr int HALO_TX = 18 * 10 * 128;
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SILU = 3, ACT_GEGLU = 4, ACT_QUICK_GELU = 5 };
 enum { DT_BF16 = 0, DT_F16 = 1, DT_F32 = 2 };
 
@@ -736,6 +745,7 @@ struct GemmSmemBars {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t res_full[GEMM_EPI_WARPS][EPI_MAX_NBUF];
+  uint64_t halo_full[2], halo_empty[2];  // A_CONV3X3_HALO: the two halo-tile slots
   uint32_t tmem_ptr;
 };
 static_assert(sizeof(GemmSmemBars) <= 1024, "barrier block");
@@ -805,9 +815,21 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       ln_rm = ln_rstd * mean;
     }
 
+    // A_CONV3X3_HALO: rows are numbered block by block (sample, 16 x 8 pixel block, y-major inside the block), so this
+    // warp's 32 rows are a 4 (y) x 8 (x) patch: panels travel through 3-D {C, W, B * H} tensor maps with {32, 8, 4} boxes
+    const bool halo = p.a_mode == A_CONV3X3_HALO;
+    int hx = 0, hy = 0;
+    if (halo) {
+      const int hw = p.conv_W * p.conv_H;
+      const int hb = row0 / hw, hr = row0 - hb * hw;
+      const int blk = hr >> 7, bxn = p.conv_W >> 3;
+      hx = (blk % bxn) * 8;
+      hy = hb * p.conv_H + (blk / bxn) * 16 + ((hr & 127) >> 5) * 4;
+    }
     auto fetch_res = [&](int pnl, uint32_t b) {  // lane 0 only
       mbar_arrive_expect_tx(&res_bar[b], panel_bytes);
-      tma_load_2d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, row0);
+      if (halo) tma_load_3d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, hx, hy);
+      else tma_load_2d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, row0);
     };
     if (has_res && pb0 < pe && !sk_partial && lane == 0) {  // first residual panel travels while the MMAs finish
       tma_store_wait_read<1>();
@@ -1027,7 +1049,8 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
+        if (halo) tma_store_3d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, hx, hy);
+        else tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
         if (sbuf_lo) tma_store_2d(&p.tma_out_lo, sbuf_lo, no0 + pnl * EPI_PANEL_COLS, row0);
         tma_store_commit();
       }

@@ -88,7 +88,8 @@ typedef struct gillb200_gemm_args {
                  * 3 = split-K over the CTA-pair wide tile + reduce pass (small-M N % 320 == 0 convs; opt-in, see gemm.cu) */
   /* optional: GroupNorm statistics of the output, float [M/32, N, 2] = per 32-row slab and column {sum, sum of squares} of
    * the rounded 16-bit output values (consumed by gillb200_groupnorm_from_stats). Needs a 16-bit output, M % 32 == 0,
-   * N % 32 == 0, 16-byte aligned rows and no GEGLU. */
+   * N % 32 == 0, 16-byte aligned rows and no GEGLU. A slab is 32 rows of ONE sample: 32 consecutive rows, or (3x3
+   * convolutions that run on the halo-tile kernel) a 4 x 8 pixel patch; slabs of a sample occupy that sample's M/32-range. */
   void* stats_out;
   /* LayerNorm folded into the NEXT GEMM (UNet transformer blocks).
    * rowstats_out (producer, optional): float [N/32, M, 2] = per 32-column panel and row {sum, sumsq} of the output; needs

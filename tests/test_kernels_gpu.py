@@ -131,9 +131,11 @@ def test_conv3x3_wide_pair_tile(ops, case):
     auto = ops.conv3x3(x, wk, bias=bias, block_n=160, **kw)
     assert rel(got, auto) < 1e-3
     if mode == "stats":
-        st = got.gn_stats.view(B, H * W // 32, Co, 2)
-        g32 = got.float().view(B, H * W // 32, 32, Co)
-        assert rel(st[..., 0], g32.sum(2)) < 1e-3 and rel(st[..., 1], (g32 * g32).sum(2)) < 1e-3
+        # slabs are 32 rows of ONE sample (consecutive rows, or a 4 x 8 pixel patch under the halo-tile conv): the consumer
+        # only ever adds all slabs of a sample, so that is what is pinned
+        st = got.gn_stats.view(B, H * W // 32, Co, 2).sum(1)
+        g = got.float().view(B, H * W, Co)
+        assert rel(st[..., 0], g.sum(1)) < 1e-3 and rel(st[..., 1], (g * g).sum(1)) < 1e-3
 
 
 @pytest.mark.parametrize("case", [(16, 8, 8, 320, 640, "res"), (16, 8, 8, 320, 1280, "rowbias"), (8, 16, 16, 320, 640, "stats"),
@@ -651,3 +653,40 @@ def test_conv3x3_narrow_equals_conv2d(ops, B, H, W, C, cout):
     assert got.shape == ref.shape and got.dtype == torch.float16
     assert rel(got, ref) < 1e-3
     assert (got.float() - ref).abs().max() < 2e-2
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 64, 320, 320, "res"), (3, 32, 32, 128, 640, 320, "rowbias"), (2, 32, 32, 128, 320, 256, "res"),
+                                  (2, 32, 32, 128, 256, 256, "stats"), (5, 16, 16, 192, 320, 160, "res"), (2, 48, 32, 128, 128, 128, "stats"),
+                                  (16, 16, 16, 640, 640, 0, "res")])
+def test_conv3x3_halo_tile(ops, case):
+    """A_CONV3X3_HALO: one 18 x 10 pixel halo tile per 64-channel block feeds all nine taps through shifted descriptors;
+    M tiles are 16 x 8 pixel blocks stored through 3-D tensor maps. Against F.conv2d and against the one-box-per-tap form
+    (separate process-wide switch is read once, so the comparison launch forces the 1-CTA kernel instead)."""
+    B, H, W, C, Co, bn, mode = case
+    torch.manual_seed(6)
+    x = torch.randn(B, H, W, C, device=dev).half()
+    w = (torch.randn(Co, C, 3, 3, device=dev) / (3 * C ** 0.5)).half()
+    bias = torch.randn(Co, device=dev)
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    kw = {}
+    if mode == "res":
+        res = torch.randn(B, H, W, Co, device=dev).half()
+        kw["residual"] = res
+        ref = ref + res.float()
+    elif mode == "rowbias":
+        rb = torch.randn(B, Co, device=dev)
+        kw["rowbias"] = rb
+        ref = ref + rb[:, None, None, :]
+    got = ops.conv3x3(x, wk, bias=bias, block_n=bn, cta_pair=2 if bn else 0, stats=(mode == "stats"), **kw)
+    assert got.dtype == torch.float16 and rel(got, ref) < 2e-3
+    one_cta = ops.conv3x3(x, wk, bias=bias, block_n=128, cta_pair=1, stream_k=1, **kw)     # per-tap boxes, 1-CTA kernel
+    assert rel(got, one_cta) < 1e-3
+    if mode == "stats":
+        st = got.gn_stats.view(B, H * W // 32, Co, 2).sum(1)
+        g = got.float().view(B, H * W, Co)
+        assert rel(st[..., 0], g.sum(1)) < 1e-3 and rel(st[..., 1], (g * g).sum(1)) < 1e-3
+        w2, b2 = torch.randn(Co, device=dev), torch.randn(Co, device=dev)
+        gn = ops.groupnorm(got, w2, b2, 32, 1e-5, silu=True)
+        gref = F.silu(F.group_norm(got.permute(0, 3, 1, 2).float(), 32, w2, b2, 1e-5)).permute(0, 2, 3, 1)
+        assert rel(gn, gref) < 2e-3
