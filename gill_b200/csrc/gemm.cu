@@ -690,6 +690,8 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       }
     }
   }
+  if (p.debug_mode == 3 && a->sk_workspace && p.sk_per == 0)  // wait-time trace of CTA 0 (measurement aid, see gemm_mma)
+    p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->sk_workspace) + SK_FLAG_BYTES);
   if (pair) {
     switch (bn) {
       case 64: return launch_gemm2<64>(p, stream);

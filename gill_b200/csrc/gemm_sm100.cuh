@@ -26,6 +26,15 @@ namespace gb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
+#ifndef GILLB200_EPI_PIPELINE
+#define GILLB200_EPI_PIPELINE 0
+#endif
+#ifdef GILLB200_GEMM_TRACE
+constexpr bool GEMM_TRACE = true;   // build with -DGILLB200_GEMM_TRACE: debug_mode 3 records CTA 0's wait times (tools/gpu_gemm_trace.py)
+#else
+constexpr bool GEMM_TRACE = false;  // (default build: the trace code folds away)
+#endif
+constexpr bool EPI_PIPELINE = GILLB200_EPI_PIPELINE != 0;  // staged epilogue: prefetch the next accumulator chunk (A/B: rebuild with 0)
 constexpr int GEMM_EPI_WARPS = 8;  // 2 per SM sub-partition; 384 threads leave 168 registers per thread (16 warps capped it at 96: spills)
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;  // warps 0-3: producer / MMA / TMEM alloc / spare
 constexpr int SMEM_BUDGET = 227 * 1024;
@@ -366,17 +375,26 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
   uint32_t acc_phase = 0;
   bool ready = false;  // full[stage] of the current phase already seen complete by the look-ahead probe
   bool b_ready = !bres;
+  // debug_mode 3 (measurement aid): CTA 0 adds up the clocks its MMA warp and first epilogue warp spend in each wait and
+  // leaves them in the stream-K scratch (tools/gpu_gemm_trace.py)
+  const bool trace = GEMM_TRACE && p.debug_mode == 3 && blockIdx.x == 0 && p.sk_ws != nullptr;
+  long long tr_empty = 0, tr_full = 0, tr_tiles = 0, tr_t0 = 0;
+  const long long tr_begin = trace ? clock64() : 0;
   Seg sg;
   while (it.next(sg)) {
     if (!b_ready) {  // (inside the loop: a CTA without tiles never loads, so it must never wait)
       mbar_wait(b_full, 0);
       b_ready = true;
     }
+    if (trace) tr_t0 = clock64();
     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    if (trace) tr_empty += clock64() - tr_t0, ++tr_tiles;
     tc_fence_after();
     const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
     for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
+      if (trace) tr_t0 = clock64();
       if (!ready) mbar_wait(&full[stage], phase);
+      if (trace) tr_full += clock64() - tr_t0;
       tc_fence_after();
       const bool wrap = stage + 1 == p.num_stages;
       const int nstage = wrap ? 0 : stage + 1;
@@ -405,6 +423,10 @@ __device__ __forceinline__ void gemm_mma(const GemmParams& p, uint8_t* smem_tile
       acc = 0;
       acc_phase ^= 1;
     }
+  }
+  if (trace && lane_id() == 0) {
+    long long* d = reinterpret_cast<long long*>(p.sk_ws);
+    d[0] = tr_empty, d[1] = tr_full, d[2] = clock64() - tr_begin, d[3] = tr_tiles;
   }
 }
 
@@ -777,6 +799,9 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
   int acc = 0;
   uint32_t acc_phase = 0;
 
+  const bool trace = GEMM_TRACE && p.debug_mode == 3 && blockIdx.x == 0 && ew == 0 && p.sk_ws != nullptr;
+  long long tr_acc = 0, tr_store = 0, tr_ld = 0, tr_res = 0, tr_tiles = 0, tr_t0 = 0, tr_fence = 0, tr_issue = 0;
+  const long long tr_begin = trace ? clock64() : 0;
   Seg sg;
   while (it.next(sg)) {
     const int tile = sg.tile;
@@ -835,7 +860,9 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       tma_store_wait_read<1>();
       fetch_res(pb0, buf);
     }
+    if (trace) tr_t0 = clock64();
     mbar_wait(&bars->tmem_full[acc], acc_phase);
+    if (trace) tr_acc += clock64() - tr_t0, ++tr_tiles;
     tc_fence_after();
     if (pb0 >= pe) release_fn(acc);
 
@@ -905,14 +932,23 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       }
     };
 
+    // Compile-time variants: the NEXT 32-column accumulator chunk is already travelling TMEM -> registers while this one is
+    // converted and staged (a panel used to be one serial chain TMEM load -> math -> st.shared -> TMA store, ~700 clocks
+    // with two epilogue warps per scheduler to hide it: the K = 320 linears spent as long draining a tile as filling it).
+    constexpr bool PIPE = VAR != EV_GENERIC && EPI_PIPELINE;
+    uint32_t rn[32];
+    if (PIPE && pb0 < pe) tmem_ld_32x32b_x32(taddr + pb0 * acc_per_panel, rn);
+
     for (int pnl = pb0; pnl < pe; ++pnl) {
       uint8_t* sbuf = stage + buf * panel_bytes;
       const uint32_t nxt = buf + 1 == nbuf ? 0 : buf + 1;
+      if (trace) tr_t0 = clock64();
       if (lane == 0) {
         tma_store_wait_read<1>();  // the store issued two panels ago has drained its staging buffer
         if (has_res && pnl + 1 < pe) fetch_res(pnl + 1, nxt);
       }
       __syncwarp();
+      if (trace) tr_store += clock64() - tr_t0;
       const bool last = pnl == pe - 1;
       const int nacc = n0 + pnl * acc_per_panel;  // first accumulator column (global) of this panel
 
@@ -951,8 +987,16 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
 #pragma unroll
           for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
           uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + pnl * 64 + h * 32, r);
-          tmem_wait_ld();
+          if (PIPE) {
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = rn[i];
+            if (h == 0) tmem_ld_32x32b_x32(taddr + pnl * 64 + 32, rn);
+            else if (!last) tmem_ld_32x32b_x32(taddr + (pnl + 1) * 64, rn);
+          } else {
+            tmem_ld_32x32b_x32(taddr + pnl * 64 + h * 32, r);
+            tmem_wait_ld();
+          }
           if (last && h == 1) release_fn(acc);
           if (sk_reduce) sk_add(r, pnl * 64 + h * 32);
           if (LNF) {  // x W'^T -> rstd * (x W'^T - mean * colsum(W')) before the bias
@@ -992,8 +1036,17 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           }
         }
         uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + pnl * 32, r);
-        tmem_wait_ld();
+        if (PIPE) {
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = rn[i];
+          if (!last) tmem_ld_32x32b_x32(taddr + (pnl + 1) * 32, rn);
+        } else {
+          if (trace) tr_t0 = clock64();
+          tmem_ld_32x32b_x32(taddr + pnl * 32, r);
+          tmem_wait_ld();
+          if (trace) tr_ld += clock64() - tr_t0;
+        }
         if (last) release_fn(acc);
         if (sk_reduce) sk_add(r, pnl * 32);
         if (LNF) {
@@ -1015,7 +1068,9 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           f[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bv[i].z;
           f[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bv[i].w;
         }
+        if (trace) tr_t0 = clock64();
         if (VAR == EV_BIAS_RES) mbar_wait(&res_bar[buf], (par >> buf) & 1);
+        if (trace) tr_res += clock64() - tr_t0;
         epi_f16_units<4, VAR == EV_BIAS_RES>(sbuf, lane, 0, f);
         if ((VAR == EV_BIAS || VAR == EV_BIAS_RES) && p.rowstats_out != nullptr && row0 + lane < p.M_out) {
           // f[] now holds this row's 32 final values (residual included): partial LayerNorm sums for the next GEMM
@@ -1046,14 +1101,17 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
         p.stats_out[static_cast<size_t>(row0 >> 5) * n_out_total + (no0 + pnl * EPI_PANEL_COLS + lane)] =
             make_float2(cs, cq);
       }
+      if (trace) tr_t0 = clock64();
       fence_proxy_async_smem();
       __syncwarp();
+      if (trace) tr_fence += clock64() - tr_t0, tr_t0 = clock64();
       if (lane == 0) {
         if (halo) tma_store_3d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, hx, hy);
         else tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
         if (sbuf_lo) tma_store_2d(&p.tma_out_lo, sbuf_lo, no0 + pnl * EPI_PANEL_COLS, row0);
         tma_store_commit();
       }
+      if (trace) tr_issue += clock64() - tr_t0;
       par ^= 1u << buf;
       buf = nxt;
     }
@@ -1068,6 +1126,10 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
     }
   }
   if (lane == 0) tma_store_wait_all<0>();  // smem must outlive the bulk reads
+  if (trace && lane == 0) {
+    long long* d = reinterpret_cast<long long*>(p.sk_ws) + 8;
+    d[0] = tr_acc, d[1] = tr_store, d[2] = tr_ld, d[3] = tr_res, d[4] = clock64() - tr_begin, d[5] = tr_tiles, d[6] = tr_fence, d[7] = tr_issue;
+  }
 }
 
 // Runtime -> compile-time variant dispatch (once per warp, outside the tile loop).
