@@ -277,6 +277,21 @@ def test_layernorm(ops, C, dt):
         assert rel(hi.float() + lo.float(), F.layer_norm(x, (C,), w, b, 1e-5)) < 2e-5
 
 
+@pytest.mark.parametrize("rows,C,dt", [(65536, 320, torch.float16), (16387, 640, torch.float16), (4099, 1280, torch.float16),
+                                       (2051, 256, torch.bfloat16), (40000, 1000 - 8, torch.float16)])
+def test_layernorm_persistent_16bit(ops, rows, C, dt):
+    """The persistent 16-bit LayerNorm (grid-stride row blocks, next block prefetched): the UNet's shapes, ragged row counts,
+    a channel count that leaves lanes without a vector, and a strided input view."""
+    torch.manual_seed(61)
+    big = (torch.randn(rows, C + 64, device=dev) * 1.5 + 0.3).to(dt)
+    x = big[:, :C]                                                    # row stride C + 64
+    w, b = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    got = ops.layernorm(x, w, b, 1e-5)
+    assert got.dtype == dt and got.shape == (rows, C)
+    ref = F.layer_norm(x.float(), (C,), w, b, 1e-5)
+    assert rel(got, ref) < (6e-3 if dt == torch.bfloat16 else 8e-4)
+
+
 @pytest.mark.parametrize("case", [(2, 64, 64, 320, 0, True), (2, 32, 32, 640, 320, True), (2, 8, 8, 1280, 1280, False),
                                   (1, 128, 128, 256, 0, True), (2, 16, 16, 1280, 640, True)])
 def test_groupnorm_nhwc_with_concat(ops, case):

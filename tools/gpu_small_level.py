@@ -62,3 +62,8 @@ for (HW, C0, C1) in [(8, 1280, 0), (8, 1280, 1280), (16, 1280, 0), (16, 1280, 12
     w = torch.randn(C, device=dev); bb = torch.randn(C, device=dev); out = torch.empty(16, HW, HW, C, device=dev, dtype=torch.float16)
     t = timeit(lambda: ops.groupnorm(x0, w, bb, 32, 1e-5, silu=True, x2=x1, out=out))
     print(f"{tag} groupnorm(from stats) B16 {HW}x{HW} C{C0}+{C1}: {t:6.1f} us  {4.0 * 16 * HW * HW * C / t / 1e3:6.0f} GB/s", flush=True)
+
+for (rows, C) in [(65536, 320), (16384, 640), (4096, 1280), (1024, 1280)]:
+    xl = torch.randn(rows, C, device=dev).half(); wl = torch.randn(C, device=dev); bl = torch.randn(C, device=dev); ol = torch.empty_like(xl)
+    t = timeit(lambda: ops.layernorm(xl, wl, bl, 1e-5, out=ol))
+    print(f"{tag} layernorm rows{rows} C{C}: {t:6.1f} us  {4.0 * rows * C / t / 1e3:6.0f} GB/s", flush=True)
