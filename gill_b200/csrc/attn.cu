@@ -37,6 +37,7 @@ struct alignas(64) AttnParams {
   int ones_col;      // >= 0: column (inside the head padding) where V holds 1.0, so O[:, ones_col] IS the softmax
                      // denominator (computed by the tensor core from the same rounded P as the numerator); -1: none
   float scale_log2;  // softmax scale * log2(e)
+  int q_tiles_per_cta;  // attn4q (short key sequences): consecutive 128-row query tiles one CTA walks with K / V resident
 };
 
 template <int HD_PAD, int BLOCK_KV>
@@ -1223,6 +1224,264 @@ __global__ void __launch_bounds__(160, Attn4Cfg<BKV_, KCH_>::CTAS_PER_SM) attn4_
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ================================================================================================================
+// attn4q: attn4 for SHORT key sequences (at most two key tiles: the UNet's 77-key cross-attention) with the CTA walking
+// several query tiles. One (query tile, head, sample) per CTA made the cross-attention pure fixed cost -- TMEM allocation,
+// barrier set-up and the Q / K / V round trips to L2 for ~1 us of work: 4096 CTAs in 7 waves, 46 us at 16x8x4096x77
+// against a 15 us memory floor. Here K and V (both tiles) are loaded once per CTA and stay in the two slots, the CTA walks
+// q_tiles_per_cta query tiles, the next Q tile is requested as soon as the last Q.K^T of the current one has retired, and
+// the grid is sized to ONE wave. Barrier parities run on a single iteration counter over (query tile, key tile).
+template <int BKV_, int KCH_>
+__global__ void __launch_bounds__(160, Attn4Cfg<BKV_, KCH_>::CTAS_PER_SM) attn4q_kernel(const __grid_constant__ AttnParams p) {
+  using C = Attn4Cfg<BKV_, KCH_>;
+  constexpr int BKV = C::BKV, KCH = C::KCH;
+  pdl_wait();
+  pdl_launch();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Attn4Bars* bars = reinterpret_cast<Attn4Bars*>(smem + C::OFF_BAR);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int nq_all = (p.Lq + 127) / 128;
+  const int qt0 = blockIdx.x * p.q_tiles_per_cta;
+  const int nq = min(p.q_tiles_per_cta, nq_all - qt0);
+  const int kv_len = p.kv_lens ? p.kv_lens[b] : p.Lk;
+  int n_tiles = (kv_len + BKV - 1) / BKV;  // 1 or 2 (host-checked: Lk <= 2 * BKV)
+  if (n_tiles < 1) n_tiles = 1;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&p.tma_q);
+    tma_prefetch_desc(&p.tma_k);
+    tma_prefetch_desc(&p.tma_v);
+    mbar_init(&bars->q_full, 1);
+    mbar_init(&bars->k_full[0], 1);
+    mbar_init(&bars->k_full[1], 1);
+    mbar_init(&bars->v_full[0], 1);
+    mbar_init(&bars->v_full[1], 1);
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->s_free, 4);
+    mbar_init(&bars->p_full, 4);
+    mbar_init(&bars->pv_done, 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 0) {
+    tmem_alloc(&bars->tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_ptr;
+  const int col0 = head * p.hd_cols;
+  const int ksteps = p.hd_cols >> 4;
+  const bool bf16 = p.in_dtype == DT_BF16;
+
+  if (warp == 4) {
+    if (lane_id() == 0) {
+      const uint32_t idesc_s = make_idesc_f16(128, BKV, bf16, false);
+      const uint32_t idesc_o = make_idesc_f16(128, p.hd_cols, bf16, true);
+      const uint32_t sq = smem_u32(smem + C::OFF_Q), sk = smem_u32(smem + C::OFF_K), sv = smem_u32(smem + C::OFF_V);
+      auto load_q = [&](int t) {
+        mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
+#pragma unroll
+        for (int c = 0; c < KCH; ++c)
+          tma_load_3d(smem + C::OFF_Q + c * C::Q_CHUNK, &p.tma_q, &bars->q_full, col0 + c * 64, (qt0 + t) * 128, b);
+      };
+      auto mma_s = [&](int slot) {
+#pragma unroll
+        for (int k = 0; k < 4 * KCH; ++k)
+          if (k < ksteps)
+            umma_f16(tmem_base + C::TMEM_S, make_smem_desc_sw128(sq + (k >> 2) * C::Q_CHUNK + (k & 3) * 32, 16, 1024),
+                     make_smem_desc_sw128(sk + slot * C::KV_BYTES + (k >> 2) * C::KV_CHUNK + (k & 3) * 32, 16, 1024),
+                     idesc_s, k != 0 ? 1u : 0u);
+      };
+      load_q(0);
+      for (int j = 0; j < n_tiles; ++j) {  // every key / value tile once: resident for all query tiles
+        mbar_arrive_expect_tx(&bars->k_full[j], C::KV_BYTES);
+        mbar_arrive_expect_tx(&bars->v_full[j], C::KV_BYTES);
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) {
+          tma_load_3d(smem + C::OFF_K + j * C::KV_BYTES + c * C::KV_CHUNK, &p.tma_k, &bars->k_full[j], col0 + c * 64, j * BKV, b);
+          tma_load_3d(smem + C::OFF_V + j * C::KV_BYTES + c * C::KV_CHUNK, &p.tma_v, &bars->v_full[j], col0 + c * 64, j * BKV, b);
+        }
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&bars->k_full[j], 0);
+        mbar_wait(&bars->v_full[j], 0);
+      }
+      int it = 0;
+      for (int t = 0; t < nq; ++t) {
+        mbar_wait(&bars->q_full, t & 1);
+        if (it > 0) mbar_wait(&bars->s_free, (it - 1) & 1);  // the previous tile's last scores sit in registers
+        tc_fence_after();
+        mma_s(0);
+        umma_commit(&bars->s_full);
+        for (int j = 0; j < n_tiles; ++j, ++it) {
+          if (j + 1 < n_tiles) {
+            mbar_wait(&bars->s_free, it & 1);
+            tc_fence_after();
+            mma_s(j + 1);
+            umma_commit(&bars->s_full);
+          }
+          if (j == n_tiles - 1 && t + 1 < nq) {
+            // the last Q.K^T of this query tile has retired (s_full of iteration `it`): the Q buffer is free
+            mbar_wait(&bars->s_full, it & 1);
+            load_q(t + 1);
+          }
+          mbar_wait(&bars->p_full, it & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)
+            umma_f16_ts(tmem_base + C::TMEM_O, tmem_base + C::TMEM_P + k * 8,
+                        make_smem_desc_sw128(sv + j * C::KV_BYTES + k * (16 * 128), C::KV_CHUNK, 1024), idesc_o,
+                        (j | k) != 0 ? 1u : 0u);
+          umma_commit(&bars->pv_done);
+        }
+      }
+    }
+  } else {
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t ts = tmem_base + C::TMEM_S + lane_off;
+    const uint32_t tp = tmem_base + C::TMEM_P + lane_off;
+    const uint32_t to = tmem_base + C::TMEM_O + lane_off;
+    const bool use_ones = p.ones_col >= 0;
+    int it = 0;
+    for (int t = 0; t < nq; ++t) {
+      const int qrow = (qt0 + t) * 128 + tid;
+      float m_used = 0.f, l = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        mbar_wait(&bars->s_full, it & 1);
+        tc_fence_after();
+        constexpr int N1 = BKV - 32;
+        uint32_t s0[32], s1[N1];
+        tmem_ld_32x32b_x32(ts, s0);
+        if constexpr (N1 == 16) tmem_ld_32x32b_x16(ts + 32, s1);
+        else tmem_ld_32x32b_x32(ts + 32, s1);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&bars->s_free);
+        const int lim = kv_len - 1 - j * BKV;  // columns > lim are masked
+        const bool no_mask = lim >= BKV - 1;
+        float mx = no_mask ? fmaxf(attn_max_n<32>(s0), attn_max_n<N1>(s1))
+                           : fmaxf(attn_max_n_masked<32>(s0, 0, lim), attn_max_n_masked<N1>(s1, 32, lim));
+        mx *= p.scale_log2;
+        float alpha = 1.f;
+        bool need = false;
+        if (j == 0) {
+          m_used = mx == -INFINITY ? 0.f : mx;
+        } else if (mx > m_used + 8.f) {
+          alpha = fast_exp2(m_used - mx);
+          m_used = mx;
+          need = true;
+        }
+        uint32_t pk[BKV / 2];
+        float part;
+        if (no_mask) {
+          if (use_ones) {
+            part = bf16 ? attn_exp_n_fast<32, false, true, 0>(s0, p.scale_log2, m_used, pk, 0) +
+                              attn_exp_n_fast<N1, false, true, 0>(s1, p.scale_log2, m_used, pk + 16, 16)
+                        : attn_exp_n_fast<32, false, false, 0>(s0, p.scale_log2, m_used, pk, 0) +
+                              attn_exp_n_fast<N1, false, false, 0>(s1, p.scale_log2, m_used, pk + 16, 16);
+          } else {
+            part = bf16 ? attn_exp_n_fast<32, true, true, 0>(s0, p.scale_log2, m_used, pk, 0) +
+                              attn_exp_n_fast<N1, true, true, 0>(s1, p.scale_log2, m_used, pk + 16, 16)
+                        : attn_exp_n_fast<32, true, false, 0>(s0, p.scale_log2, m_used, pk, 0) +
+                              attn_exp_n_fast<N1, true, false, 0>(s1, p.scale_log2, m_used, pk + 16, 16);
+          }
+        } else {
+          part = bf16 ? attn_exp_n<32, true, true, true>(s0, 0, lim, p.scale_log2, m_used, pk) +
+                            attn_exp_n<N1, true, true, true>(s1, 32, lim, p.scale_log2, m_used, pk + 16)
+                      : attn_exp_n<32, true, true, false>(s0, 0, lim, p.scale_log2, m_used, pk) +
+                            attn_exp_n<N1, true, true, false>(s1, 32, lim, p.scale_log2, m_used, pk + 16);
+        }
+        if (it >= 1) {  // the previous P.V has retired: P may be overwritten, O may be rescaled
+          mbar_wait(&bars->pv_done, (it - 1) & 1);
+          tc_fence_after();
+        }
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          l *= alpha;
+#pragma unroll 1
+          for (int c = 0; c < p.hd_cols; c += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(to + c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x16(to + c, v);
+          }
+        }
+        l += part;
+        {
+          uint32_t pa[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pa[i] = pk[i];
+          tmem_st_32x32b_x16(tp, pa);
+          if constexpr (BKV == 48) {
+            tmem_st_32x32b_x8(tp + 16, pk + 16);
+          } else {
+            uint32_t pb[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pb[i] = pk[16 + i];
+            tmem_st_32x32b_x16(tp + 16, pb);
+          }
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive(&bars->p_full);
+      }
+      // ---- this query tile's O / l (the next tile's first P.V waits for all four warps' next p_full arrival)
+      mbar_wait(&bars->pv_done, (it - 1) & 1);
+      tc_fence_after();
+      if (use_ones) {
+        l = __uint_as_float(tmem_ld_32x32b_x1(to + p.ones_col));
+        tmem_wait_ld();
+      }
+      const float inv = 1.f / l;
+      uint16_t* orow = reinterpret_cast<uint16_t*>(p.out) + static_cast<long long>(b) * p.o_bstride +
+                       static_cast<long long>(qrow) * p.ldo + col0;
+#pragma unroll 1
+      for (int c = 0; c < p.hd_cols; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(to + c, v);
+        tmem_wait_ld();
+        if (qrow < p.Lq) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+          store16(orow + c, f, 16, p.out_dtype);
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int BKV, int KCH>
+static int launch_attn4q(AttnParams p, cudaStream_t stream) {
+  using C = Attn4Cfg<BKV, KCH>;
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    GB_CUDA(cudaFuncSetAttribute(attn4q_kernel<BKV, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  }
+  // one wave: as few query tiles per CTA as keeps the whole grid resident
+  const int nq = (p.Lq + 127) / 128;
+  const long long slots = static_cast<long long>(C::CTAS_PER_SM) * num_sms();
+  int qt = static_cast<int>((static_cast<long long>(nq) * p.H * p.B + slots - 1) / slots);
+  if (qt < 1) qt = 1;
+  while (static_cast<long long>((nq + qt - 1) / qt) * p.H * p.B > slots) ++qt;
+  p.q_tiles_per_cta = qt;
+  dim3 grid((nq + qt - 1) / qt, p.H, p.B);
+  GB_CUDA(launch_pdl(attn4q_kernel<BKV, KCH>, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_COUNT_LAUNCH(1);
+  return 0;
+}
+
 template <int BKV, int KCH, int POLY>
 static int launch_attn4_t(const AttnParams& p, cudaStream_t stream) {
   using C = Attn4Cfg<BKV, KCH>;
@@ -1372,6 +1631,15 @@ extern "C" int gillb200_attention(const gillb200_attn_args* a, void* stream_) {
       // for the 77-key cross-attention; "0" falls back to attn2 (A/B aid)
       const char* e = getenv("GILLB200_ATTN_ISSUER");
       issuer = e ? atoi(e) : 1;
+    }
+    static int attn4q = -1;
+    if (attn4q < 0) {
+      const char* e = getenv("GILLB200_ATTN4Q");  // "0": one query tile per CTA also for short key sequences (A/B aid)
+      attn4q = e ? atoi(e) : 1;
+    }
+    if (attn4q && !a->causal && a->Lq > 128) {
+      if (use_attn4 && a->Lk <= 96) return launch_attn4q<48, 1>(p, stream);
+      if (use_attn4w && a->Lk <= 128) return launch_attn4q<64, 2>(p, stream);
     }
     if (use_attn4) return launch_attn4<48, 1>(p, stream);
     if (use_attn4w) return launch_attn4<64, 2>(p, stream);

@@ -409,6 +409,10 @@ PITCH_CASES = [  # B, H, Lq, Lk, hd, pitch, tile, dtype, causal     (SD-1.5 head
     (2, 8, 512, 512, 80, 96, 128, torch.float16, False), (2, 8, 300, 77, 80, 96, 128, torch.float16, False),
     (2, 8, 256, 256, 160, 176, 192, torch.float16, False), (1, 8, 64, 77, 160, 176, 192, torch.float16, False),
     (2, 3, 200, 200, 32, 48, 64, torch.bfloat16, True), (2, 8, 2048, 2048, 40, 48, 64, torch.float16, False),
+    # short key sequences at the UNet's real batch: attn4q walks several query tiles per CTA with K / V resident
+    (16, 8, 4096, 77, 40, 48, 64, torch.float16, False), (16, 8, 1024, 77, 80, 96, 128, torch.float16, False),
+    (3, 4, 700, 96, 32, 48, 64, torch.bfloat16, False), (2, 2, 1000, 128, 80, 96, 128, torch.float16, False),
+    (5, 3, 2000, 40, 40, 48, 64, torch.float16, False),
 ]
 
 
@@ -485,6 +489,23 @@ def test_attn4_growing_max_kv_lens_and_ragged_tiles(ops, hd, pt, tile, dt):
     assert torch.isfinite(got.float()).all() and rel(got, ref) < tol
     got2 = ops.attention(q, k, v, H, tile, hd ** -0.5, ones_col=hd if use_ones else 0, head_stride=pt)
     assert rel(got2, attn_ref(q, k, v, H, pt, hd ** -0.5)) < tol
+
+
+@pytest.mark.parametrize("hd,pt,tile,Lk", [(40, 48, 64, 96), (80, 96, 128, 128)])
+def test_attn4q_per_sample_key_counts(ops, hd, pt, tile, Lk):
+    """attn4q (several query tiles per CTA, K / V resident) with per-sample key counts: one or two key tiles per sample."""
+    torch.manual_seed(15)
+    B, H, Lq = 4, 4, 1500
+    L = max(Lq, Lk)
+    buf = torch.zeros(B, L, 3, H, pt, device=dev)
+    buf[..., :hd] = torch.randn(B, L, 3, H, hd, device=dev)
+    buf[:, :, 2, :, hd] = 1.0
+    buf = buf.view(B, L, 3 * H * pt).half()
+    q, k, v = buf[:, :Lq, : H * pt], buf[:, :Lk, H * pt: 2 * H * pt], buf[:, :Lk, 2 * H * pt:]
+    kvl = torch.tensor([Lk, 77, 20, Lk // 2 + 1], device=dev, dtype=torch.int32)
+    got = ops.attention(q, k, v, H, tile, hd ** -0.5, ones_col=hd, head_stride=pt, kv_lens=kvl)
+    ref = attn_ref(q, k, v, H, pt, hd ** -0.5, kv_lens=kvl)
+    assert torch.isfinite(got.float()).all() and rel(got, ref) < 3e-3
 
 
 def test_fused_attention_kv_lens_and_views(ops):
