@@ -137,10 +137,14 @@ def stage_breakdown(gill, vis, ids, lat, reps=2):
         img_ids = torch.tensor(m.retrieval_token_idx, dtype=torch.int64, device=dev)
         img_embs = m.input_embeddings(img_ids[None, :])
         full = torch.cat([embs.to(m.lm.dt), img_embs.expand(B, -1, -1).to(m.lm.dt)], dim=1)
-        hs, lg = m.lm.forward(full, logit_positions=[P - 1])
+        from gill_b200 import models as gm
+        graphed = gm.GRAPH_STAGES and hasattr(m.lm, "forward_graphed")       # as emit_images_batch runs them
+        hs, lg = (m.lm.forward_graphed if graphed else m.lm.forward)(full, logit_positions=[P - 1])
         raw = hs[:, P:P + m.num_tokens, :].float().contiguous()
         marks.append(ev())
-        gen = m.gen_text_hidden_fcs[0](raw, img_embs.float())
+        mp = m.gen_text_hidden_fcs[0]
+        gen = mp._graphed(raw, img_embs.float().contiguous()).clone() if graphed and hasattr(mp, "_graphed") \
+            else mp(raw, img_embs.float())
         marks.append(ev())
         latn = gill.sd_pipe.denoise(gen, lat)
         marks.append(ev())

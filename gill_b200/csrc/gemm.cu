@@ -587,6 +587,14 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
         }
         if (env_var && !a->ln_stats && !a->rowstats_out) p.epi_variant = EV_GENERIC;
       }
+      {
+        static int env_stg = -1;
+        if (env_stg < 0) {
+          const char* e = getenv("GILLB200_EPI_STG");  // staged panels written back by per-lane 16-byte stores (see epilogue_warp_tma)
+          env_stg = e ? atoi(e) : 0;
+        }
+        p.epi_stg = env_stg && esz == 2 && p.epi_variant != EV_GENERIC && (env_stg > 1 || p.num_k_blocks <= 8);
+      }
       p.epi_nbuf = a->residual ? 3 : 2;
       p.epi_buf_bytes = 32 * EPI_PANEL_COLS * esz;
       // as many epilogue warps as leave a >= 3-deep operand ring (fp32 panels are twice as large)

@@ -84,6 +84,7 @@ struct alignas(64) GemmParams {
   CUtensorMap tma_out;
   CUtensorMap tma_res;
   CUtensorMap tma_out_lo;  // second store target when out_lo is set (generic staged epilogue, bf16, no residual)
+  int epi_stg;        // compile-time 16-bit variants: write staged panels back with per-lane 16-byte stores instead of TMA
   int epi_tma;
   int epi_variant;    // EV_* specialisation of the staged epilogue
   int epi_warps;      // epilogue warps that take part (multiple of 4, <= GEMM_EPI_WARPS)
@@ -1102,14 +1103,32 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
             make_float2(cs, cq);
       }
       if (trace) tr_t0 = clock64();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (trace) tr_fence += clock64() - tr_t0, tr_t0 = clock64();
-      if (lane == 0) {
-        if (halo) tma_store_3d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, hx, hy);
-        else tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
-        if (sbuf_lo) tma_store_2d(&p.tma_out_lo, sbuf_lo, no0 + pnl * EPI_PANEL_COLS, row0);
-        tma_store_commit();
+      if (VAR != EV_GENERIC && p.epi_stg && !halo) {
+        // 16-bit panel (32 rows x 64 B, 64-byte swizzle) written back by ALL lanes: lane L takes 16-byte units L, L + 32,
+        // L + 64, L + 96 (unit u = row u / 4, quarter u % 4), so every warp store covers 8 rows x 64 contiguous bytes. No
+        // proxy fence, no TMA issue (measured ~190 clocks per panel on the issuing lane, profiles/r02_gemm_wait_trace.log),
+        // no drain wait before the buffer is reused.
+        __syncwarp();
+        uint16_t* o16 = static_cast<uint16_t*>(p.out);
+        const int pcol = no0 + pnl * EPI_PANEL_COLS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = i * 32 + lane, rr = u >> 2, su = u & 3;
+          const uint4 v = *reinterpret_cast<const uint4*>(sbuf + rr * 64 + ((su ^ ((rr >> 1) & 3)) << 4));
+          if (row0 + rr < p.M_out && pcol + su * 8 < n_out_total)
+            *reinterpret_cast<uint4*>(o16 + static_cast<long long>(row0 + rr) * p.ldo + pcol + su * 8) = v;
+        }
+        __syncwarp();
+      } else {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (trace) tr_fence += clock64() - tr_t0, tr_t0 = clock64();
+        if (lane == 0) {
+          if (halo) tma_store_3d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, hx, hy);
+          else tma_store_2d(&p.tma_out, sbuf, no0 + pnl * EPI_PANEL_COLS, row0);
+          if (sbuf_lo) tma_store_2d(&p.tma_out_lo, sbuf_lo, no0 + pnl * EPI_PANEL_COLS, row0);
+          tma_store_commit();
+        }
       }
       if (trace) tr_issue += clock64() - tr_t0;
       par ^= 1u << buf;

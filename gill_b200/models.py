@@ -26,6 +26,9 @@ import torch.nn as nn
 from . import layers, ops, retrieval
 from .opt import OPTB200
 
+# batched emission path: OPT prefill and GILLMapper replayed from CUDA graphs (one per input shape); "0": eager launches
+GRAPH_STAGES = os.environ.get("GILLB200_GRAPH_STAGES", "1") != "0"
+
 try:  # PIL is only needed for image prompts / PIL outputs
     from PIL import Image, UnidentifiedImageError
 except Exception:  # pragma: no cover
@@ -521,7 +524,10 @@ class GILL(nn.Module):
         img_ids = torch.tensor(m.retrieval_token_idx, dtype=torch.int64, device=m.lm.dev)
         img_embs = m.input_embeddings(img_ids[None, :])                                        # (1, 8, D)
         full = torch.cat([input_embs.to(m.lm.dev, m.lm.dt), img_embs.expand(B, -1, -1).to(m.lm.dt)], dim=1)
-        hs, lg = m.lm.forward(full, logit_positions=[P - 1])
+        if GRAPH_STAGES and hasattr(m.lm, "forward_graphed"):
+            hs, lg = m.lm.forward_graphed(full, logit_positions=[P - 1])   # ~400 launches replayed from one CUDA graph
+        else:
+            hs, lg = m.lm.forward(full, logit_positions=[P - 1])
         logits = lg[:, 0].float()
         m._postprocess_logits(logits, 0, 0, 1.0, 1e5, -float("Inf"))
         forced_ok = logits.argmax(dim=-1) == m.retrieval_token_idx[0]
@@ -531,7 +537,14 @@ class GILL(nn.Module):
             ret_emb = m.ret_text_hidden_fcs[0](raw_emb, None)[:, 0, :]
             q = ops.l2norm_rows(ret_emb.float().contiguous(), self.emb_matrix.dtype)
             out["ret"] = retrieval.retrieval_topk(self.emb_matrix, q, top_k)
-        gen_emb = m.gen_text_hidden_fcs[0](raw_emb, img_embs.float())                          # (B, 77, 768)
+        mapper = m.gen_text_hidden_fcs[0]
+        if GRAPH_STAGES:
+            gc = getattr(mapper, "_graphed", None)
+            if gc is None:
+                gc = mapper._graphed = ops.GraphedCall(lambda x, e: mapper(x, e), raw_emb.device)
+            gen_emb = gc(raw_emb, img_embs.float().contiguous()).clone()                       # (B, 77, 768)
+        else:
+            gen_emb = mapper(raw_emb, img_embs.float())
         out["gen_emb"] = gen_emb
         if self.load_sd:
             imgs = []

@@ -122,12 +122,30 @@ class OPTB200:
         hs = ops.layernorm(h, self.lnf_w, self.lnf_b, 1e-5, out_dtype=self.dt).view(B, T, D)
         logits = None
         if logit_positions is not None:
-            sel = hs[:, list(logit_positions), :].reshape(B * len(logit_positions), D).contiguous()
+            # (slices + stack: an index list would be an implicit host-to-device copy, illegal inside a graph capture)
+            sel = torch.stack([hs[:, int(pp), :] for pp in logit_positions], dim=1).reshape(B * len(logit_positions), D)
             logits = ops.gemm(sel, self.embed, out_dtype=torch.float32).view(B, len(logit_positions), -1)
         elif need_logits:
             last = hs[:, -1, :].contiguous()
             logits = ops.gemm(last, self.embed, out_dtype=torch.float32)          # tied lm_head, last position only
         return hs, logits
+
+    @torch.no_grad()
+    def forward_graphed(self, inputs_embeds: torch.Tensor, logit_positions=None):
+        """`forward` (no KV cache) replayed from a CUDA graph captured per (B, T, logit positions): a prefill is ~12
+        launches per layer whose eager submission through ctypes costs more CPU time than the GPU needs at batch 8 x 81
+        tokens. Same kernels, same arithmetic; the returned tensors are the graph's static outputs (valid until the next
+        call with the same shape). For fixed-shape callers (the batched emission path); `generate` keeps eager launches."""
+        gc = getattr(self, "_graphed", None)
+        if gc is None:
+            gc = self._graphed = {}
+        key = tuple(logit_positions) if logit_positions is not None else None
+        g = gc.get(key)
+        if g is None:
+            if len(gc) >= 4:
+                gc.pop(next(iter(gc)))
+            g = gc[key] = ops.GraphedCall(lambda x: self.forward(x, logit_positions=logit_positions), self.dev)
+        return g(inputs_embeds.to(self.dev, self.dt).contiguous())
 
     @torch.no_grad()
     def logits_of(self, hidden_rows: torch.Tensor) -> torch.Tensor:
