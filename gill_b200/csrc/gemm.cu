@@ -595,7 +595,17 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
         }
         p.epi_stg = env_stg && esz == 2 && p.epi_variant != EV_GENERIC && (env_stg > 1 || p.num_k_blocks <= 8);
       }
-      p.epi_nbuf = a->residual ? 3 : 2;
+      {
+        static int env_nb = -1;
+        if (env_nb < 0) {
+          const char* e = getenv("GILLB200_EPI_RES_NBUF");  // staging buffers per epilogue warp with a residual: 3 or 4
+          // measured (profiles/r02_gemm_res_nbuf.log): residual two panels ahead (4) = one ahead (3) on every + residual linear
+          // and conv (35.0 vs 35.4, 24.5 vs 24.8, 47.1 vs 49.0 us; convs 4.66 vs 4.73 ms per evaluation): 3 keeps the smem
+          env_nb = e ? atoi(e) : 3;
+          if (env_nb != 3 && env_nb != 4) env_nb = 3;
+        }
+        p.epi_nbuf = a->residual ? (esz == 2 ? env_nb : 3) : 2;  // (fp32 panels are 4 KB: a fourth buffer would cost ring stages)
+      }
       p.epi_buf_bytes = 32 * EPI_PANEL_COLS * esz;
       // as many epilogue warps as leave a >= 3-deep operand ring (fp32 panels are twice as large)
       // measured (tools/gpu_sweep_shapes.py): 8 warps + a deeper operand ring beat 16 warps on every plain shape

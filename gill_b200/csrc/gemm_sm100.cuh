@@ -88,7 +88,7 @@ struct alignas(64) GemmParams {
   int epi_tma;
   int epi_variant;    // EV_* specialisation of the staged epilogue
   int epi_warps;      // epilogue warps that take part (multiple of 4, <= GEMM_EPI_WARPS)
-  int epi_nbuf;       // staging buffers per warp: 2, or 3 with a residual
+  int epi_nbuf;       // staging buffers per warp: 2; with a residual 3 (next panel's residual in flight) or 4 (next two)
   int epi_buf_bytes;  // 2048 (16-bit output) or 4096 (fp32 output)
   int num_stages;     // smem ring depth actually used (<= GemmCfg::STAGES)
   // stream-K (sk_per > 0, 1-CTA kernel + staged epilogue only): the tiles' k-blocks form one linear range of
@@ -657,7 +657,7 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, uint64_t* tme
 // writes its 32x32 panel into swizzled shared memory (conflict-free 16-byte accesses) and a single lane issues one TMA
 // store; residual panels come in the same way, prefetched one panel ahead, and are overwritten in place.
 constexpr int EPI_PANEL_COLS = 32;
-constexpr int EPI_MAX_NBUF = 3;
+constexpr int EPI_MAX_NBUF = 4;
 
 // Compile-time specialisations of the staged epilogue for the shapes that dominate the UNet (fp16 output, N % 32 == 0,
 // alpha == 1, column bias present); EV_GENERIC keeps every option a runtime branch (fp32 / bf16 outputs, other
@@ -857,9 +857,13 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       if (halo) tma_load_3d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, hx, hy);
       else tma_load_2d(stage + b * panel_bytes, &p.tma_res, &res_bar[b], no0 + pnl * EPI_PANEL_COLS, row0);
     };
-    if (has_res && pb0 < pe && !sk_partial && lane == 0) {  // first residual panel travels while the MMAs finish
+    // with 4 staging buffers the residual runs TWO panels ahead (the wait-time trace of the N = 320 out-projections showed
+    // ~800-1000 clocks per tile spent waiting for residual panels fetched only one panel ahead)
+    const bool res2 = nbuf >= 4;
+    if (has_res && pb0 < pe && !sk_partial && lane == 0) {  // first residual panel(s) travel while the MMAs finish
       tma_store_wait_read<1>();
       fetch_res(pb0, buf);
+      if (res2 && pb0 + 1 < pe) fetch_res(pb0 + 1, buf + 1 == nbuf ? 0 : buf + 1);
     }
     if (trace) tr_t0 = clock64();
     mbar_wait(&bars->tmem_full[acc], acc_phase);
@@ -946,7 +950,8 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
       if (trace) tr_t0 = clock64();
       if (lane == 0) {
         tma_store_wait_read<1>();  // the store issued two panels ago has drained its staging buffer
-        if (has_res && pnl + 1 < pe) fetch_res(pnl + 1, nxt);
+        if (has_res && !res2 && pnl + 1 < pe) fetch_res(pnl + 1, nxt);
+        if (has_res && res2 && pnl + 2 < pe) fetch_res(pnl + 2, nxt + 1 == nbuf ? 0 : nxt + 1);
       }
       __syncwarp();
       if (trace) tr_store += clock64() - tr_t0;
