@@ -5,10 +5,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gill_b200 import ops
 dev = "cuda"
-for (M, N, K, res) in [(65536, 2560, 320, False), (65536, 1152, 320, False), (65536, 320, 320, True), (65536, 2560, 640, False), (16384, 2304, 640, False)]:
+for (M, N, K, res) in [(65536, 2560, 320, False), (65536, 1152, 320, False), (65536, 320, 320, True), (65536, 2560, 640, False), (16384, 2304, 640, False),
+                       (16384, 640, 640, True), (16384, 640, 768, True), (4096, 1280, 1280, True), (65536, 320, 384, True)]:
     a = torch.randn(M, K, device=dev).half(); b = torch.randn(N, K, device=dev).half() * 0.05; bias = torch.randn(N, device=dev)
     out = torch.empty(M, N, device=dev, dtype=torch.float16); r = torch.randn(M, N, device=dev).half() if res else None
     kw = dict(block_n=256 if N >= 256 and N % 256 == 0 or N > 640 else 160, cta_pair=1, stream_k=0)
+    if (M, N) in ((16384, 640), (4096, 1280)): kw = dict(block_n=160 if N == 640 else 256, cta_pair=1, stream_k=0)
     for _ in range(3): ops.gemm(a, b, out=out, bias=bias, residual=r, **kw)
     torch.cuda.synchronize()
     ws = list(ops._sk_ws.values())[0]
