@@ -1477,7 +1477,7 @@ static int launch_attn4q(AttnParams p, cudaStream_t stream) {
   while (static_cast<long long>((nq + qt - 1) / qt) * p.H * p.B > slots) ++qt;
   p.q_tiles_per_cta = qt;
   dim3 grid((nq + qt - 1) / qt, p.H, p.B);
-  GB_CUDA(launch_pdl(attn4q_kernel<BKV, KCH>, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl_light(attn4q_kernel<BKV, KCH>, grid, dim3(160), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -1490,7 +1490,7 @@ static int launch_attn4_t(const AttnParams& p, cudaStream_t stream) {
     GB_CUDA(cudaFuncSetAttribute(attn4_kernel<BKV, KCH, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  GB_CUDA(launch_pdl(attn4_kernel<BKV, KCH, POLY>, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl_light(attn4_kernel<BKV, KCH, POLY>, grid, dim3(160), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -1517,7 +1517,7 @@ static int launch_attn3(const AttnParams& p, cudaStream_t stream) {
     GB_CUDA(cudaFuncSetAttribute(attn3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  GB_CUDA(launch_pdl(attn3_kernel, grid, dim3(160), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl_light(attn3_kernel, grid, dim3(160), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -1530,7 +1530,7 @@ static int launch_attn2(const AttnParams& p, cudaStream_t stream) {
     GB_CUDA(cudaFuncSetAttribute(attn2_kernel<HD_PAD, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  GB_CUDA(launch_pdl(attn2_kernel<HD_PAD, PT>, grid, dim3(128), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl_light(attn2_kernel<HD_PAD, PT>, grid, dim3(128), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -1544,7 +1544,7 @@ static int launch_attn(const AttnParams& p, cudaStream_t stream) {
                                  C::SMEM_BYTES));
   }
   dim3 grid((p.Lq + 127) / 128, p.H, p.B);
-  GB_CUDA(launch_pdl(attn_kernel<HD_PAD, BLOCK_KV>, grid, dim3(256), C::SMEM_BYTES, stream, p));
+  GB_CUDA(launch_pdl_light(attn_kernel<HD_PAD, BLOCK_KV>, grid, dim3(256), C::SMEM_BYTES, stream, p));
   GB_COUNT_LAUNCH(1);
   return 0;
 }

@@ -414,7 +414,7 @@ extern "C" int gillb200_gather_add_rows(const void* x, const void* table, const 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(table && idx && out && D % 8 == 0 && rows > 0, "gather_add_rows: bad args");
   GB_CHECK_ARG(dtype == DT_BF16 || dtype == DT_F16, "gather_add_rows: 16-bit only");
-  GB_CUDA(launch_pdl(gather_add_rows_kernel, dim3(grid_for(rows * (D / 8), 256)), dim3(256), 0, stream, 
+  GB_CUDA(launch_pdl_light(gather_add_rows_kernel, dim3(grid_for(rows * (D / 8), 256)), dim3(256), 0, stream, 
       reinterpret_cast<const uint16_t*>(x), reinterpret_cast<const uint16_t*>(table), idx, idx_offset, rows, D,
       dtype == DT_BF16, reinterpret_cast<uint16_t*>(out)));
   GB_COUNT_LAUNCH(1);
@@ -477,9 +477,9 @@ extern "C" int gillb200_tap_sum3x3(const float* y, long long ldy, int B, int H, 
   GB_CHECK_ARG(Cout != 4 || (ldy % 4 == 0 && reinterpret_cast<uintptr_t>(y) % 16 == 0), "tap_sum3x3: Cout 4 needs 16-byte rows");
   const long long n = static_cast<long long>(B) * H * W;
   const dim3 grid(static_cast<unsigned>((n + 255) / 256));
-  if (Cout == 3) GB_CUDA(launch_pdl(tap_sum3x3_kernel<3>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
-  else if (Cout == 4) GB_CUDA(launch_pdl(tap_sum3x3_kernel<4>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
-  else GB_CUDA(launch_pdl(tap_sum3x3_kernel<8>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
+  if (Cout == 3) GB_CUDA(launch_pdl_light(tap_sum3x3_kernel<3>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
+  else if (Cout == 4) GB_CUDA(launch_pdl_light(tap_sum3x3_kernel<4>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
+  else GB_CUDA(launch_pdl_light(tap_sum3x3_kernel<8>, grid, dim3(256), 0, stream, y, ldy, B, H, W, bias, out, out_dtype, ldo));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -488,7 +488,7 @@ extern "C" int gillb200_tap_sum3x3(const float* y, long long ldy, int B, int H, 
 extern "C" int gillb200_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && C % 8 == 0, "upsample2x: bad args");
-  GB_CUDA(launch_pdl(upsample2x_kernel, dim3(grid_for(4LL * B * H * W * (C / 8), 256)), dim3(256), 0, stream, 
+  GB_CUDA(launch_pdl_light(upsample2x_kernel, dim3(grid_for(4LL * B * H * W * (C / 8), 256)), dim3(256), 0, stream, 
       reinterpret_cast<const uint16_t*>(x), B, H, W, C, reinterpret_cast<uint16_t*>(out)));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -500,7 +500,7 @@ extern "C" int gillb200_im2col3x3(const void* x, int B, int H, int W, int C, int
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && (stride == 1 || stride == 2) && ld_out >= 9 * C, "im2col3x3: bad args");
   const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  GB_CUDA(launch_pdl(im2col3x3_kernel, dim3(grid_for(1LL * B * Ho * Wo * ld_out, 256)), dim3(256), 0, stream, 
+  GB_CUDA(launch_pdl_light(im2col3x3_kernel, dim3(grid_for(1LL * B * Ho * Wo * ld_out, 256)), dim3(256), 0, stream, 
       reinterpret_cast<const uint16_t*>(x), B, H, W, C, stride, Ho, Wo, reinterpret_cast<uint16_t*>(out), ld_out));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -513,7 +513,7 @@ extern "C" int gillb200_plms_step(const void* eps_pair, int eps_dtype, float gui
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(eps_pair && ets && latents && cur_sample && n > 0, "plms_step: null pointer");
   GB_CHECK_ARG(mode >= 0 && mode <= 4 && head >= 0 && head < 4, "plms_step: bad mode/head");
-  GB_CUDA(launch_pdl(plms_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, eps_pair, eps_dtype, guidance, ets, head, mode, c_sample,
+  GB_CUDA(launch_pdl_light(plms_step_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, eps_pair, eps_dtype, guidance, ets, head, mode, c_sample,
                                                          c_eps, latents, cur_sample, lat16_pair, lat16_dtype, n));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -524,7 +524,7 @@ extern "C" int gillb200_image_to_u8(const void* x, int dtype, long long pixels, 
                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && pixels > 0 && channels > 0 && ldx >= channels, "image_to_u8: bad args");
-  GB_CUDA(launch_pdl(image_to_u8_kernel, dim3(grid_for(pixels * channels, 256)), dim3(256), 0, stream, x, dtype, pixels, ldx, channels,
+  GB_CUDA(launch_pdl_light(image_to_u8_kernel, dim3(grid_for(pixels * channels, 256)), dim3(256), 0, stream, x, dtype, pixels, ldx, channels,
                                                                            reinterpret_cast<uint8_t*>(out)));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -535,7 +535,7 @@ extern "C" int gillb200_l2norm_rows(const float* x, long long ldx, int rows, int
                                     int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && rows > 0 && n > 0, "l2norm_rows: bad args");
-  GB_CUDA(launch_pdl(l2norm_rows_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, x, ldx, rows, n, out, ldo, out_dtype));
+  GB_CUDA(launch_pdl_light(l2norm_rows_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, x, ldx, rows, n, out, ldo, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -547,12 +547,12 @@ extern "C" int gillb200_cast_add(const void* x, int x_dtype, const void* y, int 
   GB_CHECK_ARG(x && out && n > 0, "cast_add: bad args");
   if (!y && x_dtype != DT_F32 && out_dtype == DT_BF16 && n % 8 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
       reinterpret_cast<uintptr_t>(out) % 16 == 0 && reinterpret_cast<uintptr_t>(out_lo) % 16 == 0) {
-    GB_CUDA(launch_pdl(cast_split8_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x),
+    GB_CUDA(launch_pdl_light(cast_split8_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, stream, reinterpret_cast<const uint4*>(x),
                        x_dtype == DT_BF16 ? 1 : 0, reinterpret_cast<uint4*>(out), reinterpret_cast<uint4*>(out_lo), n / 8));
     GB_COUNT_LAUNCH(1);
     return 0;
   }
-  GB_CUDA(launch_pdl(cast_add_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period));
+  GB_CUDA(launch_pdl_light(cast_add_kernel, dim3(grid_for(n, 256)), dim3(256), 0, stream, x, x_dtype, y, y_dtype, out, out_dtype, out_lo, n, y_period));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -571,7 +571,7 @@ extern "C" int gillb200_attn_small_f32(const float* q, long long ldq, long long 
   if (configured.need()) {
     GB_CUDA(cudaFuncSetAttribute(attn_small_f32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
-  GB_CUDA(launch_pdl(attn_small_f32_kernel<128>, dim3(dim3(H, B)), dim3(256), smem, stream, q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
+  GB_CUDA(launch_pdl_light(attn_small_f32_kernel<128>, dim3(dim3(H, B)), dim3(256), smem, stream, q, ldq, q_bs, k, ldk, k_bs, v, ldv, v_bs, Lq, Lk, scale,
                                                                   out, ldo, o_bs, out_dtype, out_lo));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -582,7 +582,7 @@ extern "C" int gillb200_channel_mix(const float* x, int cin, const float* w, con
                                     void* out, int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && w && b && out && cin >= 1 && cin <= 8 && cout >= 1 && cout <= 8 && n > 0, "channel_mix: bad args");
-  GB_CUDA(launch_pdl(channel_mix_kernel, dim3(grid_for(n * cout, 256)), dim3(256), 0, stream, x, cin, w, b, cout, n, out, out_dtype));
+  GB_CUDA(launch_pdl_light(channel_mix_kernel, dim3(grid_for(n * cout, 256)), dim3(256), 0, stream, x, cin, w, b, cout, n, out, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
@@ -598,7 +598,7 @@ extern "C" int gillb200_clip_preprocess_u8_crop(const void* img, int B, int H, i
   GB_CHECK_ARG(H <= 5 * RH && W <= 5 * RW, "clip_preprocess_u8: down-scaling factor above 5 (H=%d W=%d -> %d x %d)", H, W, RH,
                RW);
   GB_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "clip_preprocess_u8: bad out dtype");
-  GB_CUDA(launch_pdl(clip_preprocess_u8_kernel, dim3(grid_for(1LL * B * S * S, 128)), dim3(128), 0, stream,
+  GB_CUDA(launch_pdl_light(clip_preprocess_u8_kernel, dim3(grid_for(1LL * B * S * S, 128)), dim3(128), 0, stream,
                      reinterpret_cast<const uint8_t*>(img), B, H, W, RH, RW, top, left, S, mean3[0], mean3[1], mean3[2],
                      std3[0], std3[1], std3[2], out, out_dtype, reinterpret_cast<uint8_t*>(resized_u8)));
   GB_COUNT_LAUNCH(1);

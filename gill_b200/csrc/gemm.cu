@@ -84,6 +84,15 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+bool pdl_light_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GILLB200_PDL_LIGHT");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
+
 int num_sms() {
   static int n[64] = {};
   int dev = 0;

@@ -70,6 +70,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Same, for the kernels around the GEMMs (norms, attention, elementwise): GILLB200_PDL_LIGHT=1 gives only THEM the
+// programmatic-launch attribute -- the GEMM / conv launches (stream-K flags) stay fully serialised.
+bool pdl_light_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_light(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() || pdl_light_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)
 extern long long g_launch_count;
 #define GB_COUNT_LAUNCH(n) (gb::g_launch_count += (n))

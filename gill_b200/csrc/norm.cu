@@ -820,27 +820,27 @@ extern "C" int gillb200_layernorm(const void* x, long long ldx, int in_dtype, co
       const int nblk = (rows + 4 * (32 / lpr) - 1) / (4 * (32 / lpr));
       const int grid = nblk < 5 * num_sms() ? nblk : 5 * num_sms();  // 94 registers: 5 resident CTAs per SM
       if (lpr == 8)
-        GB_CUDA(launch_pdl(layernorm_sub16_kernel<8, 5>, dim3(grid), dim3(128), 0, stream, xi, ldx, in_dtype, w, b, eps, rows, C, oo, ldo, out_dtype));
+        GB_CUDA(launch_pdl_light(layernorm_sub16_kernel<8, 5>, dim3(grid), dim3(128), 0, stream, xi, ldx, in_dtype, w, b, eps, rows, C, oo, ldo, out_dtype));
       else if (lpr == 16)
-        GB_CUDA(launch_pdl(layernorm_sub16_kernel<16, 5>, dim3(grid), dim3(128), 0, stream, xi, ldx, in_dtype, w, b, eps, rows, C, oo, ldo, out_dtype));
+        GB_CUDA(launch_pdl_light(layernorm_sub16_kernel<16, 5>, dim3(grid), dim3(128), 0, stream, xi, ldx, in_dtype, w, b, eps, rows, C, oo, ldo, out_dtype));
       else
-        GB_CUDA(launch_pdl(layernorm_sub16_kernel<32, 5>, dim3(grid), dim3(128), 0, stream, xi, ldx, in_dtype, w, b, eps, rows, C, oo, ldo, out_dtype));
+        GB_CUDA(launch_pdl_light(layernorm_sub16_kernel<32, 5>, dim3(grid), dim3(128), 0, stream, xi, ldx, in_dtype, w, b, eps, rows, C, oo, ldo, out_dtype));
       GB_COUNT_LAUNCH(1);
       GB_CUDA(cudaGetLastError());
       return 0;
     }
   }
   if (C <= 320) {
-    GB_CUDA(launch_pdl(layernorm_sub_kernel<8, 5>, dim3((rows + 15) / 16), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+    GB_CUDA(launch_pdl_light(layernorm_sub_kernel<8, 5>, dim3((rows + 15) / 16), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
                                                                      out_dtype, out_lo));
   } else if (C <= 640) {
-    GB_CUDA(launch_pdl(layernorm_sub_kernel<16, 5>, dim3((rows + 7) / 8), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+    GB_CUDA(launch_pdl_light(layernorm_sub_kernel<16, 5>, dim3((rows + 7) / 8), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
                                                                     out_dtype, out_lo));
   } else if (C <= 1280) {
-    GB_CUDA(launch_pdl(layernorm_sub_kernel<32, 5>, dim3((rows + 3) / 4), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
+    GB_CUDA(launch_pdl_light(layernorm_sub_kernel<32, 5>, dim3((rows + 3) / 4), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo,
                                                                     out_dtype, out_lo));
   } else {
-    GB_CUDA(launch_pdl(layernorm_kernel<4, 5>, dim3(rows), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
+    GB_CUDA(launch_pdl_light(layernorm_kernel<4, 5>, dim3(rows), dim3(128), 0, stream, x, ldx, in_dtype, w, b, eps, rows, C, out, ldo, out_dtype,
                                                       out_lo));
   }
   GB_COUNT_LAUNCH(1);
@@ -882,7 +882,7 @@ static int launch_gn_apply(const GnSrc& src, int dtype, int B, int HW, const flo
       per = (per + unit - 1) / unit * unit;
     }
     const int blocks = static_cast<int>((total + per - 1) / per);
-    GB_CUDA(launch_pdl(gn_apply2_kernel<UNR>, dim3(blocks, B), dim3(256), static_cast<size_t>(2 * C) * sizeof(float), stream,
+    GB_CUDA(launch_pdl_light(gn_apply2_kernel<UNR>, dim3(blocks, B), dim3(256), static_cast<size_t>(2 * C) * sizeof(float), stream,
                        src, dtype, HW, scale_shift, silu, out, out_dtype, per));
     GB_COUNT_LAUNCH(1);
     return 0;
@@ -894,7 +894,7 @@ static int launch_gn_apply(const GnSrc& src, int dtype, int B, int HW, const flo
   if (pix_per_block * want_blocks > HW) pix_per_block = (HW + want_blocks - 1) / want_blocks;
   pix_per_block = ((pix_per_block + 4 * sgs - 1) / (4 * sgs)) * (4 * sgs);
   const int blocks = (HW + pix_per_block - 1) / pix_per_block;
-  GB_CUDA(launch_pdl(gn_apply_kernel, dim3(blocks, B), dim3(256), 0, stream, src, dtype, HW, scale_shift, silu, out, out_dtype,
+  GB_CUDA(launch_pdl_light(gn_apply_kernel, dim3(blocks, B), dim3(256), 0, stream, src, dtype, HW, scale_shift, silu, out, out_dtype,
                      pix_per_block));
   GB_COUNT_LAUNCH(1);
   return 0;
@@ -928,7 +928,7 @@ extern "C" int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1
   float* scale_shift = partial + 128LL * B * G * 2;
   const int nvec = C / 8;
   const size_t smem_stats = static_cast<size_t>(nvec >= 256 ? 1 : 256 / nvec) * 2 * C * sizeof(float);
-  GB_CUDA(launch_pdl(gn_stats_kernel, dim3(dim3(chunks, B)), dim3(256), smem_stats, stream, src, dtype, HW, G, chunks, partial, counters, w, b, eps,
+  GB_CUDA(launch_pdl_light(gn_stats_kernel, dim3(dim3(chunks, B)), dim3(256), smem_stats, stream, src, dtype, HW, G, chunks, partial, counters, w, b, eps,
                                                                scale_shift));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
@@ -973,7 +973,7 @@ extern "C" int gillb200_groupnorm_from_stats(const void* x0, int C0, const void*
       if (pchunks < 1) pchunks = 1;
       const int ppc = (HW + pchunks - 1) / pchunks;
       pchunks = (HW + ppc - 1) / ppc;
-      GB_CUDA(launch_pdl(gn_fused_kernel<UNR>, dim3(nblk * pchunks, B), dim3(256), static_cast<size_t>(2 * CB) * sizeof(float),
+      GB_CUDA(launch_pdl_light(gn_fused_kernel<UNR>, dim3(nblk * pchunks, B), dim3(256), static_cast<size_t>(2 * CB) * sizeof(float),
                          stream, src, reinterpret_cast<const float2*>(stats0), reinterpret_cast<const float2*>(stats1), dtype, HW,
                          G, CB, ppc, w, b, eps, silu, out, out_dtype));
       GB_COUNT_LAUNCH(1);
@@ -982,7 +982,7 @@ extern "C" int gillb200_groupnorm_from_stats(const void* x0, int C0, const void*
   }
   float* partial = reinterpret_cast<float*>(workspace) + 1024;
   float* scale_shift = partial + 128LL * B * G * 2;  // same workspace layout as gillb200_groupnorm
-  GB_CUDA(launch_pdl(gn_finalize_stats_kernel, dim3(G, B), dim3(128), 0, stream, reinterpret_cast<const float2*>(stats0), C0,
+  GB_CUDA(launch_pdl_light(gn_finalize_stats_kernel, dim3(G, B), dim3(128), 0, stream, reinterpret_cast<const float2*>(stats0), C0,
                      reinterpret_cast<const float2*>(stats1), C1, HW / 32, G, HW, w, b, eps, scale_shift));
   GB_COUNT_LAUNCH(1);
   return launch_gn_apply(src, dtype, B, HW, scale_shift, silu, out, out_dtype, stream);
@@ -993,7 +993,7 @@ extern "C" int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype,
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GB_CHECK_ARG(x && out && n % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0, "softmax_rows: n, ldx, ldo multiples of 8");
   GB_CHECK_ARG(rows > 0 && rows < (1LL << 31), "softmax_rows: bad row count");
-  GB_CUDA(launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, x, ldx, in_dtype, scale, n, out, ldo, out_dtype));
+  GB_CUDA(launch_pdl_light(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, x, ldx, in_dtype, scale, n, out, ldo, out_dtype));
   GB_COUNT_LAUNCH(1);
   GB_CUDA(cudaGetLastError());
   return 0;
