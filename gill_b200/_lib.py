@@ -43,6 +43,7 @@ class GemmArgs(ctypes.Structure):
         ("stats_out", _c_void_p),
         ("rowstats_out", _c_void_p), ("ln_stats", _c_void_p), ("ln_cs", _c_void_p), ("ln_C", _c_int), ("ln_eps", _c_float),
         ("conv_stride", _c_int),
+        ("conv_phase", _c_int),
     ]
 
 

@@ -306,7 +306,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
     GB_CHECK_ARG(a->conv_H % cs == 0 && a->conv_W % cs == 0, "conv3x3: H, W must be multiples of the stride");
     const int W = a->conv_W / cs, H = a->conv_H / cs;  // OUTPUT size: an M tile is a box of output pixels
     GB_CHECK_ARG(a->M == a->conv_B * H * W, "conv3x3: M != B*Ho*Wo");
-    GB_CHECK_ARG(a->K == 9 * a->conv_C, "conv3x3: K != 9*C");
+    GB_CHECK_ARG(a->conv_phase >= 0 && a->conv_phase <= 4, "conv3x3: conv_phase must be 0..4");
+    GB_CHECK_ARG(a->K == (a->conv_phase ? 4 : 9) * a->conv_C, "conv3x3: K != %d*C", a->conv_phase ? 4 : 9);
+    GB_CHECK_ARG(!a->conv_phase || (cs == 1 && a->a2_mode == 0 && !a->residual && !a->rowbias && !a->out_lo && a->ldo == a->N &&
+                                    a->act == ACT_NONE),
+                 "conv_phase: stride 1, no second A source / residual / row bias / activation, ldo == N");
     int bw, bh, bb;
     if (W >= 128) {
       GB_CHECK_ARG(W % 128 == 0, "conv3x3: W=%d must be a multiple of 128 when >= 128", W);
@@ -333,7 +337,11 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
     p.conv_cblocks = a->conv_C / BLOCK_K;
     p.conv_W = W;
     p.conv_H = H;
-    kb_main = 9 * p.conv_cblocks;
+    p.conv_nt = a->conv_phase ? 4 : 9;
+    p.conv_ntx = a->conv_phase ? 2 : 3;
+    p.conv_pa = a->conv_phase ? (a->conv_phase - 1) / 2 : 0;
+    p.conv_pb = a->conv_phase ? (a->conv_phase - 1) % 2 : 0;
+    kb_main = p.conv_nt * p.conv_cblocks;
   } else {
     GB_CHECK_ARG(a->lda % 8 == 0, "lda=%lld must be a multiple of 8 elements", a->lda);
     const uint64_t dims[2] = {(uint64_t)a->K, (uint64_t)a->M};
@@ -371,6 +379,12 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
   }
 
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, p.num_k_blocks);
+  if (a->conv3x3 && a->conv_phase) {
+    // upsample-fused phase launch: only the halo-tile pair kernel implements the collapsed tap walk and the strided output
+    GB_CHECK_ARG(conv_halo_enabled() && a->conv_W % 16 == 0 && a->conv_H % 16 == 0 && a->M % 256 == 0 && a->out_dtype != DT_F32,
+                 "conv_phase needs the halo-tile kernel: H, W multiples of 16, M %% 256 == 0, 16-bit output");
+    if (!a->block_n) bn = a->N % 320 == 0 ? (a->conv_C <= 640 ? 160 : 320) : a->N % 256 == 0 ? 256 : 128;
+  }
   if (a->act == ACT_GEGLU) {
     GB_CHECK_ARG(a->N % 2 == 0, "GEGLU needs even N");
     // the smem-staged epilogue emits 32-column output panels = 64 accumulator columns under GEGLU
@@ -400,8 +414,9 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       want_sk = static_cast<double>(tiles) / static_cast<double>(waves * num_sms()) < 0.8;
     }
   }
+  if (a->conv3x3 && a->conv_phase) want_sk = false;
   bool pair = false;
-  if (a->cta_pair == 2) {
+  if (a->cta_pair == 2 || (a->conv3x3 && a->conv_phase)) {
     pair = true;
   } else if (!want_sk && a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
     // measured (tools/gpu_sweep_shapes.py, with the staged epilogue): the pair kernel wins 3..8 % from 10 k-blocks up
@@ -699,9 +714,17 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       {
         const uint64_t dims[3] = {(uint64_t)n_out, (uint64_t)a->conv_W, (uint64_t)a->conv_B * a->conv_H};
         const uint32_t box[3] = {EPI_PANEL_COLS, 8, 4};
-        const uint64_t so[2] = {(uint64_t)a->ldo * esz, (uint64_t)a->conv_W * a->ldo * esz};
-        int r = encode_tmap(&p.tma_out, a->out, a->out_dtype, 3, dims, so, box, esz == 4 ? 128 : 64, nullptr);
+        // phase launch: this launch owns pixels (2i + pa, 2j + pb) of the full-resolution [B, 2H, 2W, N] tensor
+        const uint64_t ps = a->conv_phase ? 2 : 1;
+        const uint64_t so[2] = {ps * a->ldo * esz, ps * ps * a->conv_W * a->ldo * esz};
+        char* obase = reinterpret_cast<char*>(a->out) +
+                      (a->conv_phase ? (static_cast<uint64_t>(p.conv_pa) * 2 * a->conv_W + p.conv_pb) * a->ldo * esz : 0);
+        int r = encode_tmap(&p.tma_out, obase, a->out_dtype, 3, dims, so, box, esz == 4 ? 128 : 64, nullptr);
         if (r) return r;
+        if (a->conv_phase) {
+          p.stats_hw = a->conv_H * a->conv_W;
+          p.stats_phase = a->conv_phase - 1;
+        }
         if (a->residual) {
           const uint64_t sr[2] = {(uint64_t)a->ldr * esz, (uint64_t)a->conv_W * a->ldr * esz};
           r = encode_tmap(&p.tma_res, a->residual, a->res_dtype, 3, dims, sr, box, esz == 4 ? 128 : 64, nullptr);
@@ -719,6 +742,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
   }
   if (p.debug_mode == 3 && a->sk_workspace && p.sk_per == 0)  // wait-time trace of CTA 0 (measurement aid, see gemm_mma)
     p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->sk_workspace) + SK_FLAG_BYTES);
+  GB_CHECK_ARG(!(a->conv3x3 && a->conv_phase), "conv_phase: shape does not qualify for the halo-tile pair kernel (bn=%d)", bn);
   if (pair) {
     switch (bn) {
       case 64: return launch_gemm2<64>(p, stream);

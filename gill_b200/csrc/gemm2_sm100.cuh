@@ -183,7 +183,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           __syncwarp();
           hb ^= 1;
           if (hb == 0) hphase ^= 1;
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < p.conv_nt; ++tap) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sb = smem_tiles + stage * RING_STAGE;
             const uint32_t full_leader = mapa_u32(smem_u32(&bars->full[stage]), 0);
@@ -276,14 +276,15 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(&bars->halo_full[hb], hphase);
           tc_fence_after();
           const uint64_t dh = dh0 + static_cast<uint64_t>(hb) * (HALO_BYTES >> 4);
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < p.conv_nt; ++tap) {
             if (!ready) mbar_wait(&bars->full[stage], phase);
             tc_fence_after();
             const bool wrap = stage + 1 == p.num_stages;
             const int nstage = wrap ? 0 : stage + 1;
             const uint32_t nphase = wrap ? phase ^ 1 : phase;
             ready = mbar_test_wait(&bars->full[nstage], nphase);
-            const uint64_t da = dh + static_cast<uint64_t>((tap / 3) * 10 + tap % 3) * (128 >> 4);
+            const uint64_t da =
+                dh + static_cast<uint64_t>((p.conv_pa + tap / p.conv_ntx) * 10 + p.conv_pb + tap % p.conv_ntx) * (128 >> 4);
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -292,7 +293,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
                   umma2_f16(tmem_d + C::MMA_N, da + 2 * k, db + SUB_STEP + 2 * k, idesc, (cb | tap | k) != 0 ? 1u : 0u);
               }
               umma2_commit_mcast(&bars->empty[stage], 0b11);
-              if (tap == 8) umma2_commit_mcast(&bars->halo_empty[hb], 0b11);  // every tap of this halo tile has been read
+              if (tap == p.conv_nt - 1) umma2_commit_mcast(&bars->halo_empty[hb], 0b11);  // every tap of this halo tile has been read
             }
             __syncwarp();
             db = wrap ? db0 : db + DESC_STEP;

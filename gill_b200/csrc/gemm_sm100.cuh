@@ -64,6 +64,13 @@ struct alignas(64) GemmParams {
   int conv_cblocks;  // Cin / 64
   int conv_W, conv_H;  // OUTPUT width / height (= input size / conv_stride)
   int conv_stride;     // 1, or 2: the tensor map walks the input with element strides {1,2,2,1} (no im2col buffer)
+  // A_CONV3X3_HALO tap walk: conv_nt taps per channel block; tap t reads the halo tile shifted by
+  // (conv_pa + t / conv_ntx) rows and (conv_pb + t % conv_ntx) pixels. 3x3: nt 9, ntx 3, pa = pb = 0. Phase (a, b) of an
+  // upsample-fused conv (gillb200_gemm_args::conv_phase): nt 4, ntx 2, pa = a, pb = b.
+  int conv_nt, conv_ntx, conv_pa, conv_pb;
+  // stats_out slab remap for phase launches: rows [b * stats_hw, (b + 1) * stats_hw) of this launch are sample b's; its
+  // slabs go to ((b * 4 + stats_phase) * stats_hw + r) / 32 of the full-resolution tensor's buffer. 0: slab = row / 32.
+  int stats_hw, stats_phase;
   // epilogue
   void* out;
   void* out_lo;  // optional bf16 "lo" residue: out_lo = bf16(v - float(bf16(v)))   (split-precision activations)
@@ -1104,8 +1111,12 @@ __device__ __forceinline__ void epilogue_warp_tma(const GemmParams& p, GemmSmemB
           cs += xv;
           cq = fmaf(xv, xv, cq);
         }
-        p.stats_out[static_cast<size_t>(row0 >> 5) * n_out_total + (no0 + pnl * EPI_PANEL_COLS + lane)] =
-            make_float2(cs, cq);
+        size_t slab = static_cast<size_t>(row0 >> 5);
+        if (p.stats_hw) {
+          const int sb = row0 / p.stats_hw;
+          slab = (static_cast<size_t>(sb * 4 + p.stats_phase) * p.stats_hw + (row0 - sb * p.stats_hw)) >> 5;
+        }
+        p.stats_out[slab * n_out_total + (no0 + pnl * EPI_PANEL_COLS + lane)] = make_float2(cs, cq);
       }
       if (trace) tr_t0 = clock64();
       if (VAR != EV_GENERIC && p.epi_stg && !halo) {

@@ -495,6 +495,63 @@ def gather_add_rows(table: torch.Tensor, idx: torch.Tensor, x: Optional[torch.Te
     return out
 
 
+def conv3x3_up2_weights(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, 9*C] conv weight (k = (ky*3+kx)*C + c) -> [4, Cout, 4*C]: the pre-summed 2 x 2 kernels of the four output
+    phases of `conv3x3(upsample2x(x))` (see conv3x3_up2). Phase (a, b), low-res offset (a - 1 + u, b - 1 + v):
+    rows ky in {0} / {1, 2} (a = 0; u = 0 / 1) or {0, 1} / {2} (a = 1), columns likewise; summed in fp32, rounded once."""
+    cout, C = w.shape[0], w.shape[1] // 9
+    w9 = w.float().view(cout, 3, 3, C)
+    sel = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
+    out = torch.zeros((4, cout, 4, C), dtype=torch.float32, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for u in (0, 1):
+                for v in (0, 1):
+                    out[a * 2 + b, :, u * 2 + v] = sum(w9[:, ky, kx] for ky in sel[(a, u)] for kx in sel[(b, v)])
+    return out.view(4, cout, 4 * C).to(w.dtype).contiguous()
+
+
+def conv3x3_up2_supported(x: torch.Tensor) -> bool:
+    """Shapes the halo-tile phase launches cover (gillb200_gemm_args::conv_phase)."""
+    B, H, W, C = x.shape
+    return x.is_cuda and x.dtype != torch.float32 and H % 16 == 0 and W % 16 == 0 and C % 64 == 0 and (B * H * W) % 256 == 0 \
+        and B * H * W >= 4096
+
+
+def conv3x3_up2(x: torch.Tensor, w_up2: torch.Tensor, *, bias: Optional[torch.Tensor] = None, stats: bool = False,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`conv3x3(upsample2x(x), w)` (nearest 2x, then 3x3 / pad 1) WITHOUT the upsampled tensor and with 4/9 of the flops:
+    output pixel (2i+a, 2j+b) only sees the 2 x 2 low-res pixels (i+a-1 .. i+a, j+b-1 .. j+b), so each of the four output
+    phases is a 2 x 2 convolution of the low-res input with pre-summed weights (conv3x3_up2_weights). Four launches of the
+    halo-tile implicit-GEMM kernel, each writing its quarter of the NHWC output through a strided tensor map.
+    x NHWC [B,H,W,C] -> NHWC [B,2H,2W,Cout]; with stats=True the output carries `.gn_stats` like conv3x3."""
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and w_up2.dim() == 3 and w_up2.shape[0] == 4 and w_up2.shape[2] == 4 * C and w_up2.is_contiguous()
+    N = w_up2.shape[1]
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, N), device=x.device, dtype=x.dtype)
+    assert out.is_contiguous() and out.shape == (B, 2 * H, 2 * W, N)
+    st = torch.empty((4 * B * H * W // 32, N, 2), device=x.device, dtype=torch.float32) if stats else None
+    with _P("conv3x3_up2", 2.0 * 4 * B * H * W * N * 4 * C, 2.0 * (B * H * W * C + 4 * N * 4 * C + 4 * B * H * W * N),
+            f"B{B} {H}x{W}->{2 * H}x{2 * W} C{C}->{N}"):
+        for ph in range(4):
+            g = GemmArgs()
+            g.a, g.lda = x.data_ptr(), C
+            g.conv3x3, g.conv_B, g.conv_H, g.conv_W, g.conv_C, g.conv_stride, g.conv_phase = 1, B, H, W, C, 1, ph + 1
+            g.b, g.ldb = w_up2[ph].data_ptr(), w_up2.stride(1)
+            g.M, g.N, g.K = B * H * W, N, 4 * C
+            g.in_dtype = _DT[x.dtype]
+            g.out, g.ldo, g.out_dtype = out.data_ptr(), N, _DT[out.dtype]
+            g.bias = bias.data_ptr() if bias is not None else (_zero_bias_ptr(x.device, N) or None)
+            g.act, g.alpha, g.stream_k = ACT_NONE, 1.0, 1
+            if st is not None:
+                g.stats_out = st.data_ptr()
+            check(lib().gillb200_gemm(ctypes.byref(g), _stream()), "gillb200_gemm(conv3x3 up2 phase)")
+    if st is not None:
+        out.gn_stats = st
+    return out
+
+
 def conv3x3_taps_weight(w: torch.Tensor, cout: int, pad_to: int = 16) -> torch.Tensor:
     """[Cout(+pad), 9*C] conv weight (k = tap*C + c) -> per-tap GEMM weight [9*cout (padded to a multiple of pad_to), C] with
     row tap*cout + o = W[o, tap*C : (tap+1)*C] (see conv3x3_narrow)."""

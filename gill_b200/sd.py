@@ -29,6 +29,16 @@ SD = Dict[str, torch.Tensor]
 # conv_out (320 -> 4 in the UNet, 128 -> 3 in the VAE) as a plain GEMM onto per-tap products + shifted sum; "0": the implicit
 # 3x3 conv through a 32-column tile (A/B aid)
 NARROW_CONV_OUT = os.environ.get("GILLB200_NARROW_CONV_OUT", "1") != "0"
+# up blocks: `conv3x3(upsample2x(h))` as four 2 x 2 phase convolutions of the low-res tensor (ops.conv3x3_up2); "0": upsample
+# kernel + 3x3 conv on the 4x larger tensor (A/B aid)
+FUSED_UPSAMPLE = os.environ.get("GILLB200_FUSED_UPSAMPLE", "1") != "0"
+
+
+def _upsample_conv(h, w, p, stats=True):
+    """Upsample2D of diffusers (nearest 2x + 3x3 conv): fused phase form when the shape qualifies."""
+    if FUSED_UPSAMPLE and (p + ".weight_up2") in w and ops.conv3x3_up2_supported(h):
+        return ops.conv3x3_up2(h, w[p + ".weight_up2"], bias=w[p + ".bias"], stats=stats)
+    return ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=stats)
 
 UNET_CFG = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
                 cross_attention_dim=768, heads=8, norm_groups=32, has_attn_down=(True, True, True, False),
@@ -240,6 +250,7 @@ class UNetB200:
             if i < len(boc) - 1:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
                 self._put(p + ".weight", _conv_w(sd[p + ".weight"], self.dt))
+                self._put(p + ".weight_up2", ops.conv3x3_up2_weights(_conv_w(sd[p + ".weight"], torch.float32)))
                 self._put(p + ".bias", sd[p + ".bias"], f32)
         self._put("conv_norm_out.weight", sd["conv_norm_out.weight"], f32)
         self._put("conv_norm_out.bias", sd["conv_norm_out.bias"], f32)
@@ -440,8 +451,7 @@ class UNetB200:
                 if cfg["has_attn_up"][i]:
                     h = self._transformer(h, f"up_blocks.{i}.attentions.{j}", ctx_kv)
             if i < len(boc) - 1:
-                p = f"up_blocks.{i}.upsamplers.0.conv"
-                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=True)
+                h = _upsample_conv(h, w, f"up_blocks.{i}.upsamplers.0.conv")
         n = ops.groupnorm(h, w["conv_norm_out.weight"], w["conv_norm_out.bias"], self.G, 1e-5, silu=True)
         if NARROW_CONV_OUT:
             return ops.conv3x3_narrow(n, w["conv_out.taps"], w["conv_out.bias"].numel(), bias=w["conv_out.bias"])
@@ -463,6 +473,9 @@ class VAEDecoderB200:
                 self.w[k] = v.reshape(v.shape[0], v.shape[1]).to(self.dev, dtype).contiguous()
             elif v.dim() == 4:
                 self.w[k] = _conv_w(v, dtype).to(self.dev)
+                if "upsamplers" in k and k.endswith("conv.weight"):   # pre-summed phase kernels of the fused upsample conv
+                    self.w[k[: -len("weight")] + "weight_up2"] = \
+                        ops.conv3x3_up2_weights(_conv_w(v, f32).to(self.dev)).to(dtype).contiguous()
             elif v.dim() == 2:
                 self.w[k] = v.to(self.dev, dtype).contiguous()
             else:
@@ -538,8 +551,7 @@ class VAEDecoderB200:
             for j in range(cfg["layers_per_block"] + 1):
                 h = self._resnet(h, f"decoder.up_blocks.{i}.resnets.{j}")
             if i < len(boc) - 1:
-                p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                h = ops.conv3x3(ops.upsample2x(h), w[p + ".weight"], bias=w[p + ".bias"], stats=True)
+                h = _upsample_conv(h, w, f"decoder.up_blocks.{i}.upsamplers.0.conv")
         n = ops.groupnorm(h, w["decoder.conv_norm_out.weight"], w["decoder.conv_norm_out.bias"], self.G, 1e-6,
                           silu=True)
         if NARROW_CONV_OUT:

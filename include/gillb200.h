@@ -105,6 +105,16 @@ typedef struct gillb200_gemm_args {
   float ln_eps;
   int conv_stride; /* conv3x3 only: 0/1 = stride 1; 2 = stride 2 (conv_H/conv_W stay the INPUT size, M = B*(H/2)*(W/2));
                     * the A tensor map then walks the input with TMA element strides, no im2col buffer */
+  int conv_phase;  /* conv3x3 only, 0 = plain. 1..4 = phase (a, b) = ((conv_phase - 1) / 2, (conv_phase - 1) % 2) of
+                    * "nearest-neighbour 2x upsample, then 3x3 / pad 1 convolution" (UNet / VAE up blocks, diffusers
+                    * Upsample2D behind gill/custom_sd.py:633 and :387) computed on the LOW-RESOLUTION input: output pixel
+                    * (2i + a, 2j + b) only ever sees the 2 x 2 low-res pixels (i + a - 1 .. i + a, j + b - 1 .. j + b), so
+                    * the nine taps collapse to four with pre-summed weights -- 4/9 of the flops and no upsampled tensor.
+                    * a = NHWC [conv_B, conv_H, conv_W, conv_C] (low resolution), b = [N, 4 * conv_C] with
+                    * k = (u * 2 + v) * C + c for low-res offset (a - 1 + u, b - 1 + v), M = B*H*W, K = 4*C,
+                    * out = BASE of the full-resolution NHWC tensor [conv_B, 2*conv_H, 2*conv_W, N] (ldo = N): the launch writes
+                    * its quarter of the pixels. stats_out (optional) = the full-resolution tensor's [4*M/32, N, 2] buffer.
+                    * Needs the halo-tile CTA-pair kernel: conv_H, conv_W multiples of 16, M % 256 == 0, >= 55 pair tiles. */
 } gillb200_gemm_args;
 
 long long gillb200_gemm_streamk_workspace_bytes(void);

@@ -726,3 +726,32 @@ def test_conv3x3_halo_tile(ops, case):
         gn = ops.groupnorm(got, w2, b2, 32, 1e-5, silu=True)
         gref = F.silu(F.group_norm(got.permute(0, 3, 1, 2).float(), 32, w2, b2, 1e-5)).permute(0, 2, 3, 1)
         assert rel(gn, gref) < 2e-3
+
+
+@pytest.mark.parametrize("case", [(16, 16, 16, 128, 320, True), (4, 48, 32, 64, 128, False), (4, 32, 32, 192, 640, True),
+                                  (1, 64, 64, 64, 256, True)])
+def test_conv3x3_up2_equals_upsample_then_conv(ops, case):
+    """Nearest 2x upsample + 3x3 conv as four 2 x 2 phase convolutions of the low-res tensor (pre-summed weights, halo-tile
+    kernel, strided output maps, remapped GroupNorm-statistics slabs) == F.conv2d(F.interpolate(x, 2x nearest))."""
+    B, H, W, C, Co, stats = case
+    torch.manual_seed(8)
+    x = torch.randn(B, H, W, C, device=dev).half()
+    w4 = (torch.randn(Co, C, 3, 3, device=dev) / (3 * C ** 0.5)).half()
+    bias = torch.randn(Co, device=dev)
+    wk = w4.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    assert ops.conv3x3_up2_supported(x)
+    got = ops.conv3x3_up2(x, ops.conv3x3_up2_weights(wk), bias=bias, stats=stats)
+    up = F.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w4.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert got.shape == ref.shape and got.dtype == torch.float16
+    assert rel(got, ref) < 2e-3
+    two = ops.conv3x3(ops.upsample2x(x), wk, bias=bias)
+    assert rel(got, two) < 2e-3
+    if stats:
+        st = got.gn_stats.view(B, 4 * H * W // 32, Co, 2).sum(1)
+        g = got.float().view(B, 4 * H * W, Co)
+        assert rel(st[..., 0], g.sum(1)) < 1e-3 and rel(st[..., 1], (g * g).sum(1)) < 1e-3
+        w2, b2 = torch.randn(Co, device=dev), torch.randn(Co, device=dev)
+        gn = ops.groupnorm(got, w2, b2, 32, 1e-5, silu=True)
+        gref = F.silu(F.group_norm(got.permute(0, 3, 1, 2).float(), 32, w2, b2, 1e-5)).permute(0, 2, 3, 1)
+        assert rel(gn, gref) < 2e-3
