@@ -44,6 +44,7 @@ class GemmArgs(ctypes.Structure):
         ("rowstats_out", _c_void_p), ("ln_stats", _c_void_p), ("ln_cs", _c_void_p), ("ln_C", _c_int), ("ln_eps", _c_float),
         ("conv_stride", _c_int),
         ("conv_phase", _c_int),
+        ("gn_scale_shift", _c_void_p), ("gn_silu", _c_int), ("a_cat", _c_void_p), ("a_cat_C", _c_int),
     ]
 
 

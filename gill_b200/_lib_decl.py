@@ -21,6 +21,7 @@ def declare(L):
     d("gillb200_groupnorm_workspace_bytes", ci, ci, restype=cll)
     d("gillb200_groupnorm", vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, cf, ci, vp, ci, vp, vp)
     d("gillb200_groupnorm_from_stats", vp, ci, vp, vp, ci, vp, ci, ci, ci, ci, vp, vp, cf, ci, vp, ci, vp, vp)
+    d("gillb200_groupnorm_scale_shift", ci, vp, ci, vp, ci, ci, ci, vp, vp, cf, vp, vp)
     d("gillb200_softmax_rows", vp, cll, ci, cf, cll, ci, vp, cll, ci, vp)
     d("gillb200_gather_add_rows", vp, vp, vp, cll, cll, ci, ci, vp, vp)
     d("gillb200_upsample2x", vp, ci, ci, ci, ci, vp, vp)

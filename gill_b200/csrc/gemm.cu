@@ -151,21 +151,21 @@ static int launch_gemm(GemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-template <int BN, bool HALO = false>
+template <int BN, bool HALO = false, bool GN = false>
 static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
   using C = Gemm2Cfg<BN>;
   static PerDeviceOnce configured;
   if (configured.need()) {
-    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
+    GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, HALO, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
   }
   // halo mode: two resident halo-tile slots in front of a ring of B half-tiles (8 stages at most: the barrier block)
-  const int smem_bytes = HALO ? plan_smem(p, C::B_BYTES, 8, C::HALO_RES) : plan_smem(p, C::STAGE_BYTES, C::STAGES);
+  const int smem_bytes = HALO ? plan_smem(p, C::B_BYTES, 8, GN ? C::HALO_RES_GN : C::HALO_RES) : plan_smem(p, C::STAGE_BYTES, C::STAGES);
   GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (pair, BN=%d)", BN);
   const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_n = (p.N + BN - 1) / BN;
   const int tiles = num_m2 * num_n;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  GB_CUDA(launch_pdl(gemm2_kernel<BN, HALO>, dim3(2 * pairs), dim3(GEMM_THREADS), smem_bytes, stream, p));  // cluster (2,1,1)
+  GB_CUDA(launch_pdl(gemm2_kernel<BN, HALO, GN>, dim3(2 * pairs), dim3(GEMM_THREADS), smem_bytes, stream, p));  // cluster (2,1,1)
   GB_COUNT_LAUNCH(1);
   return 0;
 }
@@ -307,6 +307,12 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
     const int W = a->conv_W / cs, H = a->conv_H / cs;  // OUTPUT size: an M tile is a box of output pixels
     GB_CHECK_ARG(a->M == a->conv_B * H * W, "conv3x3: M != B*Ho*Wo");
     GB_CHECK_ARG(a->conv_phase >= 0 && a->conv_phase <= 4, "conv3x3: conv_phase must be 0..4");
+    GB_CHECK_ARG(!a->a_cat || (a->gn_scale_shift && a->a_cat_C > 0 && a->a_cat_C < a->conv_C && a->a_cat_C % BLOCK_K == 0 &&
+                               (a->conv_C - a->a_cat_C) % BLOCK_K == 0),
+                 "a_cat: needs gn_scale_shift and channel counts that are multiples of 64 (conv_C=%d a_cat_C=%d)", a->conv_C,
+                 a->a_cat_C);
+    GB_CHECK_ARG(!a->gn_scale_shift || (cs == 1 && a->a2_mode == 0 && a->conv_phase == 0),
+                 "gn_scale_shift: stride-1 3x3 convs without a K-concatenated second A source");
     GB_CHECK_ARG(a->K == (a->conv_phase ? 4 : 9) * a->conv_C, "conv3x3: K != %d*C", a->conv_phase ? 4 : 9);
     GB_CHECK_ARG(!a->conv_phase || (cs == 1 && a->a2_mode == 0 && !a->residual && !a->rowbias && !a->out_lo && a->ldo == a->N &&
                                     a->act == ACT_NONE),
@@ -379,6 +385,14 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
   }
 
   int bn = a->block_n ? a->block_n : pick_block_n(a->M, a->N, p.num_k_blocks);
+  const bool gn_fused = a->conv3x3 && a->gn_scale_shift != nullptr;
+  if (gn_fused) {
+    // GroupNorm-fused conv: halo-tile pair kernel only; the widest tile gives the two transform warps the most MMA time
+    // per halo tile to hide under (9 taps x 640 clocks at 256 x 320 against ~3000 clocks of transform)
+    GB_CHECK_ARG(conv_halo_enabled() && a->conv_W % 16 == 0 && a->conv_H % 16 == 0 && a->M % 256 == 0 && a->out_dtype != DT_F32,
+                 "gn_scale_shift needs the halo-tile kernel: H, W multiples of 16, M %% 256 == 0, 16-bit output");
+    if (!a->block_n) bn = a->N % 320 == 0 ? 320 : a->N % 256 == 0 ? 256 : 128;
+  }
   if (a->conv3x3 && a->conv_phase) {
     // upsample-fused phase launch: only the halo-tile pair kernel implements the collapsed tap walk and the strided output
     GB_CHECK_ARG(conv_halo_enabled() && a->conv_W % 16 == 0 && a->conv_H % 16 == 0 && a->M % 256 == 0 && a->out_dtype != DT_F32,
@@ -414,9 +428,9 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       want_sk = static_cast<double>(tiles) / static_cast<double>(waves * num_sms()) < 0.8;
     }
   }
-  if (a->conv3x3 && a->conv_phase) want_sk = false;
+  if ((a->conv3x3 && a->conv_phase) || gn_fused) want_sk = false;
   bool pair = false;
-  if (a->cta_pair == 2 || (a->conv3x3 && a->conv_phase)) {
+  if (a->cta_pair == 2 || (a->conv3x3 && a->conv_phase) || gn_fused) {
     pair = true;
   } else if (!want_sk && a->cta_pair == 0 && (bn == 128 || bn == 160 || bn == 256)) {
     // measured (tools/gpu_sweep_shapes.py, with the staged epilogue): the pair kernel wins 3..8 % from 10 k-blocks up
@@ -451,7 +465,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       // pairs instead of 256). Measured (profiles/r02_conv_halo.log): C320->320 104.9 -> 93.7 us, 64x64 C640->320 177.1 ->
       // 173.0, 32x32 C640->640 92.3 -> 89.5, C320->640 56.5 -> 52.4; from C = 960 up the wide tile wins or ties.
       if (a->block_n == 0 && a->conv3x3 && a->conv_C <= 640 && conv_halo_enabled() && p.conv_stride == 1 && a->conv_W % 16 == 0 &&
-          a->conv_H % 16 == 0 && a->M % 256 == 0)
+          a->conv_H % 16 == 0 && a->M % 256 == 0 && !gn_fused)
         bn = 160;
     }
     // Too few wide tiles for the 74 SM pairs (8x8 level: 16, 16x16 C640: 32): cut K into slices so that tiles x slices
@@ -704,12 +718,22 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       const int esz = a->out_dtype == DT_F32 ? 4 : 2;
       const int n_out = a->act == ACT_GEGLU ? a->N / 2 : a->N;
       {
-        const uint64_t dims[4] = {(uint64_t)a->conv_C, (uint64_t)a->conv_W, (uint64_t)a->conv_H, (uint64_t)a->conv_B};
-        const uint64_t strides[3] = {(uint64_t)a->conv_C * 2, (uint64_t)a->conv_W * a->conv_C * 2,
-                                     (uint64_t)a->conv_H * a->conv_W * a->conv_C * 2};
+        const int c1 = a->a_cat ? a->a_cat_C : 0, c0 = a->conv_C - c1;  // channels of the first / second (cat) source
         const uint32_t box[4] = {64, 10, 18, 1};
+        const uint64_t dims[4] = {(uint64_t)c0, (uint64_t)a->conv_W, (uint64_t)a->conv_H, (uint64_t)a->conv_B};
+        const uint64_t strides[3] = {(uint64_t)c0 * 2, (uint64_t)a->conv_W * c0 * 2, (uint64_t)a->conv_H * a->conv_W * c0 * 2};
         int r = encode_tmap(&p.tma_a, a->a, bf16 ? DT_BF16 : DT_F16, 4, dims, strides, box, 128, nullptr);
         if (r) return r;
+        p.halo_c0_blocks = c0 / BLOCK_K;
+        if (c1) {
+          const uint64_t dims1[4] = {(uint64_t)c1, (uint64_t)a->conv_W, (uint64_t)a->conv_H, (uint64_t)a->conv_B};
+          const uint64_t str1[3] = {(uint64_t)c1 * 2, (uint64_t)a->conv_W * c1 * 2, (uint64_t)a->conv_H * a->conv_W * c1 * 2};
+          r = encode_tmap(&p.tma_a2, a->a_cat, bf16 ? DT_BF16 : DT_F16, 4, dims1, str1, box, 128, nullptr);
+          if (r) return r;
+        }
+        p.gn_ss = a->gn_scale_shift;
+        p.gn_silu = a->gn_silu;
+        p.gn_C = a->conv_C;
       }
       {
         const uint64_t dims[3] = {(uint64_t)n_out, (uint64_t)a->conv_W, (uint64_t)a->conv_B * a->conv_H};
@@ -732,6 +756,14 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
         }
       }
       p.a_mode = A_CONV3X3_HALO;
+      if (gn_fused) {
+        switch (bn) {
+          case 128: return launch_gemm2<128, true, true>(p, stream);
+          case 160: return launch_gemm2<160, true, true>(p, stream);
+          case 320: return launch_gemm2<320, true, true>(p, stream);
+          default: return launch_gemm2<256, true, true>(p, stream);
+        }
+      }
       switch (bn) {
         case 128: return launch_gemm2<128, true>(p, stream);
         case 160: return launch_gemm2<160, true>(p, stream);
@@ -743,6 +775,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
   if (p.debug_mode == 3 && a->sk_workspace && p.sk_per == 0)  // wait-time trace of CTA 0 (measurement aid, see gemm_mma)
     p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(a->sk_workspace) + SK_FLAG_BYTES);
   GB_CHECK_ARG(!(a->conv3x3 && a->conv_phase), "conv_phase: shape does not qualify for the halo-tile pair kernel (bn=%d)", bn);
+  GB_CHECK_ARG(!gn_fused, "gn_scale_shift: shape does not qualify for the halo-tile pair kernel (bn=%d)", bn);
   if (pair) {
     switch (bn) {
       case 64: return launch_gemm2<64>(p, stream);

@@ -39,7 +39,9 @@ struct Gemm2Cfg {
   static constexpr int ACC_STRIDE = BLOCK_N <= 64 ? 64 : BLOCK_N <= 128 ? 128 : BLOCK_N <= 256 ? 256 : 512;
   static constexpr int TMEM_COLS = NACC * ACC_STRIDE;
   // A_CONV3X3_HALO: two resident halo-tile slots in front of a B-only ring
+  // (three slots with the GroupNorm transform: load latency + transform of a slot must hide under the MMAs of the others)
   static constexpr int HALO_RES = 2 * HALO_BYTES;
+  static constexpr int HALO_RES_GN = 3 * HALO_BYTES;
   static_assert(MMA_N % 32 == 0 && MMA_N >= 64 && MMA_N <= 256 && TMEM_COLS <= 512, "invalid 2-CTA UMMA N");
   static_assert(B_SUB % 1024 == 0, "B sub-tiles must keep 1024-B alignment");
 };
@@ -87,15 +89,17 @@ __device__ __forceinline__ PairSched make_pair_sched(int kb_per_tile, int pair, 
   return s;
 }
 
-template <int BLOCK_N, bool HALO = false>
+template <int BLOCK_N, bool HALO = false, bool GN = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(!GN || HALO, "the GroupNorm transform lives on the halo tile");
   using C = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // HALO: [2 halo slots][num_stages x B half-tiles]; else [num_stages x (A + B half-tile)]
   constexpr int RING_STAGE = HALO ? C::B_BYTES : C::STAGE_BYTES;
-  uint8_t* smem_tiles = smem + (HALO ? C::HALO_RES : 0);
+  constexpr int HSLOTS = GN ? 3 : 2;
+  uint8_t* smem_tiles = smem + (HALO ? HSLOTS * HALO_BYTES : 0);
   GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem_tiles + p.num_stages * RING_STAGE);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;
 
@@ -133,8 +137,11 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->tmem_full[i], 1);
       mbar_init(&bars->tmem_empty[i], 2 * (p.epi_tma ? p.epi_warps : GEMM_EPI_WARPS));
+    }
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&bars->halo_full[i], 1);
       mbar_init(&bars->halo_empty[i], 1);
+      mbar_init(&bars->halo_ready[i], 4);  // two transform warps in each CTA of the pair
     }
     if (p.epi_tma) {
       tma_prefetch_desc(&p.tma_out);
@@ -177,12 +184,23 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(&bars->halo_empty[hb], hphase ^ 1);
           const uint32_t hfull_leader = mapa_u32(smem_u32(&bars->halo_full[hb]), 0);
           if (elect_one()) {
-            if (leader) mbar_arrive_expect_tx(&bars->halo_full[hb], 2 * HALO_TX);
-            tma2_load_4d(smem + hb * HALO_BYTES, &p.tma_a, hfull_leader, cb * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
+            if (GN) {
+              // each CTA's transform warps wait for THEIR tile on the local barrier; the leader's MMA warp waits for
+              // halo_ready instead
+              mbar_arrive_expect_tx(&bars->halo_full[hb], HALO_TX);
+              const bool src0 = cb < p.halo_c0_blocks;
+              tma_load_4d(smem + hb * HALO_BYTES, src0 ? &p.tma_a : &p.tma_a2, &bars->halo_full[hb],
+                          (src0 ? cb : cb - p.halo_c0_blocks) * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
+            } else {
+              if (leader) mbar_arrive_expect_tx(&bars->halo_full[hb], 2 * HALO_TX);
+              tma2_load_4d(smem + hb * HALO_BYTES, &p.tma_a, hfull_leader, cb * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
+            }
           }
           __syncwarp();
-          hb ^= 1;
-          if (hb == 0) hphase ^= 1;
+          if (++hb == HSLOTS) {
+            hb = 0;
+            hphase ^= 1;
+          }
           for (int tap = 0; tap < p.conv_nt; ++tap) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sb = smem_tiles + stage * RING_STAGE;
@@ -273,7 +291,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::ACC_STRIDE;
         for (int cb = 0; cb < p.conv_cblocks; ++cb) {
-          mbar_wait(&bars->halo_full[hb], hphase);
+          mbar_wait(GN ? &bars->halo_ready[hb] : &bars->halo_full[hb], hphase);
           tc_fence_after();
           const uint64_t dh = dh0 + static_cast<uint64_t>(hb) * (HALO_BYTES >> 4);
           for (int tap = 0; tap < p.conv_nt; ++tap) {
@@ -300,8 +318,10 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
             stage = nstage;
             phase = nphase;
           }
-          hb ^= 1;
-          if (hb == 0) hphase ^= 1;
+          if (++hb == HSLOTS) {
+            hb = 0;
+            hphase ^= 1;
+          }
         }
         if (elect_one()) umma2_commit_mcast(&bars->tmem_full[acc], 0b11);
         __syncwarp();
@@ -363,6 +383,86 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         if (++acc == C::NACC) {
           acc = 0;
           acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (GN && (warp == 2 || warp == 3)) {
+    // ---------------- GroupNorm(+SiLU) of the input, in place on every halo tile (both CTAs, 64 threads each).
+    // Thread t owns 16-byte chunk t % 8 (8 channels: their scale / shift sit in registers for the whole channel block) of
+    // pixels t / 8, t / 8 + 8, ...; a warp touches 4 consecutive 128-byte rows per access (the swizzle only permutes chunks
+    // inside a row). Pixels outside the image become exactly zero: the convolution pads the NORMALISED tensor.
+    const int tt = (warp - 2) * 32 + static_cast<int>(lane_id());
+    const int c8 = tt & 7;
+    const bool bf = p.in_dtype == DT_BF16;
+    int hb = 0;
+    uint32_t hphase = 0;
+    PairSched sched = sched0;
+    Seg sg;
+    const int hw = p.conv_W * p.conv_H, bxn = p.conv_W >> 3;
+    while (sched.next(sg)) {
+      const int tile = sg.tile / 3;
+      const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+      const int cb0 = m0 / hw, blk = (m0 - cb0 * hw) >> 7;
+      const int cx0 = (blk % bxn) * 8, cy0 = (blk / bxn) * 16;
+      for (int cb = 0; cb < p.conv_cblocks; ++cb) {
+        const float* ss = p.gn_ss + static_cast<size_t>(cb0) * 2 * p.gn_C + cb * BLOCK_K + c8 * 8;
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(ss)), a1 = __ldg(reinterpret_cast<const float4*>(ss + 4));
+        const float4 d0 = __ldg(reinterpret_cast<const float4*>(ss + p.gn_C)), d1 = __ldg(reinterpret_cast<const float4*>(ss + p.gn_C + 4));
+        const float sa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float sd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        mbar_wait(&bars->halo_full[hb], hphase);
+        uint8_t* tile_s = smem + hb * HALO_BYTES;
+        // four pixels per step, loads first: four independent ex2 / rcp chains per thread (one warp per scheduler has no other
+        // way to hide the MUFU latency -- the single-pixel loop took longer than the nine taps of MMAs it should hide under)
+        const f32x2 nl2e = pk2(-1.4426950408889634f, -1.4426950408889634f), one2 = pk2(1.f, 1.f);
+#pragma unroll 1
+        for (int px0 = (p.debug_mode == 4 ? 180 : tt >> 3); px0 < 180; px0 += 32) {  // (debug_mode 4: barriers only, results invalid)
+          uint4 v[4];
+          uint4* ptr[4];
+          bool inb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int px = px0 + 8 * u;
+            const int py = px / 10, pxx = px - py * 10;
+            const int gy = cy0 - 1 + py, gx = cx0 - 1 + pxx;
+            inb[u] = px < 180 && gy >= 0 && gy < p.conv_H && gx >= 0 && gx < p.conv_W;
+            ptr[u] = reinterpret_cast<uint4*>(tile_s + px * 128 + ((c8 ^ (px & 7)) << 4));
+            v[u] = px < 180 ? *ptr[u] : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = bf ? unpack_bf16x2(w4[j]) : unpack_f16x2(w4[j]);
+              f32x2 y = fma2(pk2(f.x, f.y), pk2(sa[2 * j], sa[2 * j + 1]), pk2(sd[2 * j], sd[2 * j + 1]));
+              float y0, y1;
+              if (p.gn_silu) {
+                float z0, z1, e0, e1, s0, s1, r0, r1;
+                upk2(mul2(y, nl2e), z0, z1);
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+                upk2(add2(pk2(e0, e1), one2), s0, s1);
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s0));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(s1));
+                upk2(mul2(y, pk2(r0, r1)), y0, y1);
+              } else {
+                upk2(y, y0, y1);
+              }
+              w4[j] = inb[u] ? (bf ? pack_bf16x2(y0, y1) : pack_f16x2(y0, y1)) : 0u;
+            }
+            v[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (px0 + 8 * u < 180) *ptr[u] = v[u];
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
+        __syncwarp();
+        if (lane_id() == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->halo_ready[hb]), 0));
+        if (++hb == HSLOTS) {
+          hb = 0;
+          hphase ^= 1;
         }
       }
     }

@@ -71,6 +71,12 @@ struct alignas(64) GemmParams {
   // stats_out slab remap for phase launches: rows [b * stats_hw, (b + 1) * stats_hw) of this launch are sample b's; its
   // slabs go to ((b * 4 + stats_phase) * stats_hw + r) / 32 of the full-resolution tensor's buffer. 0: slab = row / 32.
   int stats_hw, stats_phase;
+  // A_CONV3X3_HALO with GroupNorm(+SiLU) of the input applied in shared memory (gemm2_kernel<BN, true, true>): two warps of
+  // each CTA rewrite every halo tile in place -- y = x * scale + shift per (sample, channel), SiLU, zero outside the image --
+  // before the MMAs read it; ONE pass per input element per CTA tile instead of a separate elementwise kernel over the
+  // whole tensor. halo_c0_blocks: channel blocks [0, halo_c0_blocks) come from tma_a, the rest from tma_a2 (cat source).
+  const float* gn_ss;
+  int gn_silu, gn_C, halo_c0_blocks;
   // epilogue
   void* out;
   void* out_lo;  // optional bf16 "lo" residue: out_lo = bf16(v - float(bf16(v)))   (split-precision activations)
@@ -775,7 +781,8 @@ struct GemmSmemBars {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint64_t res_full[GEMM_EPI_WARPS][EPI_MAX_NBUF];
-  uint64_t halo_full[2], halo_empty[2];  // A_CONV3X3_HALO: the two halo-tile slots
+  uint64_t halo_full[3], halo_empty[3];  // A_CONV3X3_HALO: the halo-tile slots (two; three with the GroupNorm transform)
+  uint64_t halo_ready[3];                // ... with the GroupNorm transform: both CTAs' transform warps are done with the slot
   uint32_t tmem_ptr;
 };
 static_assert(sizeof(GemmSmemBars) <= 1024, "barrier block");

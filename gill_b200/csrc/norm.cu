@@ -988,6 +988,20 @@ extern "C" int gillb200_groupnorm_from_stats(const void* x0, int C0, const void*
   return launch_gn_apply(src, dtype, B, HW, scale_shift, silu, out, out_dtype, stream);
 }
 
+extern "C" int gillb200_groupnorm_scale_shift(int C0, const void* stats0, int C1, const void* stats1, int B, int HW, int G,
+                                              const float* w, const float* b, float eps, float* scale_shift, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int C = C0 + C1;
+  GB_CHECK_ARG(stats0 && w && b && scale_shift, "null pointer");
+  GB_CHECK_ARG(C0 % 8 == 0 && C1 % 8 == 0 && C % G == 0 && G <= 64 && C <= 4096, "groupnorm: C0=%d C1=%d G=%d", C0, C1, G);
+  GB_CHECK_ARG(C1 == 0 || stats1 != nullptr, "groupnorm: second source's statistics missing");
+  GB_CHECK_ARG(HW % 32 == 0 && B <= 1024, "groupnorm_scale_shift: HW=%d must be a multiple of 32, B <= 1024", HW);
+  GB_CUDA(launch_pdl_light(gn_finalize_stats_kernel, dim3(G, B), dim3(128), 0, stream, reinterpret_cast<const float2*>(stats0), C0,
+                           reinterpret_cast<const float2*>(stats1), C1, HW / 32, G, HW, w, b, eps, scale_shift));
+  GB_COUNT_LAUNCH(1);
+  return 0;
+}
+
 extern "C" int gillb200_softmax_rows(const void* x, long long ldx, int in_dtype, float scale, long long rows, int n,
                                      void* out, long long ldo, int out_dtype, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

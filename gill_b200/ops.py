@@ -267,8 +267,14 @@ def conv3x3(
     stream_k: int = 0,
     stride: int = 1,
     stats: bool = False,
+    gn=None,
+    x2: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
     """3x3 / pad 1 convolution (stride 1 or 2) as an implicit GEMM.
+
+    gn = (scale_shift [B,2,C] fp32 from groupnorm_scale_shift, silu): GroupNorm(+SiLU) of the INPUT applied inside the conv
+    (x is the raw activation; the normalised tensor is never written); x2: second NHWC source holding the last x2.shape[3]
+    input channels (cat([x, x2], -1) without the concat; only with gn). Both need conv3x3_gn_supported(x, w).
 
     x: NHWC [B,H,W,C] (C % 64 == 0); w: [Cout, 9*C (+k2)] with k = (ky*3+kx)*C + c; returns NHWC [B,H/s,W/s,Cout].
     rowbias [B, Cout] is added per sample (time embedding); a2 [B*H*W, k2] K-concatenates a 1x1 shortcut input whose
@@ -279,13 +285,23 @@ def conv3x3(
     _chk2d(w, "w")
     N = w.shape[0]
     assert stride in (1, 2) and H % stride == 0 and W % stride == 0
+    C0 = C
+    if x2 is not None:
+        assert gn is not None and x2.is_contiguous() and x2.shape[:3] == x.shape[:3] and x2.dtype == x.dtype
+        C = C0 + x2.shape[3]
     Hi, Wi = H, W
     H, W = H // stride, W // stride
     if out is None:
         out = torch.empty((B, H, W, N), device=x.device, dtype=out_dtype or x.dtype)
     g = GemmArgs()
-    g.a, g.lda = x.data_ptr(), C
+    g.a, g.lda = x.data_ptr(), C0
     g.conv3x3, g.conv_B, g.conv_H, g.conv_W, g.conv_C, g.conv_stride = 1, B, Hi, Wi, C, stride
+    if gn is not None:
+        ss, silu = gn
+        assert ss.dtype == torch.float32 and ss.is_contiguous() and ss.shape == (B, 2, C) and stride == 1 and a2 is None
+        g.gn_scale_shift, g.gn_silu = ss.data_ptr(), int(silu)
+        if x2 is not None:
+            g.a_cat, g.a_cat_C = x2.data_ptr(), x2.shape[3]
     if a2 is not None:
         _chk2d(a2, "a2")
         g.a2, g.lda2, g.k2, g.a2_mode = a2.data_ptr(), a2.stride(0), a2.shape[1], 1
@@ -464,6 +480,32 @@ def groupnorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, ep
                                        b.data_ptr(), eps, int(silu), out.data_ptr(), _DT[out.dtype], ws.data_ptr(),
                                        _stream()), "gillb200_groupnorm")
     return out
+
+
+def conv3x3_gn_supported(x: torch.Tensor, n_out: int, x2: Optional[torch.Tensor] = None, min_tiles: int = 48) -> bool:
+    """Shapes for which conv3x3(..., gn=...) can apply the GroupNorm inside the conv (halo-tile CTA-pair kernel) and whose
+    producers left GroupNorm statistics."""
+    B, H, W, C0 = x.shape
+    C1 = 0 if x2 is None else x2.shape[3]
+    tiles = (B * H * W // 256) * ((n_out + 319) // 320 if n_out % 320 == 0 else (n_out + 255) // 256)
+    return (USE_EPILOGUE_GN_STATS and x.dtype != torch.float32 and H % 16 == 0 and W % 16 == 0 and (B * H * W) % 256 == 0
+            and C0 % 64 == 0 and C1 % 64 == 0 and n_out % 32 == 0 and tiles >= min_tiles
+            and getattr(x, "gn_stats", None) is not None and (x2 is None or getattr(x2, "gn_stats", None) is not None))
+
+
+def groupnorm_scale_shift(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, groups: int, eps: float,
+                          x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The (sample, group) reduction of GroupNorm only, from the producers' `.gn_stats`: float [B, 2, C] = per sample and
+    channel (scale, shift) with y = x * scale + shift -- for a consumer that applies the normalisation itself
+    (conv3x3(..., gn=...))."""
+    B, H, W, C0 = x.shape
+    C1 = 0 if x2 is None else x2.shape[3]
+    st0, st1 = x.gn_stats, (x2.gn_stats if x2 is not None else None)
+    ss = torch.empty((B, 2, C0 + C1), device=x.device, dtype=torch.float32)
+    with _P("groupnorm", 0.0, 0.0, f"B{B} {H}x{W} C{C0 + C1} (scale/shift only)"):
+        check(lib().gillb200_groupnorm_scale_shift(C0, st0.data_ptr(), C1, _ptr(st1), B, H * W, groups, w.data_ptr(), b.data_ptr(),
+                                                   eps, ss.data_ptr(), _stream()), "gillb200_groupnorm_scale_shift")
+    return ss
 
 
 def softmax_rows(x: torch.Tensor, scale: float, out_dtype: torch.dtype, out: Optional[torch.Tensor] = None):

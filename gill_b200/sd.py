@@ -34,6 +34,24 @@ NARROW_CONV_OUT = os.environ.get("GILLB200_NARROW_CONV_OUT", "1") != "0"
 FUSED_UPSAMPLE = os.environ.get("GILLB200_FUSED_UPSAMPLE", "1") != "0"
 
 
+# resnets: GroupNorm + SiLU applied inside the consuming 3x3 conv (ops.conv3x3(..., gn=...)) instead of a separate
+# elementwise pass over the tensor. OPT-IN ("1"): correct (tests) and the extra barrier hand-off is free, but the in-place
+# transform of the halo tiles runs on two warps = two of the SM's four XU pipes (2 MUFU + the 16-bit conversions per
+# element) and takes longer than the nine taps of MMAs it should hide under: UNet evaluation 17.55 -> 18.17 ms, conv family
+# +0.96 ms against 0.75 ms of GroupNorm saved (profiles/r02_gn_fused_conv.log).
+FUSED_GN = os.environ.get("GILLB200_FUSED_GN", "0") != "0"
+
+
+def _gn_silu_conv(x, w, pn, pc, G, eps, x2=None, **conv_kw):
+    """norm -> SiLU -> conv3x3 of a resnet (x2: second source of a channel concat)."""
+    wt = w[pc + ".weight"]
+    if FUSED_GN and ops.conv3x3_gn_supported(x, wt.shape[0], x2):
+        ss = ops.groupnorm_scale_shift(x, w[pn + ".weight"], w[pn + ".bias"], G, eps, x2=x2)
+        return ops.conv3x3(x, wt, bias=w[pc + ".bias"], gn=(ss, True), x2=x2, **conv_kw)
+    n = ops.groupnorm(x, w[pn + ".weight"], w[pn + ".bias"], G, eps, silu=True, x2=x2)
+    return ops.conv3x3(n, wt, bias=w[pc + ".bias"], **conv_kw)
+
+
 def _upsample_conv(h, w, p, stats=True):
     """Upsample2D of diffusers (nearest 2x + 3x3 conv): fused phase form when the shape qualifies."""
     if FUSED_UPSAMPLE and (p + ".weight_up2") in w and ops.conv3x3_up2_supported(h):
@@ -332,9 +350,7 @@ class UNetB200:
         B, H, W, _ = x.shape
         lo, hi = self._temb_off[p]
         rb = self._temb_cur[:, lo:hi]
-        n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-5, silu=True, x2=x2)
-        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], rowbias=rb, stats=True)
-        n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-5, silu=True)
+        h = _gn_silu_conv(x, w, p + ".norm1", p + ".conv1", G, 1e-5, x2=x2, rowbias=rb, stats=True)
         if (p + ".conv_shortcut.weight") in w:
             M = B * H * W
             if x2 is not None:
@@ -346,7 +362,7 @@ class UNetB200:
         else:
             assert x2 is None
             sc = x
-        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc, stats=True)
+        return _gn_silu_conv(h, w, p + ".norm2", p + ".conv2", G, 1e-5, residual=sc, stats=True)
 
     def _transformer(self, x, p, ctx_kv):
         w, G, Hh = self.w, self.G, self.heads
@@ -502,15 +518,13 @@ class VAEDecoderB200:
     def _resnet(self, x, p):
         w, G = self.w, self.G
         B, H, W, _ = x.shape
-        n = ops.groupnorm(x, w[p + ".norm1.weight"], w[p + ".norm1.bias"], G, 1e-6, silu=True)
-        h = ops.conv3x3(n, w[p + ".conv1.weight"], bias=w[p + ".conv1.bias"], stats=True)
-        n = ops.groupnorm(h, w[p + ".norm2.weight"], w[p + ".norm2.bias"], G, 1e-6, silu=True)
+        h = _gn_silu_conv(x, w, p + ".norm1", p + ".conv1", G, 1e-6, stats=True)
         if (p + ".conv_shortcut.weight") in w:
             sc = ops.gemm(x.view(B * H * W, -1), w[p + ".conv_shortcut.weight"],
                           bias=w[p + ".conv_shortcut.bias"]).view(B, H, W, -1)
         else:
             sc = x
-        return ops.conv3x3(n, w[p + ".conv2.weight"], bias=w[p + ".conv2.bias"], residual=sc, stats=True)
+        return _gn_silu_conv(h, w, p + ".norm2", p + ".conv2", G, 1e-6, residual=sc, stats=True)
 
     def _mid_attention(self, x):
         """Single-head attention over H*W tokens with head dim 512: too wide for the fused kernel's smem tiles, and

@@ -115,6 +115,16 @@ typedef struct gillb200_gemm_args {
                     * out = BASE of the full-resolution NHWC tensor [conv_B, 2*conv_H, 2*conv_W, N] (ldo = N): the launch writes
                     * its quarter of the pixels. stats_out (optional) = the full-resolution tensor's [4*M/32, N, 2] buffer.
                     * Needs the halo-tile CTA-pair kernel: conv_H, conv_W multiples of 16, M % 256 == 0, >= 55 pair tiles. */
+  /* conv3x3 only, optional: GroupNorm(+SiLU) of the INPUT applied on the fly (the resnet pattern norm -> SiLU -> conv of
+   * the UNet / VAE, gill/custom_sd.py:633): gn_scale_shift = float [conv_B, 2, conv_C], y = x * scale + shift per sample and
+   * channel (from gillb200_groupnorm_scale_shift), gn_silu != 0 applies SiLU; zero padding is applied AFTER the normalisation,
+   * as nn.Conv2d does. The raw activation is what `a` points at -- the normalised tensor is never written. a_cat / a_cat_C:
+   * optional second NHWC source [conv_B, conv_H, conv_W, a_cat_C] holding the LAST a_cat_C of the conv_C input channels
+   * (torch.cat([h, skip], 1) of the up blocks without the concat). Halo-tile CTA-pair kernel only (see conv_phase). */
+  const float* gn_scale_shift;
+  int gn_silu;
+  const void* a_cat;
+  int a_cat_C;
 } gillb200_gemm_args;
 
 long long gillb200_gemm_streamk_workspace_bytes(void);
@@ -196,6 +206,10 @@ int gillb200_groupnorm(const void* x0, int C0, const void* x1, int C1, int dtype
                        const float* b, float eps, int silu, void* out, int out_dtype, void* workspace, void* stream);
 /* GroupNorm(+SiLU) whose statistics come from the producing GEMMs' stats_out buffers (stats1 only with a second source):
  * one small reduction per (sample, group) + the elementwise pass -- no statistics read of the activation. */
+/* Only the (sample, group) reduction of the producers' statistics: scale_shift [B, 2, C0 + C1] for a consumer that applies
+ * the normalisation itself (gillb200_gemm_args::gn_scale_shift). */
+int gillb200_groupnorm_scale_shift(int C0, const void* stats0, int C1, const void* stats1, int B, int HW, int G,
+                                   const float* w, const float* b, float eps, float* scale_shift, void* stream);
 int gillb200_groupnorm_from_stats(const void* x0, int C0, const void* stats0, const void* x1, int C1, const void* stats1,
                                   int dtype, int B, int HW, int G, const float* w, const float* b, float eps, int silu,
                                   void* out, int out_dtype, void* workspace, void* stream);

@@ -755,3 +755,49 @@ def test_conv3x3_up2_equals_upsample_then_conv(ops, case):
         gn = ops.groupnorm(got, w2, b2, 32, 1e-5, silu=True)
         gref = F.silu(F.group_norm(got.permute(0, 3, 1, 2).float(), 32, w2, b2, 1e-5)).permute(0, 2, 3, 1)
         assert rel(gn, gref) < 2e-3
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 128, 0, 320, "rowbias"), (4, 32, 32, 128, 64, 640, "res"), (16, 16, 16, 192, 128, 320, "none"),
+                                  (2, 32, 32, 64, 0, 256, "res")])
+def test_conv3x3_with_groupnorm_fused_into_the_input(ops, case):
+    """norm -> SiLU -> conv3x3 with the GroupNorm applied on the halo tile inside the conv (scale / shift from the producers'
+    statistics, zero padding after the normalisation, optional channel-concat second source) == GroupNorm kernel + conv."""
+    B, H, W, C0, C1, Co, mode = case
+    torch.manual_seed(9)
+
+    def produce(C):
+        a = torch.randn(B * H * W, 64, device=dev).half()
+        wt = (torch.randn(C, 64, device=dev) * 0.2).half()
+        o = ops.gemm(a, wt, bias=torch.randn(C, device=dev), stats=True)
+        o4 = o.view(B, H, W, C)
+        o4.gn_stats = o.gn_stats
+        return o4
+
+    x0 = produce(C0)
+    x1 = produce(C1) if C1 else None
+    C = C0 + C1
+    gw, gb = torch.randn(C, device=dev), torch.randn(C, device=dev)
+    w4 = (torch.randn(Co, C, 3, 3, device=dev) / (3 * C ** 0.5)).half()
+    bias = torch.randn(Co, device=dev)
+    wk = w4.permute(0, 2, 3, 1).reshape(Co, 9 * C).contiguous()
+    kw = {}
+    if mode == "res":
+        kw["residual"] = torch.randn(B, H, W, Co, device=dev).half()
+    elif mode == "rowbias":
+        kw["rowbias"] = torch.randn(B, Co, device=dev)
+    assert ops.conv3x3_gn_supported(x0, Co, x1, min_tiles=0)
+    ss = ops.groupnorm_scale_shift(x0, gw, gb, 32, 1e-5, x2=x1)
+    got = ops.conv3x3(x0, wk, bias=bias, gn=(ss, True), x2=x1, stats=True, **kw)
+    xc = x0 if x1 is None else torch.cat([x0, x1], -1)
+    n = F.silu(F.group_norm(xc.permute(0, 3, 1, 2).float(), 32, gw, gb, 1e-5))
+    ref = F.conv2d(n, w4.float(), bias, padding=1).permute(0, 2, 3, 1)
+    if mode == "res":
+        ref = ref + kw["residual"].float()
+    elif mode == "rowbias":
+        ref = ref + kw["rowbias"][:, None, None, :]
+    assert got.shape == ref.shape and rel(got, ref) < 3e-3
+    two = ops.conv3x3(ops.groupnorm(x0, gw, gb, 32, 1e-5, silu=True, x2=x1), wk, bias=bias, **kw)
+    assert rel(got, two) < 2e-3
+    st = got.gn_stats.view(B, H * W // 32, Co, 2).sum(1)
+    g = got.float().view(B, H * W, Co)
+    assert rel(st[..., 0], g.sum(1)) < 1e-3
