@@ -757,6 +757,7 @@ extern "C" int gillb200_gemm(const gillb200_gemm_args* a_in, void* stream_) {
       }
       p.a_mode = A_CONV3X3_HALO;
       if (gn_fused) {
+        p.epi_warps = 4;  // warps 4-7; warps 8 and 9 join warps 2 and 3 as transform warps (one per scheduler)
         switch (bn) {
           case 128: return launch_gemm2<128, true, true>(p, stream);
           case 160: return launch_gemm2<160, true, true>(p, stream);

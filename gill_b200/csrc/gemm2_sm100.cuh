@@ -141,7 +141,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bars->halo_full[i], 1);
       mbar_init(&bars->halo_empty[i], 1);
-      mbar_init(&bars->halo_ready[i], 4);  // two transform warps in each CTA of the pair
+      mbar_init(&bars->halo_ready[i], 8);  // four transform warps in each CTA of the pair
     }
     if (p.epi_tma) {
       tma_prefetch_desc(&p.tma_out);
@@ -386,12 +386,14 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         }
       }
     }
-  } else if (GN && (warp == 2 || warp == 3)) {
+  } else if (GN && (warp == 2 || warp == 3 || warp == 8 || warp == 9)) {
     // ---------------- GroupNorm(+SiLU) of the input, in place on every halo tile (both CTAs, 64 threads each).
     // Thread t owns 16-byte chunk t % 8 (8 channels: their scale / shift sit in registers for the whole channel block) of
     // pixels t / 8, t / 8 + 8, ...; a warp touches 4 consecutive 128-byte rows per access (the swizzle only permutes chunks
     // inside a row). Pixels outside the image become exactly zero: the convolution pads the NORMALISED tensor.
-    const int tt = (warp - 2) * 32 + static_cast<int>(lane_id());
+    // FOUR warps on the four schedulers (2, 3, 8, 9 -> SMSP 2, 3, 0, 1; the epilogue runs on warps 4-7 in this mode): the
+    // transform is bound by the XU pipe (2 MUFU + the 16-bit conversions per element) and two warps only reach two of them
+    const int tt = (warp < 4 ? warp - 2 : warp - 6) * 32 + static_cast<int>(lane_id());
     const int c8 = tt & 7;
     const bool bf = p.in_dtype == DT_BF16;
     int hb = 0;
@@ -416,13 +418,13 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
         // way to hide the MUFU latency -- the single-pixel loop took longer than the nine taps of MMAs it should hide under)
         const f32x2 nl2e = pk2(-1.4426950408889634f, -1.4426950408889634f), one2 = pk2(1.f, 1.f);
 #pragma unroll 1
-        for (int px0 = (p.debug_mode == 4 ? 180 : tt >> 3); px0 < 180; px0 += 32) {  // (debug_mode 4: barriers only, results invalid)
+        for (int px0 = (p.debug_mode == 4 ? 180 : tt >> 3); px0 < 180; px0 += 64) {  // (debug_mode 4: barriers only, results invalid)
           uint4 v[4];
           uint4* ptr[4];
           bool inb[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int px = px0 + 8 * u;
+            const int px = px0 + 16 * u;
             const int py = px / 10, pxx = px - py * 10;
             const int gy = cy0 - 1 + py, gx = cx0 - 1 + pxx;
             inb[u] = px < 180 && gy >= 0 && gy < p.conv_H && gx >= 0 && gx < p.conv_W;
@@ -437,7 +439,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
               const float2 f = bf ? unpack_bf16x2(w4[j]) : unpack_f16x2(w4[j]);
               f32x2 y = fma2(pk2(f.x, f.y), pk2(sa[2 * j], sa[2 * j + 1]), pk2(sd[2 * j], sd[2 * j + 1]));
               float y0, y1;
-              if (p.gn_silu) {
+              if (p.gn_silu && p.debug_mode != 5) {  // (debug_mode 5: affine only, no MUFU -- measurement aid)
                 float z0, z1, e0, e1, s0, s1, r0, r1;
                 upk2(mul2(y, nl2e), z0, z1);
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
@@ -455,7 +457,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (px0 + 8 * u < 180) *ptr[u] = v[u];
+            if (px0 + 16 * u < 180) *ptr[u] = v[u];
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
         __syncwarp();

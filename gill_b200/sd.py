@@ -36,9 +36,9 @@ FUSED_UPSAMPLE = os.environ.get("GILLB200_FUSED_UPSAMPLE", "1") != "0"
 
 # resnets: GroupNorm + SiLU applied inside the consuming 3x3 conv (ops.conv3x3(..., gn=...)) instead of a separate
 # elementwise pass over the tensor. OPT-IN ("1"): correct (tests) and the extra barrier hand-off is free, but the in-place
-# transform of the halo tiles runs on two warps = two of the SM's four XU pipes (2 MUFU + the 16-bit conversions per
-# element) and takes longer than the nine taps of MMAs it should hide under: UNet evaluation 17.55 -> 18.17 ms, conv family
-# +0.96 ms against 0.75 ms of GroupNorm saved (profiles/r02_gn_fused_conv.log).
+# transform of the halo tiles (four warps, one per scheduler: 2 MUFU + the 16-bit conversions per element) does not hide
+# under the nine taps of MMAs: break-even at best per conv (profiles/r02_gn_fused_conv.log; with two warps the UNet
+# evaluation went 17.55 -> 18.17 ms).
 FUSED_GN = os.environ.get("GILLB200_FUSED_GN", "0") != "0"
 
 
