@@ -26,6 +26,9 @@ namespace gb {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
+#ifndef GILLB200_GELU_ESTRIN
+#define GILLB200_GELU_ESTRIN 0  // measured: 137.9 vs 131-135 us (M65536 N2560 K320 GEGLU) -- no gain, Horner keeps the scalar form bit for bit
+#endif
 #ifndef GILLB200_EPI_PIPELINE
 #define GILLB200_EPI_PIPELINE 0
 #endif
@@ -213,6 +216,19 @@ __device__ __forceinline__ f32x2 gelu_poly2(f32x2 g) {
   const f32x2 x = pk2(x0, x1);
   const f32x2 t = mul2(x, x);
 #define GB_C2(c) pk2(c, c)
+#if GILLB200_GELU_ESTRIN
+  // Estrin evaluation (12 packed operations, dependency depth 5 instead of Horner's 10): the epilogue warps run at ~0.23 IPC
+  // on dependent FFMA2 chains that the compiler does not interleave at 168 registers (SASS of the GEGLU epilogue)
+  const f32x2 t2 = mul2(t, t), t4 = mul2(t2, t2), t8 = mul2(t4, t4);
+  const f32x2 a0 = fma2(GB_C2(-3.760564203e-01f), t, GB_C2(1.128376151e+00f));
+  const f32x2 a1 = fma2(GB_C2(-2.645343569e-02f), t, GB_C2(1.125671519e-01f));
+  const f32x2 a2 = fma2(GB_C2(-7.009955072e-04f), t, GB_C2(4.897189191e-03f));
+  const f32x2 a3 = fma2(GB_C2(-5.322654538e-06f), t, GB_C2(7.394709949e-05f));
+  const f32x2 a4 = fma2(GB_C2(-4.469938970e-09f), t, GB_C2(2.302152890e-07f));
+  const f32x2 b0 = fma2(a1, t2, a0), b1 = fma2(a3, t2, a2);
+  f32x2 p = fma2(b1, t4, b0);
+  p = fma2(a4, t8, p);
+#else
   f32x2 p = GB_C2(-4.469938970e-09f);
   p = fma2(p, t, GB_C2(2.302152890e-07f));
   p = fma2(p, t, GB_C2(-5.322654538e-06f));
@@ -223,6 +239,7 @@ __device__ __forceinline__ f32x2 gelu_poly2(f32x2 g) {
   p = fma2(p, t, GB_C2(1.125671519e-01f));
   p = fma2(p, t, GB_C2(-3.760564203e-01f));
   p = fma2(p, t, GB_C2(1.128376151e+00f));
+#endif
   const f32x2 hg = mul2(g, GB_C2(0.5f));
 #undef GB_C2
   return fma2(hg, mul2(p, x), hg);
