@@ -172,35 +172,55 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       PairSched sched = sched0;
       Seg sg;
       const int hw = p.conv_W * p.conv_H, bxn = p.conv_W >> 3;
+      auto issue_halo = [&](int code, int cb) {  // halo tile of (tile code, channel block) into the next slot
+        const int tile = code / 3;
+        const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
+        const int cb0 = m0 / hw, blk = (m0 - cb0 * hw) >> 7;
+        const int cx0 = (blk % bxn) * 8, cy0 = (blk / bxn) * 16;
+        mbar_wait(&bars->halo_empty[hb], hphase ^ 1);
+        const uint32_t hfull_leader = mapa_u32(smem_u32(&bars->halo_full[hb]), 0);
+        if (elect_one()) {
+          if (GN) {
+            // each CTA's transform warps wait for THEIR tile on the local barrier; the leader's MMA warp waits for
+            // halo_ready instead
+            mbar_arrive_expect_tx(&bars->halo_full[hb], HALO_TX);
+            const bool src0 = cb < p.halo_c0_blocks;
+            tma_load_4d(smem + hb * HALO_BYTES, src0 ? &p.tma_a : &p.tma_a2, &bars->halo_full[hb],
+                        (src0 ? cb : cb - p.halo_c0_blocks) * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&bars->halo_full[hb], 2 * HALO_TX);
+            tma2_load_4d(smem + hb * HALO_BYTES, &p.tma_a, hfull_leader, cb * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
+          }
+        }
+        __syncwarp();
+        if (++hb == HSLOTS) {
+          hb = 0;
+          hphase ^= 1;
+        }
+      };
+      // GN: the halo tile of the NEXT (tile, channel block) is requested BEFORE this block's weight tiles -- issued after
+      // them it could run at most one B-ring depth (~5 taps) ahead of the MMAs, less than TMA latency + transform time
+      PairSched ahead = sched0;
+      Seg sa;
+      bool more = GN && ahead.next(sa);
+      int acb = 0;
+      auto issue_ahead = [&]() {
+        if (!more) return;
+        issue_halo(sa.tile, acb);
+        if (++acb == p.conv_cblocks) {
+          acb = 0;
+          more = ahead.next(sa);
+        }
+      };
+      if (GN) issue_ahead();
       while (sched.next(sg)) {
         const int part = sg.tile % 3;
         const int tile = sg.tile / 3;
-        const int m0 = (tile % num_m2) * 2 * BLOCK_M + static_cast<int>(rank) * BLOCK_M;
         const int n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0) + static_cast<int>(rank) * (C::MMA_N / 2);
         const int nmma = part == 0 ? C::NMMA : 1;
-        const int cb0 = m0 / hw, blk = (m0 - cb0 * hw) >> 7;
-        const int cx0 = (blk % bxn) * 8, cy0 = (blk / bxn) * 16;
         for (int cb = 0; cb < p.conv_cblocks; ++cb) {
-          mbar_wait(&bars->halo_empty[hb], hphase ^ 1);
-          const uint32_t hfull_leader = mapa_u32(smem_u32(&bars->halo_full[hb]), 0);
-          if (elect_one()) {
-            if (GN) {
-              // each CTA's transform warps wait for THEIR tile on the local barrier; the leader's MMA warp waits for
-              // halo_ready instead
-              mbar_arrive_expect_tx(&bars->halo_full[hb], HALO_TX);
-              const bool src0 = cb < p.halo_c0_blocks;
-              tma_load_4d(smem + hb * HALO_BYTES, src0 ? &p.tma_a : &p.tma_a2, &bars->halo_full[hb],
-                          (src0 ? cb : cb - p.halo_c0_blocks) * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
-            } else {
-              if (leader) mbar_arrive_expect_tx(&bars->halo_full[hb], 2 * HALO_TX);
-              tma2_load_4d(smem + hb * HALO_BYTES, &p.tma_a, hfull_leader, cb * BLOCK_K, cx0 - 1, cy0 - 1, cb0);
-            }
-          }
-          __syncwarp();
-          if (++hb == HSLOTS) {
-            hb = 0;
-            hphase ^= 1;
-          }
+          if (GN) issue_ahead();
+          else issue_halo(sg.tile, cb);
           for (int tap = 0; tap < p.conv_nt; ++tap) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sb = smem_tiles + stage * RING_STAGE;

@@ -35,11 +35,10 @@ FUSED_UPSAMPLE = os.environ.get("GILLB200_FUSED_UPSAMPLE", "1") != "0"
 
 
 # resnets: GroupNorm + SiLU applied inside the consuming 3x3 conv (ops.conv3x3(..., gn=...)) instead of a separate
-# elementwise pass over the tensor. OPT-IN ("1"): correct (tests) and the extra barrier hand-off is free, but the in-place
-# transform of the halo tiles (four warps, one per scheduler: 2 MUFU + the 16-bit conversions per element) does not hide
-# under the nine taps of MMAs: break-even at best per conv (profiles/r02_gn_fused_conv.log; with two warps the UNet
-# evaluation went 17.55 -> 18.17 ms).
-FUSED_GN = os.environ.get("GILLB200_FUSED_GN", "0") != "0"
+# elementwise pass over the tensor (four transform warps rewrite each halo tile in place; the next tile is requested one
+# whole channel block ahead). Same box: UNet evaluation 17.76 -> 17.43 ms, VAE decode 19.7 -> 18.3 ms
+# (profiles/r02_gn_fused_conv.log). "0": separate GroupNorm kernel (A/B aid)
+FUSED_GN = os.environ.get("GILLB200_FUSED_GN", "1") != "0"
 
 
 def _gn_silu_conv(x, w, pn, pc, G, eps, x2=None, **conv_kw):
