@@ -159,7 +159,7 @@ static int launch_gemm2(GemmParams& p, cudaStream_t stream) {
     GB_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, HALO, GN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET));
   }
   // halo mode: two resident halo-tile slots in front of a ring of B half-tiles (8 stages at most: the barrier block)
-  const int smem_bytes = HALO ? plan_smem(p, C::B_BYTES, 8, GN ? C::HALO_RES_GN : C::HALO_RES) : plan_smem(p, C::STAGE_BYTES, C::STAGES);
+  const int smem_bytes = HALO ? plan_smem(p, C::B_BYTES, 8, (GN || HALO_AHEAD_ALWAYS) ? C::HALO_RES_GN : C::HALO_RES) : plan_smem(p, C::STAGE_BYTES, C::STAGES);
   GB_CHECK_ARG(p.num_stages >= 2, "no room for a 2-stage ring next to the epilogue staging (pair, BN=%d)", BN);
   const int num_m2 = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int num_n = (p.N + BN - 1) / BN;

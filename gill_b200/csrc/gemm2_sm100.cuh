@@ -17,6 +17,11 @@
 
 namespace gb {
 
+#ifndef GILLB200_HALO_AHEAD
+#define GILLB200_HALO_AHEAD 0  // measured for plain halo convs: 4.99 vs 4.65 ms per UNet evaluation (a third slot costs weight-ring stages)
+#endif
+constexpr bool HALO_AHEAD_ALWAYS = GILLB200_HALO_AHEAD != 0;
+
 template <int BLOCK_N>
 struct Gemm2Cfg {
   // BLOCK_N <= 256: one tcgen05.mma of N = BLOCK_N per K-step, two TMEM accumulator stages.
@@ -98,7 +103,8 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // HALO: [2 halo slots][num_stages x B half-tiles]; else [num_stages x (A + B half-tile)]
   constexpr int RING_STAGE = HALO ? C::B_BYTES : C::STAGE_BYTES;
-  constexpr int HSLOTS = GN ? 3 : 2;
+  constexpr bool AHEAD = GN || HALO_AHEAD_ALWAYS;  // three halo slots, next tile requested one channel block ahead
+  constexpr int HSLOTS = AHEAD ? 3 : 2;
   uint8_t* smem_tiles = smem + (HALO ? HSLOTS * HALO_BYTES : 0);
   GemmSmemBars* bars = reinterpret_cast<GemmSmemBars*>(smem_tiles + p.num_stages * RING_STAGE);
   uint8_t* epi_stage = reinterpret_cast<uint8_t*>(bars) + C::BAR_BYTES;
@@ -202,7 +208,7 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
       // them it could run at most one B-ring depth (~5 taps) ahead of the MMAs, less than TMA latency + transform time
       PairSched ahead = sched0;
       Seg sa;
-      bool more = GN && ahead.next(sa);
+      bool more = AHEAD && ahead.next(sa);
       int acb = 0;
       auto issue_ahead = [&]() {
         if (!more) return;
@@ -212,14 +218,14 @@ gemm2_kernel(const __grid_constant__ GemmParams p) {
           more = ahead.next(sa);
         }
       };
-      if (GN) issue_ahead();
+      if (AHEAD) issue_ahead();
       while (sched.next(sg)) {
         const int part = sg.tile % 3;
         const int tile = sg.tile / 3;
         const int n0 = (tile / num_m2) * BLOCK_N + (part == 2 ? C::MMA_N : 0) + static_cast<int>(rank) * (C::MMA_N / 2);
         const int nmma = part == 0 ? C::NMMA : 1;
         for (int cb = 0; cb < p.conv_cblocks; ++cb) {
-          if (GN) issue_ahead();
+          if (AHEAD) issue_ahead();
           else issue_halo(sg.tile, cb);
           for (int tap = 0; tap < p.conv_nt; ++tap) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
