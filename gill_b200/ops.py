@@ -542,9 +542,10 @@ def conv3x3_up2_weights(w: torch.Tensor) -> torch.Tensor:
     phases of `conv3x3(upsample2x(x))` (see conv3x3_up2). Phase (a, b), low-res offset (a - 1 + u, b - 1 + v):
     rows ky in {0} / {1, 2} (a = 0; u = 0 / 1) or {0, 1} / {2} (a = 1), columns likewise; summed in fp32, rounded once."""
     cout, C = w.shape[0], w.shape[1] // 9
-    w9 = w.float().view(cout, 3, 3, C)
+    acc = torch.float32 if w.dtype in (torch.float16, torch.bfloat16) else w.dtype
+    w9 = w.to(acc).view(cout, 3, 3, C)
     sel = {(0, 0): [0], (0, 1): [1, 2], (1, 0): [0, 1], (1, 1): [2]}
-    out = torch.zeros((4, cout, 4, C), dtype=torch.float32, device=w.device)
+    out = torch.zeros((4, cout, 4, C), dtype=acc, device=w.device)
     for a in (0, 1):
         for b in (0, 1):
             for u in (0, 1):

@@ -164,3 +164,53 @@ def test_bank_disk_format_roundtrip_and_reference_conversion(tmp_path):
         gbank.load_bank_rows(str(out), 10, n + 1, device="cpu")
     with pytest.raises(ValueError):
         gbank.save_prepared_bank(expect.float(), paths, str(out))
+
+
+def test_up2_phase_weights_reproduce_upsample_then_conv_on_cpu():
+    """The algebra behind ops.conv3x3_up2 (gillb200_gemm_args::conv_phase), checked on the CPU with plain torch: nearest 2x
+    upsample + 3x3 / pad 1 conv == four 2 x 2 convolutions of the LOW-RES tensor with the pre-summed phase weights, output
+    phase (a, b) reading low-res offsets (a - 1 + u, b - 1 + v)."""
+    import torch.nn.functional as F
+
+    from gill_b200 import ops
+
+    torch.manual_seed(0)
+    B, C, Co, H, W = 2, 5, 7, 6, 4
+    x = torch.randn(B, C, H, W, dtype=torch.float64)
+    w4 = torch.randn(Co, C, 3, 3, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w4, padding=1)
+    wk = w4.permute(0, 2, 3, 1).reshape(Co, 9 * C)                         # k = (ky*3+kx)*C + c, as sd._conv_w lays it out
+    wph = ops.conv3x3_up2_weights(wk)                                      # [4, Co, 4*C], k = (u*2+v)*C + c
+    assert wph.shape == (4, Co, 4 * C)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for a in (0, 1):
+        for b in (0, 1):
+            w2 = wph[a * 2 + b].view(Co, 2, 2, C).permute(0, 3, 1, 2)      # [Co, C, u, v]
+            out[:, :, a::2, b::2] = F.conv2d(xp[:, :, a:a + H + 1, b:b + W + 1], w2)
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_narrow_conv_tap_weights_reproduce_conv_on_cpu():
+    """The algebra behind ops.conv3x3_narrow: a 3x3 / pad 1 conv == one GEMM onto the nine per-tap products followed by the
+    nine-tap shifted sum of gillb200_tap_sum3x3 (restated here in torch)."""
+    import torch.nn.functional as F
+
+    from gill_b200 import ops
+
+    torch.manual_seed(1)
+    B, C, Co, H, W = 2, 6, 4, 5, 7
+    x = torch.randn(B, H, W, C, dtype=torch.float64)
+    w4 = torch.randn(Co, C, 3, 3, dtype=torch.float64)
+    wk = w4.permute(0, 2, 3, 1).reshape(Co, 9 * C)
+    wt = ops.conv3x3_taps_weight(wk, Co, pad_to=16)                        # [48, C], row tap*Co + o
+    assert wt.shape == (48, C) and (wt[9 * Co:] == 0).all()
+    y = (x.reshape(-1, C) @ wt.T).view(B, H, W, -1)                        # per-tap products at every pixel
+    out = torch.zeros(B, H, W, Co, dtype=torch.float64)
+    for dy in range(3):
+        for dx in range(3):
+            t = dy * 3 + dx
+            ys = F.pad(y[..., t * Co:(t + 1) * Co], (0, 0, 1, 1, 1, 1))    # zero outside the image
+            out += ys[:, dy:dy + H, dx:dx + W]
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w4, padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
