@@ -55,4 +55,18 @@ elif which == "topk1":
 elif which == "convwide":
     x = torch.randn(16, 64, 64, 320, device=dev).half(); w = torch.randn(320, 2880, device=dev).half() * 0.02; bias = torch.randn(320, device=dev)
     for _ in range(3): ops.conv3x3(x, w, bias=bias, block_n=320)
+elif which == "convgn":
+    # resnet conv1 of an up block: GroupNorm + SiLU of cat([h, skip]) applied inside the halo-tile conv
+    def produce(C):
+        a = torch.randn(16 * 64 * 64, 64, device=dev).half(); wt = (torch.randn(C, 64, device=dev) * 0.2).half()
+        o = ops.gemm(a, wt, stats=True); o4 = o.view(16, 64, 64, C); o4.gn_stats = o.gn_stats
+        return o4
+    x0, x1 = produce(320), produce(320)
+    w = torch.randn(320, 9 * 640, device=dev).half() * 0.02; bias = torch.randn(320, device=dev)
+    ss = ops.groupnorm_scale_shift(x0, torch.randn(640, device=dev), torch.randn(640, device=dev), 32, 1e-5, x2=x1)
+    for _ in range(3): ops.conv3x3(x0, w, bias=bias, gn=(ss, True), x2=x1, stats=True)
+elif which == "convup2":
+    x = torch.randn(16, 32, 32, 640, device=dev).half(); w = torch.randn(640, 9 * 640, device=dev).half() * 0.02
+    wph = ops.conv3x3_up2_weights(w); bias = torch.randn(640, device=dev)
+    for _ in range(2): ops.conv3x3_up2(x, wph, bias=bias, stats=True)
 torch.cuda.synchronize()
